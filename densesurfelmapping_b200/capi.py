@@ -1,0 +1,226 @@
+"""ctypes binding of the C ABI in include/dsm.h (the reference-facing boundary).
+
+`FusionFunctions` mirrors the reference class of the same name (fusion_functions.h:23-95): the
+same two public methods, same argument meaning.  It is a thin veneer: every call goes straight
+into libdsm_b200.so; there is no Python or CPU implementation behind it, and loading fails
+loudly when the library (or a B200) is missing.
+"""
+import ctypes
+import os
+import numpy as np
+
+from .elements import SEED_DTYPE, SURFEL_DTYPE, num_seeds
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdsm_b200.so")
+
+DSM_OK = 0
+ERRORS = {-1: "DSM_E_INVALID", -2: "DSM_E_SHAPE", -3: "DSM_E_NODEVICE", -4: "DSM_E_CUDA",
+          -5: "DSM_E_NOMEM", -6: "DSM_E_CAPACITY", -7: "DSM_E_STATE", -8: "DSM_E_NCCL"}
+NUM_KERNELS = 12
+
+# every symbol include/dsm.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "dsm_version", "dsm_strerror", "dsm_last_error", "dsm_create", "dsm_destroy", "dsm_num_seeds",
+    "dsm_fuse_frame", "dsm_batch_upload", "dsm_batch_run", "dsm_batch_download", "dsm_sync",
+    "dsm_fuse_batch", "dsm_batch_restore_pool", "dsm_get_labels", "dsm_get_seeds",
+    "dsm_debug_stop_after", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
+]
+
+
+class DsmParams(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float), ("cy", ctypes.c_float),
+                ("fuse_far", ctypes.c_float), ("fuse_near", ctypes.c_float),
+                ("max_batch", ctypes.c_int32), ("max_local_surfels", ctypes.c_int32)]
+
+
+class DsmError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__(f"{ERRORS.get(code, code)}: {detail}")
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libdsm_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built: run `python -m densesurfelmapping_b200.build` "
+                                "(or __graft_entry__.build()); this package has no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    L.dsm_version.restype = ci
+    L.dsm_strerror.restype = ctypes.c_char_p
+    L.dsm_strerror.argtypes = [ci]
+    L.dsm_last_error.restype = ctypes.c_char_p
+    L.dsm_last_error.argtypes = [vp]
+    L.dsm_kernel_name.restype = ctypes.c_char_p
+    L.dsm_kernel_name.argtypes = [ci]
+    L.dsm_create.argtypes = [ctypes.POINTER(DsmParams), ci, vp, ctypes.POINTER(vp)]
+    L.dsm_destroy.argtypes = [vp]
+    L.dsm_destroy.restype = None
+    L.dsm_num_seeds.argtypes = [vp]
+    L.dsm_fuse_frame.argtypes = [vp, ci, vp, cs, vp, cs, vp, vp, ci, vp, ci, ctypes.POINTER(ci)]
+    L.dsm_batch_upload.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
+    L.dsm_batch_run.argtypes = [vp]
+    L.dsm_batch_download.argtypes = [vp, vp, vp, vp]
+    L.dsm_sync.argtypes = [vp]
+    L.dsm_fuse_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dsm_batch_restore_pool.argtypes = [vp]
+    L.dsm_get_labels.argtypes = [vp, ci, vp]
+    L.dsm_get_seeds.argtypes = [vp, ci, vp]
+    L.dsm_debug_stop_after.argtypes = [vp, ci]
+    L.dsm_profile_enable.argtypes = [vp, ctypes.c_uint32]
+    L.dsm_profile_reset.argtypes = [vp]
+    L.dsm_profile_read.argtypes = [vp, vp, vp]
+    L.dsm_device_buffer.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cs)]
+    _lib = L
+    return L
+
+
+def kernel_names():
+    L = load_library()
+    return [L.dsm_kernel_name(i).decode() for i in range(NUM_KERNELS)]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """Owns one dsm_ctx (one per GPU)."""
+
+    def __init__(self, cam, max_batch=1, max_local_surfels=1 << 20, device=0, cuda_stream=None):
+        self.lib = load_library()
+        self.cam = cam
+        self.S = num_seeds(cam.width, cam.height)
+        self.max_batch = max_batch
+        p = DsmParams(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.far, cam.near,
+                      max_batch, max_local_surfels)
+        h = ctypes.c_void_p()
+        rc = self.lib.dsm_create(ctypes.byref(p), device, cuda_stream, ctypes.byref(h))
+        if rc != DSM_OK:
+            raise DsmError(rc, self.lib.dsm_strerror(rc).decode())
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != DSM_OK:
+            raise DsmError(rc, self.lib.dsm_last_error(self.h).decode() or self.lib.dsm_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dsm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference-identical single frame ----
+    def fuse_frame(self, ref_idx, gray, depth, pose, local):
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        pose = np.ascontiguousarray(pose, dtype=np.float32).reshape(16)
+        local = np.array(local, dtype=SURFEL_DTYPE, copy=True)
+        new = np.zeros(self.S, dtype=SURFEL_DTYPE)
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_fuse_frame(self.h, int(ref_idx), _ptr(gray), gray.strides[0], _ptr(depth), depth.strides[0],
+                                         _ptr(pose), _ptr(local) if len(local) else None, len(local),
+                                         _ptr(new), self.S, ctypes.byref(n)))
+        return local, new[:n.value].copy()
+
+    # ---- batch stages ----
+    def batch_upload(self, ref_idx, gray, depth, poses, local, offsets):
+        self._keep = (np.ascontiguousarray(ref_idx, dtype=np.int32), np.ascontiguousarray(gray, dtype=np.uint8),
+                      np.ascontiguousarray(depth, dtype=np.float32), np.ascontiguousarray(poses, dtype=np.float32),
+                      np.ascontiguousarray(local, dtype=SURFEL_DTYPE), np.ascontiguousarray(offsets, dtype=np.int32))
+        r, g, d, p, l, o = self._keep
+        n = len(r)
+        assert g.shape == (n, self.cam.height, self.cam.width) and d.shape == g.shape and len(o) == n + 1
+        self.nb = n
+        self.n_pool = int(o[-1])
+        self._ck(self.lib.dsm_batch_upload(self.h, n, _ptr(r), _ptr(g), _ptr(d), _ptr(p), _ptr(l) if len(l) else None, _ptr(o)))
+
+    def batch_run(self):
+        self._ck(self.lib.dsm_batch_run(self.h))
+
+    def batch_restore_pool(self):
+        self._ck(self.lib.dsm_batch_restore_pool(self.h))
+
+    def sync(self):
+        self._ck(self.lib.dsm_sync(self.h))
+
+    def batch_download(self):
+        local = np.zeros(self.n_pool, dtype=SURFEL_DTYPE)
+        new = np.zeros((self.nb, self.S), dtype=SURFEL_DTYPE)
+        cnt = np.zeros(self.nb, dtype=np.int32)
+        self._ck(self.lib.dsm_batch_download(self.h, _ptr(local) if self.n_pool else None, _ptr(new), _ptr(cnt)))
+        self.sync()
+        return local, [new[b, :cnt[b]].copy() for b in range(self.nb)]
+
+    def fuse_batch(self, ref_idx, gray, depth, poses, local, offsets):
+        self.batch_upload(ref_idx, gray, depth, poses, local, offsets)
+        self.batch_run()
+        return self.batch_download()
+
+    # ---- parity readback ----
+    def labels(self, frame=0):
+        out = np.empty((self.cam.height, self.cam.width), dtype=np.int32)
+        self._ck(self.lib.dsm_get_labels(self.h, frame, _ptr(out)))
+        return out
+
+    def seeds(self, frame=0):
+        out = np.zeros(self.S, dtype=SEED_DTYPE)
+        self._ck(self.lib.dsm_get_seeds(self.h, frame, _ptr(out)))
+        return out
+
+    def debug_stop_after(self, n):
+        self._ck(self.lib.dsm_debug_stop_after(self.h, int(n)))
+
+    # ---- measurement ----
+    def profile_enable(self, mask):
+        self._ck(self.lib.dsm_profile_enable(self.h, mask))
+
+    def profile_reset(self):
+        self._ck(self.lib.dsm_profile_reset(self.h))
+
+    def profile_read(self):
+        ms = np.zeros(NUM_KERNELS, dtype=np.float32)
+        n = np.zeros(NUM_KERNELS, dtype=np.int32)
+        self._ck(self.lib.dsm_profile_read(self.h, _ptr(ms), _ptr(n)))
+        return ms, n
+
+    def device_buffer(self, which):
+        p = ctypes.c_void_p()
+        sz = ctypes.c_size_t()
+        self._ck(self.lib.dsm_device_buffer(self.h, which, ctypes.byref(p), ctypes.byref(sz)))
+        return p.value, sz.value
+
+
+class FusionFunctions:
+    """Python mirror of the reference's `class FusionFunctions` public surface
+    (fusion_functions.h:84-94): initialize(...) then fuse_initialize_map(...)."""
+
+    def __init__(self, device=0, max_local_surfels=1 << 20):
+        self._device = device
+        self._cap = max_local_surfels
+        self._ctx = None
+
+    def initialize(self, width, height, fx, fy, cx, cy, fuse_far, fuse_near):
+        from .synth import Camera
+        self._ctx = Context(Camera(width, height, fx, fy, cx, cy, fuse_near, fuse_far),
+                            max_batch=1, max_local_surfels=self._cap, device=self._device)
+
+    def fuse_initialize_map(self, reference_frame_index, image, depth, pose, local_surfels):
+        """Returns (local_surfels_updated, new_surfels) — the reference mutates the first in place
+        and clears+fills the second (fusion_functions.cpp:30-83)."""
+        if self._ctx is None:
+            raise RuntimeError("initialize() has not been called")
+        return self._ctx.fuse_frame(reference_frame_index, image, depth, pose, local_surfels)

@@ -1,0 +1,584 @@
+// Host side of the C ABI declared in include/dsm.h: context, HBM allocation, the per-frame
+// kernel schedule (mirrors FusionFunctions::fuse_initialize_map / generate_super_pixels,
+// fusion_functions.cpp:30-83, :960-975) and the copies either side of it.
+// No CPU implementation of any phase lives here: if CUDA is unavailable every call fails.
+#include "dsm_device.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+struct ProfRec
+{
+    int id;
+    cudaEvent_t e0, e1;
+};
+
+struct dsm_ctx
+{
+    dsm_params p;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    DsmDev d;
+    int S, Wp;
+    size_t px;    // pitched pixels per frame
+    int nb;       // frames in the current batch
+    int n_pool;   // local surfels in the current batch
+    bool uploaded, ran;
+    int stop_after; // debug: number of kernels to enqueue (<= 0: all)
+    // raw allocations (non-const views of what DsmDev holds)
+    uint8_t *gray;
+    float *depth;
+    dsm_surfel_t *pool_snap;
+    int32_t *poolofs, *refidx;
+    float *pose, *ipose;
+    dsm_seed_t *seed_export;
+    // pinned host staging for the small per-batch tables
+    float *h_pose; // [B][32]: pose then inverse
+    int32_t *h_ofs;
+    int32_t *h_ref;
+    // profiling
+    uint32_t prof_mask;
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> ev_free;
+    float prof_ms[DSM_NUM_KERNELS];
+    int32_t prof_n[DSM_NUM_KERNELS];
+    char err[512];
+};
+
+static const char *kKernelNames[DSM_NUM_KERNELS] = {
+    "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_update", "seed_commit",
+    "normals_plane_fit", "surfel_fuse", "surfel_init", "seeds_export", "reserved0", "reserved1"};
+
+#define CK(call)                                                                                         \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+        {                                                                                                \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return DSM_E_CUDA;                                                                           \
+        }                                                                                                \
+    } while (0)
+
+extern "C" int dsm_version(void) { return DSM_VERSION; }
+
+extern "C" const char *dsm_strerror(int code)
+{
+    switch (code)
+    {
+    case DSM_OK: return "ok";
+    case DSM_E_INVALID: return "invalid argument";
+    case DSM_E_SHAPE: return "unsupported image shape (W%8 or H%8 > 4, or smaller than 24x24 / fewer than 10 seeds)";
+    case DSM_E_NODEVICE: return "no usable CUDA device (sm_100 required)";
+    case DSM_E_CUDA: return "CUDA error";
+    case DSM_E_NOMEM: return "out of memory";
+    case DSM_E_CAPACITY: return "surfel capacity exceeded";
+    case DSM_E_STATE: return "invalid call sequence";
+    case DSM_E_NCCL: return "NCCL error";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *dsm_last_error(const dsm_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" const char *dsm_kernel_name(int id) { return (id >= 0 && id < DSM_NUM_KERNELS) ? kKernelNames[id] : "?"; }
+extern "C" int dsm_num_seeds(const dsm_ctx *ctx) { return ctx ? ctx->S : DSM_E_INVALID; }
+
+template <typename T>
+static cudaError_t dmalloc(T **p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+extern "C" void dsm_destroy(dsm_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->prof_pending)
+    {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    for (auto &e : ctx->ev_free) cudaEventDestroy(e);
+    DsmDev &d = ctx->d;
+    cudaFree(ctx->gray);
+    cudaFree(ctx->depth);
+    cudaFree(d.labels);
+    cudaFree(d.seed);
+    cudaFree(d.inv_md);
+    cudaFree(d.tstable);
+    cudaFree(d.cand);
+    cudaFree(d.cflag);
+    cudaFree(d.abortc);
+    cudaFree(d.plane);
+    cudaFree(d.fused);
+    cudaFree(d.list);
+    cudaFree(d.nlist);
+    cudaFree(d.pool);
+    cudaFree(ctx->pool_snap);
+    cudaFree(ctx->poolofs);
+    cudaFree(d.newsurf);
+    cudaFree(d.nnew);
+    cudaFree(ctx->pose);
+    cudaFree(ctx->ipose);
+    cudaFree(ctx->refidx);
+    cudaFree(ctx->seed_export);
+    cudaFreeHost(ctx->h_pose);
+    cudaFreeHost(ctx->h_ofs);
+    cudaFreeHost(ctx->h_ref);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_stream, dsm_ctx **out)
+{
+    if (!params || !out) return DSM_E_INVALID;
+    *out = nullptr;
+    const int W = params->width, H = params->height;
+    if (params->max_batch < 1 || params->max_local_surfels < 0) return DSM_E_INVALID;
+    if (W < 3 * DSM_SP || H < 3 * DSM_SP || W % DSM_SP > 4 || H % DSM_SP > 4) return DSM_E_SHAPE;
+    if ((W / DSM_SP) * (H / DSM_SP) < DSM_THREAD_NUM) return DSM_E_SHAPE;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DSM_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DSM_E_NODEVICE;
+    if (prop.major != 10) return DSM_E_NODEVICE; // the only code in this library is sm_100a SASS
+    if (cudaSetDevice(device) != cudaSuccess) return DSM_E_NODEVICE;
+
+    dsm_ctx *ctx = new (std::nothrow) dsm_ctx();
+    if (!ctx) return DSM_E_NOMEM;
+    memset(&ctx->d, 0, sizeof(ctx->d));
+    ctx->p = *params;
+    ctx->device = device;
+    ctx->err[0] = 0;
+    ctx->prof_mask = 0;
+    memset(ctx->prof_ms, 0, sizeof(ctx->prof_ms));
+    memset(ctx->prof_n, 0, sizeof(ctx->prof_n));
+    ctx->nb = 0;
+    ctx->n_pool = 0;
+    ctx->uploaded = ctx->ran = false;
+    ctx->stop_after = 0;
+    ctx->own_stream = (cuda_stream == nullptr);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    if (ctx->own_stream && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        delete ctx;
+        return DSM_E_CUDA;
+    }
+    const int B = params->max_batch;
+    const int Wp = (W + 15) / 16 * 16;
+    const int spw = W / DSM_SP, sph = H / DSM_SP, S = spw * sph;
+    const size_t px = (size_t)H * Wp;
+    ctx->S = S;
+    ctx->Wp = Wp;
+    ctx->px = px;
+    DsmDev &d = ctx->d;
+    d.W = W, d.H = H, d.Wp = Wp, d.spw = spw, d.sph = sph, d.S = S, d.B = B;
+    d.fx = params->fx, d.fy = params->fy, d.cx = params->cx, d.cy = params->cy;
+    d.fuse_far = params->fuse_far, d.fuse_near = params->fuse_near;
+    d.camera_f = (float)((fabs((double)params->fx) + fabs((double)params->fy)) / 2.0); // (:250)
+    d.px_stride = px;
+    const size_t npool = (size_t)(params->max_local_surfels > 0 ? params->max_local_surfels : 1);
+    cudaError_t e = cudaSuccess;
+    // +64 bytes/elements of slack so the 16-byte vector accesses on the last pitched row stay in bounds
+#define ALLOC(ptr, n)                        \
+    if (e == cudaSuccess) e = dmalloc(&(ptr), (size_t)(n))
+    ALLOC(ctx->gray, B * px + 64);
+    ALLOC(ctx->depth, B * px + 64);
+    ALLOC(d.labels, B * px + 64);
+    ALLOC(d.seed, (size_t)B * S);
+    ALLOC(d.inv_md, (size_t)B * S);
+    ALLOC(d.tstable, (size_t)B * S);
+    ALLOC(d.cand, (size_t)B * S);
+    ALLOC(d.cflag, (size_t)B * S);
+    ALLOC(d.abortc, (size_t)B * 16);
+    ALLOC(d.plane, (size_t)B * S * 3);
+    ALLOC(d.fused, (size_t)B * S);
+    ALLOC(d.list, B * px);
+    ALLOC(d.nlist, (size_t)B);
+    ALLOC(d.pool, npool);
+    ALLOC(ctx->pool_snap, npool);
+    ALLOC(ctx->poolofs, (size_t)B + 1);
+    ALLOC(d.newsurf, (size_t)B * S);
+    ALLOC(d.nnew, (size_t)B);
+    ALLOC(ctx->pose, (size_t)B * 16);
+    ALLOC(ctx->ipose, (size_t)B * 16);
+    ALLOC(ctx->refidx, (size_t)B);
+    ALLOC(ctx->seed_export, (size_t)S);
+#undef ALLOC
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_pose, (size_t)B * 32 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ofs, ((size_t)B + 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ref, (size_t)B * sizeof(int32_t));
+    if (e != cudaSuccess)
+    {
+        dsm_destroy(ctx);
+        return e == cudaErrorMemoryAllocation ? DSM_E_NOMEM : DSM_E_CUDA;
+    }
+    d.gray = ctx->gray;
+    d.depth = ctx->depth;
+    d.poolofs = ctx->poolofs;
+    d.pose = ctx->pose;
+    d.ipose = ctx->ipose;
+    d.refidx = ctx->refidx;
+    d.max_pool_per_frame = 0;
+    *out = ctx;
+    return DSM_OK;
+}
+
+// general 4x4 float inverse (adjugate / determinant) of a column-major matrix: stands in for
+// Eigen's `pose.inverse()` (fusion_functions.cpp:59); same formula as the oracle's Eigen stand-in.
+static void inverse4f(const float *m, float *out)
+{
+    float inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    float inv_det = 1.0f / det;
+    for (int i = 0; i < 16; i++) out[i] = inv[i] * inv_det;
+}
+
+// ---- profiling helpers ----
+static cudaEvent_t prof_event(dsm_ctx *ctx)
+{
+    if (!ctx->ev_free.empty())
+    {
+        cudaEvent_t e = ctx->ev_free.back();
+        ctx->ev_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope
+{
+    dsm_ctx *ctx;
+    int id;
+    cudaEvent_t e0, e1;
+    bool on;
+    ProfScope(dsm_ctx *c, int k) : ctx(c), id(k), on((c->prof_mask >> k) & 1u)
+    {
+        if (on)
+        {
+            e0 = prof_event(ctx);
+            e1 = prof_event(ctx);
+            cudaEventRecord(e0, ctx->stream);
+        }
+    }
+    ~ProfScope()
+    {
+        if (on)
+        {
+            cudaEventRecord(e1, ctx->stream);
+            ctx->prof_pending.push_back(ProfRec{id, e0, e1});
+        }
+    }
+};
+
+extern "C" int dsm_profile_enable(dsm_ctx *ctx, uint32_t mask)
+{
+    if (!ctx) return DSM_E_INVALID;
+    ctx->prof_mask = mask;
+    return DSM_OK;
+}
+static int prof_drain(dsm_ctx *ctx, bool accumulate)
+{
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof_pending)
+    {
+        if (accumulate)
+        {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+            ctx->prof_ms[r.id] += ms;
+            ctx->prof_n[r.id] += 1;
+        }
+        ctx->ev_free.push_back(r.e0);
+        ctx->ev_free.push_back(r.e1);
+    }
+    ctx->prof_pending.clear();
+    return DSM_OK;
+}
+extern "C" int dsm_profile_reset(dsm_ctx *ctx)
+{
+    if (!ctx) return DSM_E_INVALID;
+    int rc = prof_drain(ctx, false);
+    memset(ctx->prof_ms, 0, sizeof(ctx->prof_ms));
+    memset(ctx->prof_n, 0, sizeof(ctx->prof_n));
+    return rc;
+}
+extern "C" int dsm_profile_read(dsm_ctx *ctx, float *ms_total, int32_t *launches)
+{
+    if (!ctx || !ms_total || !launches) return DSM_E_INVALID;
+    int rc = prof_drain(ctx, true);
+    if (rc != DSM_OK) return rc;
+    memcpy(ms_total, ctx->prof_ms, sizeof(ctx->prof_ms));
+    memcpy(launches, ctx->prof_n, sizeof(ctx->prof_n));
+    return DSM_OK;
+}
+
+// ---- batch stages ----
+static int upload_tables(dsm_ctx *ctx, int n, const int32_t *ref, const float *poses, const int32_t *ofs, int n_local_single)
+{
+    int total = 0, maxper = 0;
+    for (int b = 0; b < n; b++)
+    {
+        memcpy(ctx->h_pose + (size_t)b * 32, poses + (size_t)b * 16, 16 * sizeof(float));
+        inverse4f(poses + (size_t)b * 16, ctx->h_pose + (size_t)b * 32 + 16);
+        ctx->h_ref[b] = ref[b];
+    }
+    if (ofs)
+    {
+        if (ofs[0] != 0) return DSM_E_INVALID;
+        for (int b = 0; b <= n; b++) ctx->h_ofs[b] = ofs[b];
+        for (int b = 0; b < n; b++)
+        {
+            int c = ofs[b + 1] - ofs[b];
+            if (c < 0) return DSM_E_INVALID;
+            if (c > maxper) maxper = c;
+        }
+        total = ofs[n];
+    }
+    else
+    {
+        ctx->h_ofs[0] = 0;
+        for (int b = 1; b <= n; b++) ctx->h_ofs[b] = n_local_single;
+        total = maxper = n_local_single;
+    }
+    if (total > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
+    ctx->n_pool = total;
+    ctx->d.max_pool_per_frame = maxper;
+    // pose and inverse interleaved on the host: two strided copies
+    CK(cudaMemcpy2DAsync(ctx->pose, 16 * sizeof(float), ctx->h_pose, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->ipose, 16 * sizeof(float), ctx->h_pose + 16, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->poolofs, ctx->h_ofs, ((size_t)n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->refidx, ctx->h_ref, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    return DSM_OK;
+}
+
+extern "C" int dsm_batch_upload(dsm_ctx *ctx, int n, const int32_t *ref, const uint8_t *gray, const float *depth,
+                                const float *poses, const dsm_surfel_t *local, const int32_t *ofs)
+{
+    if (!ctx || !ref || !gray || !depth || !poses || !ofs) return DSM_E_INVALID;
+    if (n < 1 || n > ctx->p.max_batch) return DSM_E_INVALID;
+    if (ofs[n] > 0 && !local) return DSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    // the pinned tables are reused: make sure the previous batch's copies have drained
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = upload_tables(ctx, n, ref, poses, ofs, 0);
+    if (rc != DSM_OK) return rc;
+    const int W = ctx->p.width, H = ctx->p.height;
+    // [n][H][W] packed -> [n][H][Wp] pitched, one strided copy each
+    CK(cudaMemcpy2DAsync(ctx->gray, ctx->Wp, gray, W, W, (size_t)n * H, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->depth, (size_t)ctx->Wp * 4, depth, (size_t)W * 4, (size_t)W * 4, (size_t)n * H, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_pool > 0)
+    {
+        CK(cudaMemcpyAsync(ctx->d.pool, local, (size_t)ctx->n_pool * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->pool_snap, ctx->d.pool, (size_t)ctx->n_pool * sizeof(dsm_surfel_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->nb = n;
+    ctx->uploaded = true;
+    ctx->ran = false;
+    return DSM_OK;
+}
+
+extern "C" int dsm_batch_restore_pool(dsm_ctx *ctx)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (!ctx->uploaded) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_pool > 0)
+        CK(cudaMemcpyAsync(ctx->d.pool, ctx->pool_snap, (size_t)ctx->n_pool * sizeof(dsm_surfel_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return DSM_OK;
+}
+
+// The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79).
+extern "C" int dsm_batch_run(dsm_ctx *ctx)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (!ctx->uploaded) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    const DsmDev &d = ctx->d;
+    const int nb = ctx->nb;
+    cudaStream_t st = ctx->stream;
+    int budget = ctx->stop_after > 0 ? ctx->stop_after : 1 << 30;
+#define STEP(ID, CALL)                  \
+    if (budget-- > 0)                   \
+    {                                   \
+        ProfScope p(ctx, ID);           \
+        CALL;                           \
+    }
+    STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
+    for (int it = 0; it < 3; it++) // ITERATION_NUM (fusion_functions.h:8)
+    {
+        if (it == 0)
+        {
+            STEP(DSM_K_ASSIGN_FIRST, dsm_launch_assign(d, nb, true, st));
+        }
+        else
+        {
+            STEP(DSM_K_ASSIGN, dsm_launch_assign(d, nb, false, st));
+            STEP(DSM_K_RELAX, dsm_launch_relax(d, nb, st));
+        }
+        STEP(DSM_K_UPDATE_SEEDS, dsm_launch_update_seeds(d, nb, st));
+        STEP(DSM_K_COMMIT_SEEDS, dsm_launch_commit_seeds(d, nb, st));
+    }
+    STEP(DSM_K_PLANE_FIT, dsm_launch_plane_fit(d, nb, st));
+    if (d.max_pool_per_frame > 0)
+    {
+        STEP(DSM_K_FUSE, dsm_launch_fuse(d, nb, st));
+    }
+    STEP(DSM_K_INIT_SURFELS, dsm_launch_init_surfels(d, nb, st));
+#undef STEP
+    CK(cudaGetLastError());
+    ctx->ran = true;
+    return DSM_OK;
+}
+
+extern "C" int dsm_debug_stop_after(dsm_ctx *ctx, int n)
+{
+    if (!ctx) return DSM_E_INVALID;
+    ctx->stop_after = n;
+    return DSM_OK;
+}
+
+extern "C" int dsm_batch_download(dsm_ctx *ctx, dsm_surfel_t *local_out, dsm_surfel_t *new_out, int32_t *n_new)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (!ctx->ran) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    if (local_out && ctx->n_pool > 0)
+        CK(cudaMemcpyAsync(local_out, ctx->d.pool, (size_t)ctx->n_pool * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (new_out)
+        CK(cudaMemcpyAsync(new_out, ctx->d.newsurf, (size_t)ctx->nb * ctx->S * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_new)
+        CK(cudaMemcpyAsync(n_new, ctx->d.nnew, (size_t)ctx->nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return DSM_OK;
+}
+
+extern "C" int dsm_sync(dsm_ctx *ctx)
+{
+    if (!ctx) return DSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uint8_t *gray, const float *depth,
+                              const float *poses, dsm_surfel_t *local, const int32_t *ofs,
+                              dsm_surfel_t *new_out, int32_t *n_new)
+{
+    int rc = dsm_batch_upload(ctx, n, ref, gray, depth, poses, local, ofs);
+    if (rc != DSM_OK) return rc;
+    rc = dsm_batch_run(ctx);
+    if (rc != DSM_OK) return rc;
+    rc = dsm_batch_download(ctx, local, new_out, n_new);
+    if (rc != DSM_OK) return rc;
+    return dsm_sync(ctx);
+}
+
+extern "C" int dsm_fuse_frame(dsm_ctx *ctx, int ref_idx, const uint8_t *gray, size_t gray_pitch,
+                              const float *depth, size_t depth_pitch, const float pose[16],
+                              dsm_surfel_t *local, int n_local, dsm_surfel_t *new_out, int new_cap, int *n_new)
+{
+    if (!ctx || !gray || !depth || !pose || n_local < 0 || new_cap < 0 || !n_new) return DSM_E_INVALID;
+    if (n_local > 0 && !local) return DSM_E_INVALID;
+    if (new_cap > 0 && !new_out) return DSM_E_INVALID;
+    const int W = ctx->p.width, H = ctx->p.height;
+    if (gray_pitch < (size_t)W || depth_pitch < (size_t)W * 4) return DSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int32_t ref = ref_idx;
+    int rc = upload_tables(ctx, 1, &ref, pose, nullptr, n_local);
+    if (rc != DSM_OK) return rc;
+    CK(cudaMemcpy2DAsync(ctx->gray, ctx->Wp, gray, gray_pitch, W, H, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->depth, (size_t)ctx->Wp * 4, depth, depth_pitch, (size_t)W * 4, H, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_local > 0)
+        CK(cudaMemcpyAsync(ctx->d.pool, local, (size_t)n_local * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->nb = 1;
+    ctx->uploaded = true;
+    rc = dsm_batch_run(ctx);
+    if (rc != DSM_OK) return rc;
+    if (n_local > 0)
+        CK(cudaMemcpyAsync(local, ctx->d.pool, (size_t)n_local * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, ctx->d.nnew, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_new = cnt;
+    const int ncopy = cnt < new_cap ? cnt : new_cap;
+    if (ncopy > 0)
+    {
+        CK(cudaMemcpyAsync(new_out, ctx->d.newsurf, (size_t)ncopy * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+// ---- parity / debug readback ----
+extern "C" int dsm_get_labels(dsm_ctx *ctx, int frame, int32_t *labels_hw)
+{
+    if (!ctx || !labels_hw || frame < 0 || frame >= ctx->p.max_batch) return DSM_E_INVALID;
+    if (!ctx->ran) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->p.width, H = ctx->p.height;
+    CK(cudaMemcpy2DAsync(labels_hw, (size_t)W * 4, ctx->d.labels + (size_t)frame * ctx->px, (size_t)ctx->Wp * 4,
+                         (size_t)W * 4, H, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSM_OK;
+}
+
+extern "C" int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds)
+{
+    if (!ctx || !seeds || frame < 0 || frame >= ctx->p.max_batch) return DSM_E_INVALID;
+    if (!ctx->ran) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < 13) ? 1 : 0, ctx->stream);
+    CK(cudaMemcpyAsync(seeds, ctx->seed_export, (size_t)ctx->S * sizeof(dsm_seed_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+extern "C" int dsm_device_buffer(dsm_ctx *ctx, int which, void **dev_ptr, size_t *bytes)
+{
+    if (!ctx || !dev_ptr || !bytes) return DSM_E_INVALID;
+    switch (which)
+    {
+    case DSM_BUF_NEW_SURFELS:
+        *dev_ptr = ctx->d.newsurf;
+        *bytes = (size_t)ctx->p.max_batch * ctx->S * sizeof(dsm_surfel_t);
+        return DSM_OK;
+    case DSM_BUF_NEW_COUNTS:
+        *dev_ptr = ctx->d.nnew;
+        *bytes = (size_t)ctx->p.max_batch * sizeof(int32_t);
+        return DSM_OK;
+    case DSM_BUF_LOCAL:
+        *dev_ptr = ctx->d.pool;
+        *bytes = (size_t)(ctx->p.max_local_surfels > 0 ? ctx->p.max_local_surfels : 1) * sizeof(dsm_surfel_t);
+        return DSM_OK;
+    default:
+        return DSM_E_INVALID;
+    }
+}

@@ -1,0 +1,87 @@
+// Device-side data layout shared by the kernels (dsm_kernels.cu) and the host driver (dsm_capi.cu).
+//
+// HBM layout per context (B = max_batch frames, P = H*Wp pitched pixels, S = seeds per frame):
+//   gray    u8  [B][H][Wp]      Wp = W rounded up to 16 so every row starts 16-byte aligned
+//   depth   f32 [B][H][Wp]      (vector loads, 1-D bulk copies)
+//   labels  i32 [B][H][Wp]      superpixel_index of the reference (fusion_functions.h:37)
+//   seed    float4 [B][S]       (x, y, mean_intensity, mean_depth)  -- the clustering state
+//   inv_md  f64 [B][S]          1.0 / mean_depth, hoisted out of calculate_cost (:380)
+//   tstable i32 [B][S]          stable flag + raster time stamp: INT_MAX = stable,
+//                               -1 = unstable, k >= 0 = un-stabled when raster scan reached k
+//   cand    float4 [B][S]       update_seeds results before the chunk-abort commit (H3)
+//   cflag   i32 [B][S]          bit0 new-stable, bit1 processed
+//   abortc  i32 [B][16]         per 10-way chunk: first seed index that hit `return` (:516)
+//   plane   float4 [B][S][3]    (n.xyz, view_cos) (posi.xyz, mean_depth) (size, I, x, y)
+//   fused   i32 [B][S]          Superpixel_seed::fused
+//   list    int2 [B][P]         pixels owned by stable seeds: (pitched raster index, winner)
+//   nlist   i32 [B]
+//   pool    dsm_surfel_t [max_local]   AoS, ABI layout (44 B) so upload/download are plain copies
+//   poolofs i32 [B+1]
+//   newsurf dsm_surfel_t [B][S], nnew i32 [B]
+//   pose/ipose f32 [B][16] column-major, refidx i32 [B]
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/dsm.h"
+
+#define DSM_SP 8
+#define DSM_THREAD_NUM 10 // the reference's static 10-way partition (fusion_functions.h:9), needed for H3
+#define DSM_STABLE 0x7fffffff
+
+struct DsmDev
+{
+    // geometry
+    int W, H, Wp, spw, sph, S, B;
+    float fx, fy, cx, cy, fuse_far, fuse_near, camera_f;
+    // per-frame strides in elements
+    size_t px_stride; // H*Wp
+    // buffers
+    const uint8_t *gray;
+    const float *depth;
+    int32_t *labels;
+    float4 *seed;
+    double *inv_md;
+    int32_t *tstable;
+    float4 *cand;
+    int32_t *cflag;
+    int32_t *abortc;
+    float4 *plane;
+    int32_t *fused;
+    int2 *list;
+    int32_t *nlist;
+    dsm_surfel_t *pool;
+    const int32_t *poolofs;
+    dsm_surfel_t *newsurf;
+    int32_t *nnew;
+    const float *pose;
+    const float *ipose;
+    const int32_t *refidx;
+    int max_pool_per_frame; // largest per-frame pool slice in this batch (grid sizing)
+};
+
+enum DsmKernelId
+{
+    DSM_K_SEED_INIT = 0,
+    DSM_K_ASSIGN_FIRST = 1,
+    DSM_K_ASSIGN = 2,
+    DSM_K_RELAX = 3,
+    DSM_K_UPDATE_SEEDS = 4,
+    DSM_K_COMMIT_SEEDS = 5,
+    DSM_K_PLANE_FIT = 6,
+    DSM_K_FUSE = 7,
+    DSM_K_INIT_SURFELS = 8,
+    DSM_K_SEEDS_EXPORT = 9,
+    DSM_K_RESERVED0 = 10,
+    DSM_K_RESERVED1 = 11,
+};
+
+// launchers (dsm_kernels.cu); nb = frames in this batch
+void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s);
+void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_update_seeds(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_commit_seeds(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_plane_fit(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, int raw_md, cudaStream_t s);

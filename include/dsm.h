@@ -1,0 +1,170 @@
+/*
+ * dsm.h — C ABI of the B200-native DenseSurfelMapping per-frame hot path.
+ *
+ * Drop-in boundary: this library replaces exactly one call site of the reference,
+ *
+ *     SurfelMap::fuse_map -> fusion_functions.fuse_initialize_map(...)   surfel_map.cpp:1066-1073
+ *     SurfelMap::SurfelMap -> fusion_functions.initialize(...)            surfel_map.cpp:53
+ *
+ * i.e. the public surface of `class FusionFunctions` (fusion_functions.h:84-94).  Everything
+ * behind it (superpixel extraction, back-projection + normals, robust per-superpixel plane
+ * fit, surfel associate / weighted-fuse / initialise; fusion_functions.cpp:30-975) runs as
+ * hand-written sm_100a CUDA kernels.  There is NO CPU fallback: every entry point returns
+ * DSM_E_CUDA / DSM_E_NODEVICE when no B200-class device is usable.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int return (0 = DSM_OK, negative = error),
+ * no exceptions cross the boundary, one context per GPU, calls on one context are serialised
+ * by the caller (the reference is single-threaded at this call site too: ros_node.cpp:38-41).
+ * Element layouts are byte-identical to the reference PODs (elements.h:5-31).
+ *
+ * INTEGRATION.md shows the reference-side binding (a FusionFunctions-compatible C++ adapter,
+ * include/dsm_fusion_functions.hpp, plus the ctypes stub used by the tests).
+ */
+#ifndef DSM_H
+#define DSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSM_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes ---- */
+#define DSM_OK 0
+#define DSM_E_INVALID (-1)   /* bad argument (null pointer, negative count, batch too large ...) */
+#define DSM_E_SHAPE (-2)     /* unsupported image shape: W%8 > 4 or H%8 > 4 (reference UB, fusion_functions.cpp:408-451) */
+#define DSM_E_NODEVICE (-3)  /* no CUDA device / device is not sm_100 */
+#define DSM_E_CUDA (-4)      /* a CUDA runtime call or kernel failed; see dsm_last_error() */
+#define DSM_E_NOMEM (-5)     /* device or host allocation failed */
+#define DSM_E_CAPACITY (-6)  /* more surfels than the context was created for */
+#define DSM_E_STATE (-7)     /* call sequence error (e.g. download before run) */
+#define DSM_E_NCCL (-8)      /* NCCL unavailable or a collective failed */
+
+/* ---- element types: byte-identical to the reference ---- */
+
+/* reference: elements.h:22-31 `struct SurfelElement` (44 bytes) */
+typedef struct dsm_surfel_t
+{
+    float px, py, pz;   /* world position */
+    float nx, ny, nz;   /* world normal */
+    float size;         /* radius, metres */
+    float color;        /* gray 0..255 stored as float */
+    float weight;
+    int32_t update_times; /* 0 == dead */
+    int32_t last_update;  /* reference KEYFRAME index of the last fuse (surfel_map.cpp:145,161) */
+} dsm_surfel_t;
+
+/* reference: elements.h:5-20 `struct Superpixel_seed` (60 bytes) — parity/debug readback only */
+typedef struct dsm_seed_t
+{
+    float x, y;
+    float size;
+    float norm_x, norm_y, norm_z;
+    float posi_x, posi_y, posi_z;
+    float view_cos;
+    float mean_depth;
+    float mean_intensity;
+    uint8_t fused;
+    uint8_t stable;
+    uint8_t _pad[2];
+    float min_eigen_value; /* debug fields of the reference; always 0 here */
+    float max_eigen_value;
+} dsm_seed_t;
+
+/* ---- context parameters ---- */
+/* The first eight fields are the arguments of FusionFunctions::initialize
+ * (fusion_functions.h:84-87, fusion_functions.cpp:7-28).  The rest size the GPU-resident
+ * buffers.  The algorithm constants are the reference's "drive" set
+ * (fusion_functions.h:7-16: SP_SIZE 8, ITERATION_NUM 3, HUBER_RANGE 0.4, BASELINE 0.5,
+ * DISPARITY_ERROR 4.0, MIN_TOLERATE_DIFF 0.1, MAX_ANGLE_COS 0.1) compiled into the kernels. */
+typedef struct dsm_params
+{
+    int32_t width, height;
+    float fx, fy, cx, cy;
+    float fuse_far, fuse_near;
+    int32_t max_batch;         /* frames processed per dsm_batch_* call (>= 1) */
+    int32_t max_local_surfels; /* capacity of the local-surfel pool, summed over the batch */
+} dsm_params;
+
+typedef struct dsm_ctx dsm_ctx;
+
+/* ---- lifetime ---- */
+int dsm_version(void);
+const char *dsm_strerror(int code);
+/* last CUDA/NCCL error text recorded on this context (never NULL) */
+const char *dsm_last_error(const dsm_ctx *ctx);
+
+/* Replaces FusionFunctions::initialize (fusion_functions.cpp:7-28).  `device` is the CUDA
+ * ordinal.  `cuda_stream` may be NULL (the context creates its own non-blocking stream) or a
+ * cudaStream_t owned by the caller on which all work of this context is enqueued. */
+int dsm_create(const dsm_params *params, int device, void *cuda_stream, dsm_ctx **out);
+void dsm_destroy(dsm_ctx *ctx);
+int dsm_num_seeds(const dsm_ctx *ctx); /* S = (W/8)*(H/8) */
+
+/* ---- reference-identical single-frame call ----
+ * Replaces FusionFunctions::fuse_initialize_map (fusion_functions.cpp:30-83) with the same
+ * semantics: `gray` is CV_8UC1 (row pitch gray_pitch bytes), `depth` CV_32FC1 metres (row
+ * pitch depth_pitch bytes), `pose_colmajor` = Eigen::Matrix4f T_world<-cam memory order,
+ * `local[n_local]` is updated IN PLACE and never resized (dead surfels are flagged
+ * update_times == 0, the caller compacts: surfel_map.cpp:1077-1109), `new_out` receives the
+ * newly initialised surfels in seed-index order (the reference clears and push_backs,
+ * fusion_functions.cpp:320,359); at most new_cap are written, *n_new is the full count.
+ * Host pointers; uploads, runs all kernels, downloads, synchronises. */
+int dsm_fuse_frame(dsm_ctx *ctx, int reference_frame_index,
+                   const uint8_t *gray, size_t gray_pitch,
+                   const float *depth, size_t depth_pitch,
+                   const float pose_colmajor[16],
+                   dsm_surfel_t *local, int n_local,
+                   dsm_surfel_t *new_out, int new_cap, int *n_new);
+
+/* ---- batch of independent frames (BASELINE configs 3/4) ----
+ * Frame b has its own image pair, pose, reference index and its own slice of the local pool:
+ * local[local_offsets[b] .. local_offsets[b+1]).  gray/depth are tightly packed
+ * [n_frames][H][W].  new_out is [n_frames][S] (S = dsm_num_seeds), n_new is [n_frames].
+ * The three stages are exposed separately so that a caller (and bench.py) can keep inputs
+ * resident in HBM and time the kernels alone; dsm_fuse_batch() chains them and synchronises. */
+int dsm_batch_upload(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_index,
+                     const uint8_t *gray, const float *depth, const float *poses_colmajor,
+                     const dsm_surfel_t *local, const int32_t *local_offsets);
+int dsm_batch_run(dsm_ctx *ctx);     /* enqueue K0..K6 for the uploaded batch; asynchronous */
+int dsm_batch_download(dsm_ctx *ctx, dsm_surfel_t *local_out, dsm_surfel_t *new_out, int32_t *n_new);
+int dsm_sync(dsm_ctx *ctx);          /* wait for the context's stream */
+int dsm_fuse_batch(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_index,
+                   const uint8_t *gray, const float *depth, const float *poses_colmajor,
+                   dsm_surfel_t *local, const int32_t *local_offsets,
+                   dsm_surfel_t *new_out, int32_t *n_new);
+/* Re-upload only the local pool (the kernels update it in place, so a benchmark that replays
+ * the same batch must restore it between steps). Device-to-device from an internal snapshot
+ * taken at the last dsm_batch_upload. */
+int dsm_batch_restore_pool(dsm_ctx *ctx);
+
+/* ---- parity / debug readback (what the reference keeps private: fusion_functions.h:34-37) ---- */
+int dsm_get_labels(dsm_ctx *ctx, int frame, int32_t *labels_hw);   /* superpixel_index, [H][W] */
+int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds_s);   /* superpixel_seeds, [S] */
+
+/* debug: enqueue only the first n kernels of the schedule on the next dsm_batch_run (n <= 0: all).
+ * Lets the parity tests localise a mismatch to one pass; never used on the product path. */
+int dsm_debug_stop_after(dsm_ctx *ctx, int n_kernels);
+
+/* ---- measurement hooks ----
+ * Per-kernel CUDA-event timing on the context's stream.  mask selects kernels (bit k = kernel
+ * id k, see dsm_kernel_name); 0 disables.  Accumulates until dsm_profile_reset(). */
+#define DSM_NUM_KERNELS 12
+int dsm_profile_enable(dsm_ctx *ctx, uint32_t kernel_mask);
+int dsm_profile_reset(dsm_ctx *ctx);
+/* resolves pending events (synchronises); ms_total/launches are [DSM_NUM_KERNELS] */
+int dsm_profile_read(dsm_ctx *ctx, float *ms_total, int32_t *launches);
+const char *dsm_kernel_name(int kernel_id);
+/* raw device pointers for zero-copy interop (e.g. the multi-GPU gather); which: see DSM_BUF_* */
+#define DSM_BUF_NEW_SURFELS 0 /* dsm_surfel_t [max_batch][S] */
+#define DSM_BUF_NEW_COUNTS 1  /* int32 [max_batch] */
+#define DSM_BUF_LOCAL 2       /* dsm_surfel_t [max_local_surfels] */
+int dsm_device_buffer(dsm_ctx *ctx, int which, void **dev_ptr, size_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSM_H */

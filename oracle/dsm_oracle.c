@@ -760,6 +760,24 @@ int dsmor_fuse(void *p, int ref_idx, const uint8_t *gray, const float *depth, co
     return initialize_surfels(c, ref_idx, pose_colmajor16, (surfel_t *)new_out, cap_new);
 }
 
+/* test hook: seeds init + `iters` assign passes, the last one optionally without update_seeds;
+ * lets the GPU tests localise a mismatch to a single pass */
+void dsmor_debug_iters(void *p, const uint8_t *gray, const float *depth, int iters, int last_with_update)
+{
+    ctx_t *c = (ctx_t *)p;
+    c->gray = gray;
+    c->depth = depth;
+    memset(c->seeds, 0, (size_t)c->S * sizeof(seed_t));
+    memset(c->labels, 0, (size_t)c->W * c->H * sizeof(int32_t));
+    memset(c->normals, 0, (size_t)c->W * c->H * 3 * sizeof(float));
+    initialize_seeds(c);
+    for (int it = 0; it < iters; it++)
+    {
+        update_pixels(c);
+        if (it < iters - 1 || last_with_update) update_seeds(c);
+    }
+}
+
 void dsmor_get_labels(void *p, int32_t *out)
 {
     ctx_t *c = (ctx_t *)p;

@@ -128,6 +128,14 @@ class Restatement(_Base):
     prefix = "dsmor_"
     libname = "libdsm_oracle.so"
 
+    def debug_iters(self, gray, depth, iters, last_with_update=True):
+        """seed init + `iters` assign passes (last update_seeds optional); returns (labels, seeds)."""
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        self.lib.dsmor_debug_iters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        self.lib.dsmor_debug_iters(self.h, gray.ctypes.data, depth.ctypes.data, int(iters), int(bool(last_with_update)))
+        return self.labels(), self.seeds()
+
 
 def have_reference():
     return os.path.exists(os.path.join(REFDIR, "libdsm_ref_serial.so"))

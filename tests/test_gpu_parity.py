@@ -1,0 +1,169 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/dsm.h), against the
+oracle on the same seeded inputs.  Bar: labels + clustering state bit-exact, surfel geometry
+within 1e-4 (norm-based), integer fields exact."""
+import numpy as np
+import pytest
+
+from densesurfelmapping_b200 import synth
+from densesurfelmapping_b200.elements import SURFEL_DTYPE
+from util import check_seeds, check_surfels, compact_like_caller, oracle_for, bits_equal_nan
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from densesurfelmapping_b200 import capi as m
+    m.load_library()  # raises if the CUDA extension was not built: no fallback
+    return m
+
+
+def _stream(capi, cam, n_frames, flat=False, ref_div=2):
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=200000)
+    orc = oracle_for(cam)
+    pool_g = np.zeros(0, SURFEL_DTYPE)
+    pool_o = np.zeros(0, SURFEL_DTYPE)
+    for t in range(n_frames):
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(cam, t, pose, flat=flat)
+        lo, no = orc.fuse(t // ref_div, gray, depth, pose, pool_o)
+        lg, ng = ctx.fuse_frame(t // ref_div, gray, depth, pose, pool_g)
+        lab_o, lab_g = orc.labels(), ctx.labels()
+        nbad = int((lab_o != lab_g).sum())
+        assert nbad == 0, f"frame {t}: {nbad} label mismatches (first at {np.argwhere(lab_o != lab_g)[:4].tolist()})"
+        check_seeds(ctx.seeds(), orc.seeds())
+        check_surfels(lg, lo, f"frame {t} local")
+        check_surfels(ng, no, f"frame {t} new")
+        # carry the ORACLE's pool into both so that one tolerance-sized drift cannot compound
+        pool_o = compact_like_caller(lo, no)
+        pool_g = pool_o.copy()
+    ctx.close()
+
+
+def test_stage_by_stage_vga(capi):
+    """Localises a mismatch to one pass: after each assign / update the labels and the
+    clustering state must equal the restatement's."""
+    import pyoracle
+    cam = synth.VGA
+    gray, depth = synth.make_frame(cam, 0)
+    ro = pyoracle.Restatement(cam)
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=16)
+    pose = synth.identity_pose()
+    ctx.batch_upload([0], gray[None], depth[None], pose[None], np.zeros(0, SURFEL_DTYPE), [0, 0])
+    # (kernels to run, oracle iterations, last-with-update)
+    stages = [(2, 1, False), (4, 1, True), (6, 2, False), (8, 2, True), (10, 3, False), (12, 3, True)]
+    for nk, iters, upd in stages:
+        ctx.debug_stop_after(nk)
+        ctx.batch_run()
+        ctx.sync()
+        lab_o, seeds_o = ro.debug_iters(gray, depth, iters, upd)
+        lab_g, seeds_g = ctx.labels(), ctx.seeds()
+        nbad = int((lab_o != lab_g).sum())
+        assert nbad == 0, f"after {nk} kernels: {nbad} label mismatches, first {np.argwhere(lab_o != lab_g)[:4].tolist()}"
+        for f in ("x", "y", "mean_intensity", "mean_depth"):
+            bad = np.nonzero(~bits_equal_nan(seeds_g[f], seeds_o[f]))[0]
+            assert len(bad) == 0, f"after {nk} kernels: seed.{f} differs at {bad[:6]}: {seeds_g[f][bad[:6]]} vs {seeds_o[f][bad[:6]]}"
+        bad = np.nonzero(seeds_g["stable"] != seeds_o["stable"])[0]
+        assert len(bad) == 0, f"after {nk} kernels: stable differs at {bad[:8]}"
+    ctx.debug_stop_after(0)
+    ctx.close()
+
+
+def test_single_frame_vga_identity(capi):
+    """BASELINE config 1: one 640x480 frame, identity pose, empty pool then the same frame again."""
+    cam = synth.VGA
+    gray, depth = synth.make_frame(cam, 0)
+    pose = synth.identity_pose()
+    orc = oracle_for(cam)
+    ff = capi.FusionFunctions()
+    ff.initialize(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.far, cam.near)
+    lo, no = orc.fuse(0, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+    lg, ng = ff.fuse_initialize_map(0, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+    assert (orc.labels() == ff._ctx.labels()).all()
+    check_surfels(ng, no, "initialise")
+    lo2, no2 = orc.fuse(1, gray, depth, pose, no)
+    lg2, ng2 = ff.fuse_initialize_map(1, gray, depth, pose, no)
+    assert (orc.labels() == ff._ctx.labels()).all()
+    check_seeds(ff._ctx.seeds(), orc.seeds())
+    check_surfels(lg2, lo2, "fuse")
+    check_surfels(ng2, no2, "new after fuse")
+    assert (lg2["update_times"] > 1).sum() > 100  # the pure-fuse case really fused
+
+
+def test_stream_kitti(capi):
+    """BASELINE config 2 shape: 1226x370 stream with a carried pool (fuse + kill + initialise)."""
+    _stream(capi, synth.KITTI, 4)
+
+
+def test_stream_kitti_flat(capi):
+    """Noise-free piecewise-constant scene: the summation-order-sensitive case and
+    the NaN-normal seeds (H6-iii)."""
+    _stream(capi, synth.KITTI, 3, flat=True)
+
+
+def test_stream_vga_flat(capi):
+    _stream(capi, synth.VGA, 3, flat=True)
+
+
+def test_stream_hd(capi):
+    """BASELINE config 5 shape (1280x720)."""
+    _stream(capi, synth.HD, 2)
+
+
+def test_kitti00_shape(capi):
+    """1241x376 (W%8 == 1, H%8 == 0): the real KITTI-00 frame size."""
+    _stream(capi, synth.KITTI00, 2)
+
+
+def test_batch_matches_per_frame(capi):
+    """BASELINE config 3 shape: a batch of independent frames, each with its own pool slice."""
+    cam = synth.KITTI
+    B = 5
+    orc = oracle_for(cam)
+    grays, depths, poses, refs, pools = [], [], [], [], []
+    for b in range(B):
+        pose0 = synth.pose_stream(b)
+        g0, d0 = synth.make_frame(cam, 100 + b, pose0)
+        _, seeded = orc.fuse(0, g0, d0, pose0, np.zeros(0, SURFEL_DTYPE))  # predecessor view -> pool
+        pose1 = synth.pose_stream(b + 1)
+        g1, d1 = synth.make_frame(cam, 200 + b, pose1)
+        grays.append(g1), depths.append(d1), poses.append(pose1), refs.append(b % 3), pools.append(seeded if b != 2 else seeded[:0])
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in pools])]).astype(np.int32)
+    ctx = capi.Context(cam, max_batch=B, max_local_surfels=int(offsets[-1]) + 8)
+    local, news = ctx.fuse_batch(refs, np.stack(grays), np.stack(depths), np.stack(poses), np.concatenate(pools), offsets)
+    for b in range(B):
+        lo, no = orc.fuse(refs[b], grays[b], depths[b], poses[b], pools[b])
+        assert (orc.labels() == ctx.labels(b)).all(), f"batch frame {b} labels"
+        check_seeds(ctx.seeds(b), orc.seeds())
+        check_surfels(local[offsets[b]:offsets[b + 1]], lo, f"batch frame {b} local")
+        check_surfels(news[b], no, f"batch frame {b} new")
+    ctx.close()
+
+
+def test_pitched_input_and_errors(capi):
+    cam = synth.VGA
+    gray, depth = synth.make_frame(cam, 7)
+    gp = np.zeros((cam.height, cam.width + 24), np.uint8)
+    dp = np.zeros((cam.height, cam.width + 8), np.float32)
+    gp[:, :cam.width] = gray
+    dp[:, :cam.width] = depth
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=16)
+    import ctypes
+    new = np.zeros(ctx.S, SURFEL_DTYPE)
+    n = ctypes.c_int(0)
+    pose = synth.identity_pose()
+    rc = ctx.lib.dsm_fuse_frame(ctx.h, 0, gp.ctypes.data, gp.strides[0], dp.ctypes.data, dp.strides[0],
+                                pose.ctypes.data, None, 0, new.ctypes.data, ctx.S, ctypes.byref(n))
+    assert rc == 0
+    _, want = oracle_for(cam).fuse(0, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+    check_surfels(new[:n.value], want, "pitched")
+    # capacity error: more local surfels than the context was created for
+    with pytest.raises(capi.DsmError) as ei:
+        ctx.fuse_frame(0, gray, depth, pose, np.zeros(17, SURFEL_DTYPE))
+    assert ei.value.code == -6
+    ctx.close()
+    # shape error: W%8 > 4 is undefined behaviour in the reference (fusion_functions.cpp:408-451)
+    bad = synth.Camera(645, 480, 525.0, 525.0, 319.5, 239.5, 0.5, 30.0)
+    with pytest.raises(capi.DsmError) as ei:
+        capi.Context(bad)
+    assert ei.value.code == -2
