@@ -236,6 +236,15 @@ static void update_pixels(ctx_t *c)
         }
 }
 
+/* test instrumentation: how often the chunk-abandoning `return` (:516-517) fired since the last reset */
+static int g_abort_events = 0;
+int dsmor_debug_abort_events(int reset)
+{
+    int v = g_abort_events;
+    if (reset) g_abort_events = 0;
+    return v;
+}
+
 /* ---- update_seeds_kernel (:468-562), with the per-chunk early return (:516-517) ---- */
 static void update_seeds(ctx_t *c)
 {
@@ -274,7 +283,11 @@ static void update_seeds(ctx_t *c)
                             n_d += 1.0f;
                         }
                     }
-            if (n_i == 0) break; /* reference `return`: abandons the REST OF THIS CHUNK (H3) */
+            if (n_i == 0)
+            { /* reference `return`: abandons the REST OF THIS CHUNK (H3) */
+                g_abort_events++;
+                break;
+            }
             sum_i /= n_i;
             sum_x /= n_i;
             sum_y /= n_i;

@@ -1,0 +1,143 @@
+"""CPU tests (-m "not gpu"): the oracle against the golden vectors minted from the reference's own
+source, and the restatement against the serialised reference build when that library is present."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import pyoracle
+from densesurfelmapping_b200 import synth
+from densesurfelmapping_b200.elements import SEED_DTYPE, SURFEL_DTYPE
+from util import bits_equal_nan
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def canon(a):
+    """field-by-field bytes (struct padding excluded) with every NaN canonicalised: NaN payload/sign
+    and padding bytes are not part of the contract."""
+    parts = []
+    for f in a.dtype.names:
+        v = np.ascontiguousarray(a[f]).copy()
+        if v.dtype.kind == "f":
+            v[np.isnan(v)] = np.float32(np.nan)
+        parts.append(v.tobytes())
+    return b"".join(parts)
+
+
+def crc(x):
+    return zlib.crc32(x if isinstance(x, (bytes, bytearray)) else np.ascontiguousarray(x).tobytes()) & 0xFFFFFFFF
+
+
+def assert_records_equal(a, b, what):
+    assert len(a) == len(b), what
+    for f in a.dtype.names:
+        if a.dtype[f].kind == "f":
+            bad = np.nonzero(~bits_equal_nan(a[f], b[f]))[0]
+        else:
+            bad = np.nonzero(a[f] != b[f])[0]
+        assert len(bad) == 0, f"{what}.{f} differs at {bad[:6]}"
+
+
+def oracles(cam):
+    out = [("restatement", pyoracle.Restatement(cam))]
+    if pyoracle.have_reference():
+        out.append(("reference_serial", pyoracle.RefSerial(cam)))
+    return out
+
+
+def test_golden_vga_two_pass():
+    """BASELINE config 1: every oracle reproduces the committed golden vectors bit for bit."""
+    z = np.load(os.path.join(GOLD, "vga_two_pass.npz"))
+    cam = synth.VGA
+    g, d = synth.make_frame(cam, 0)
+    assert crc(g) == int(z["gray_crc"]) and crc(d) == int(z["depth_crc"]), "synthetic generator drifted from the golden inputs"
+    pose = synth.identity_pose()
+    for name, o in oracles(cam):
+        _, new0 = o.fuse(0, g, d, pose, np.zeros(0, SURFEL_DTYPE))
+        assert (o.labels() == z["labels0"].astype(np.int32)).all(), name
+        assert_records_equal(o.seeds(), z["seeds0"].view(SEED_DTYPE).reshape(-1), name + " seeds0")
+        assert_records_equal(new0, z["new0"].view(SURFEL_DTYPE).reshape(-1), name + " new0")
+        loc1, new1 = o.fuse(1, g, d, pose, new0)
+        assert (o.labels() == z["labels1"].astype(np.int32)).all(), name
+        assert_records_equal(o.seeds(), z["seeds1"].view(SEED_DTYPE).reshape(-1), name + " seeds1")
+        assert_records_equal(loc1, z["local1"].view(SURFEL_DTYPE).reshape(-1), name + " local1")
+        assert_records_equal(new1, z["new1"].view(SURFEL_DTYPE).reshape(-1), name + " new1")
+        assert (loc1["update_times"] == 2).sum() > 1000  # the pure-fuse pass really fused
+
+
+@pytest.mark.parametrize("key,camname,flat", [("kitti", "kitti", False), ("kitti_flat", "kitti", True), ("vga_flat", "vga", True)])
+def test_golden_stream_checksums(key, camname, flat):
+    """Larger frames: CRC32 of labels / seeds / surfels over a short stream with a carried pool."""
+    sums = json.load(open(os.path.join(GOLD, "checksums.json")))[key]
+    cam = synth.CAMERAS[camname]
+    o = pyoracle.Restatement(cam)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    for rec in sums:
+        t = rec["frame"]
+        pose = synth.pose_stream(t)
+        g, d = synth.make_frame(cam, t, pose, flat=flat)
+        assert crc(g) == rec["gray_crc"] and crc(d) == rec["depth_crc"]
+        loc, new = o.fuse(t // 2, g, d, pose, pool)
+        assert crc(o.labels()) == rec["labels_crc"], f"{key} frame {t} labels"
+        assert crc(canon(o.seeds())) == rec["seeds_crc"], f"{key} frame {t} seeds"
+        assert crc(canon(loc)) == rec["local_crc"] and crc(canon(new)) == rec["new_crc"], f"{key} frame {t} surfels"
+        assert len(new) == rec["n_new"]
+        keep = loc[loc["update_times"] > 0] if len(loc) else loc
+        pool = np.concatenate([keep, new])
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref/libdsm_ref_serial.so not built")
+def test_restatement_equals_reference_serial_small():
+    """A small odd-shaped frame (W%8 == 4, H%8 == 2) with a pool: byte-identical modulo NaN payload."""
+    cam = synth.Camera(324, 242, 260.0, 260.0, 161.5, 120.5, 0.5, 30.0)
+    rs, ro = pyoracle.RefSerial(cam), pyoracle.Restatement(cam)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    for t in range(3):
+        pose = synth.pose_stream(t)
+        g, d = synth.make_frame(cam, 50 + t, pose)
+        lr, nr = rs.fuse(t, g, d, pose, pool)
+        lo, no = ro.fuse(t, g, d, pose, pool)
+        assert (rs.labels() == ro.labels()).all()
+        assert_records_equal(ro.seeds(), rs.seeds(), "seeds")
+        assert_records_equal(lo, lr, "local")
+        assert_records_equal(no, nr, "new")
+        pool = np.concatenate([lr[lr["update_times"] > 0] if len(lr) else lr, nr])
+
+
+def test_every_seed_keeps_its_centre_pixel():
+    """Why the update_seeds early `return` (fusion_functions.cpp:516-517) can never fire for a valid
+    shape: the pixel at (8sx+4, 8sy+4) has exactly one candidate seed, so every seed always owns it."""
+    cam = synth.VGA
+    o = pyoracle.Restatement(cam)
+    g, d = synth.make_frame(cam, 3)
+    lab, _ = o.superpixels(g, d)
+    spw = cam.width // 8
+    for s in range(0, o.S, 37):
+        sx, sy = s % spw, s // spw
+        assert lab[8 * sy + 4, 8 * sx + 4] == s
+    o.lib.dsmor_debug_abort_events.restype = int
+    assert o.lib.dsmor_debug_abort_events(0) == 0
+
+
+def test_quirks_documented_in_survey_appendix_a():
+    cam = synth.VGA
+    o = pyoracle.Restatement(cam)
+    g, d = synth.make_frame(cam, 0)
+    lab, seeds = o.superpixels(g, d)
+    assert lab.min() >= 0 and lab.max() < o.S
+    # rejected seeds keep zero normal / view_cos (H6-i) and are never initialised
+    rej = (seeds["norm_x"] == 0) & (seeds["norm_y"] == 0) & (seeds["norm_z"] == 0)
+    assert rej.any() and (seeds["view_cos"][rej] == 0).all() and (seeds["size"][rej] == 0).all()
+    _, new = o.fuse(0, g, d, synth.identity_pose(), np.zeros(0, SURFEL_DTYPE))
+    ok = ~rej & (seeds["mean_depth"] != 0) & ~(seeds["view_cos"] < 0.1)
+    assert len(new) == int(ok.sum())
+    assert (new["update_times"] == 1).all() and (new["last_update"] == 0).all()
+    # unsupported shapes are rejected rather than reading out of bounds (H6-ii)
+    import ctypes
+    lib = pyoracle._lib("libdsm_oracle.so")
+    lib.dsmor_create.restype = ctypes.c_void_p
+    lib.dsmor_create.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_float] * 6
+    assert lib.dsmor_create(645, 480, 1.0, 1.0, 1.0, 1.0, 30.0, 0.5) is None
