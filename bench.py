@@ -232,7 +232,8 @@ def kernel_alg_bytes(name, P, S, npool, nnew):
         "stable_relax": 0,
         "slic_update": 9 * P + 20 * S + 20 * S,
         "seed_commit": 24 * S + 28 * S,
-        "normals_plane_fit": 8 * P + 16 * S + 48 * S,
+        "pixel_normals": 4 * P + 12 * P,
+        "seed_plane_fit": 8 * P + 12 * P + 16 * S + 48 * S,
         "surfel_fuse": 88 * npool + 48 * S,
         "surfel_init": 52 * S + 44 * nnew,
     }.get(name, 0)
@@ -314,17 +315,17 @@ def run_gpu_arm(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ctx.profile_enable(0x1FF)
+    ctx.profile_enable(0x5FF)
     ctx.profile_reset()
     for _ in range(max(args.warmup, 3)):
         step()
     ms, nl = ctx.profile_read()
     names = capi.kernel_names()
-    kernel_ms = {names[i]: float(ms[i]) / max(args.warmup, 3) for i in range(9) if nl[i]}  # ms per step
-    per_launch_ms = {names[i]: float(ms[i] / nl[i]) for i in range(9) if nl[i]}
+    kernel_ms = {names[i]: float(ms[i]) / max(args.warmup, 3) for i in range(len(names)) if nl[i]}  # ms per step
+    per_launch_ms = {names[i]: float(ms[i] / nl[i]) for i in range(len(names)) if nl[i]}
     dom = max(kernel_ms, key=kernel_ms.get)
     dom_id = names.index(dom)
-    launches_per_step = int(sum(nl[:9]) // max(args.warmup, 3))
+    launches_per_step = int(sum(nl) // max(args.warmup, 3))
     nnew_avg = float(np.mean([len(p) for p in ctx.batch_download()[1]]))
     ctx.profile_enable(1 << dom_id)  # inside the timed region only the dominant kernel carries events
     ctx.profile_reset()

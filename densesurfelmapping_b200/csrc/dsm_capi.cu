@@ -35,6 +35,7 @@ struct dsm_ctx
     int32_t *poolofs, *refidx;
     float *pose, *ipose;
     dsm_seed_t *seed_export;
+    float *kx, *ky;
     // pinned host staging for the small per-batch tables
     float *h_pose; // [B][32]: pose then inverse
     int32_t *h_ofs;
@@ -50,7 +51,7 @@ struct dsm_ctx
 
 static const char *kKernelNames[DSM_NUM_KERNELS] = {
     "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_update", "seed_commit",
-    "normals_plane_fit", "surfel_fuse", "surfel_init", "seeds_export", "reserved0", "reserved1"};
+    "seed_plane_fit", "surfel_fuse", "surfel_init", "seeds_export", "pixel_normals", "reserved1"};
 
 #define CK(call)                                                                                         \
     do                                                                                                   \
@@ -128,6 +129,10 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(ctx->ipose);
     cudaFree(ctx->refidx);
     cudaFree(ctx->seed_export);
+    cudaFree(d.nrm);
+    cudaFree(ctx->kx);
+    cudaFree(ctx->ky);
+    cudaFree(d.pflist);
     cudaFreeHost(ctx->h_pose);
     cudaFreeHost(ctx->h_ofs);
     cudaFreeHost(ctx->h_ref);
@@ -210,7 +215,20 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(ctx->ipose, (size_t)B * 16);
     ALLOC(ctx->refidx, (size_t)B);
     ALLOC(ctx->seed_export, (size_t)S);
+    ALLOC(d.nrm, 3 * (B * px) + 64);
+    ALLOC(ctx->kx, (size_t)Wp + 16);
+    ALLOC(ctx->ky, (size_t)H + 16);
+    ALLOC(d.pflist, (size_t)B * ((S + 31) / 32) * 232 * 32);
 #undef ALLOC
+    d.nrm_plane = B * px;
+    if (e == cudaSuccess)
+    { // back-projection factor tables: the same float ops as back_project (fusion_functions.cpp:94-95)
+        std::vector<float> hx((size_t)Wp + 16), hy((size_t)H + 16);
+        for (int u = 0; u < Wp + 16; u++) hx[u] = ((float)u - params->cx) / params->fx;
+        for (int v = 0; v < H + 16; v++) hy[v] = ((float)v - params->cy) / params->fy;
+        e = cudaMemcpy(ctx->kx, hx.data(), hx.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->ky, hy.data(), hy.size() * sizeof(float), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_pose, (size_t)B * 32 * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ofs, ((size_t)B + 1) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ref, (size_t)B * sizeof(int32_t));
@@ -225,6 +243,8 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     d.pose = ctx->pose;
     d.ipose = ctx->ipose;
     d.refidx = ctx->refidx;
+    d.kx = ctx->kx;
+    d.ky = ctx->ky;
     d.max_pool_per_frame = 0;
     *out = ctx;
     return DSM_OK;
@@ -443,6 +463,7 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
         STEP(DSM_K_UPDATE_SEEDS, dsm_launch_update_seeds(d, nb, st));
         STEP(DSM_K_COMMIT_SEEDS, dsm_launch_commit_seeds(d, nb, st));
     }
+    STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
     STEP(DSM_K_PLANE_FIT, dsm_launch_plane_fit(d, nb, st));
     if (d.max_pool_per_frame > 0)
     {
@@ -554,7 +575,7 @@ extern "C" int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds)
     if (!ctx || !seeds || frame < 0 || frame >= ctx->p.max_batch) return DSM_E_INVALID;
     if (!ctx->ran) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < 13) ? 1 : 0, ctx->stream);
+    dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < 14) ? 1 : 0, ctx->stream);
     CK(cudaMemcpyAsync(seeds, ctx->seed_export, (size_t)ctx->S * sizeof(dsm_seed_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());

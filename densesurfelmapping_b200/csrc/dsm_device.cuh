@@ -11,6 +11,9 @@
 //   cand    float4 [B][S]       update_seeds results before the chunk-abort commit (H3)
 //   cflag   i32 [B][S]          bit0 new-stable, bit1 processed
 //   abortc  i32 [B][16]         per 10-way chunk: first seed index that hit `return` (:516)
+//   nrm     f32 [3][B][H][Wp]   pixel normals (K3 -> K4), 12 B/px instead of the reference's 36 B/px
+//   kx, ky  f32 [Wp+16], [H+16] back-projection factors, computed once per context
+//   pflist  float4 [B][S/32][232][32]  plane-fit inlier points, [k][seed] so thread-per-seed reads coalesce
 //   plane   float4 [B][S][3]    (n.xyz, view_cos) (posi.xyz, mean_depth) (size, I, x, y)
 //   fused   i32 [B][S]          Superpixel_seed::fused
 //   list    int2 [B][P]         pixels owned by stable seeds: (pitched raster index, winner)
@@ -46,6 +49,11 @@ struct DsmDev
     int32_t *cflag;
     int32_t *abortc;
     float4 *plane;
+    float *nrm;         // pixel normals, 3 planes of B*px_stride floats (x | y | z)
+    size_t nrm_plane;   // B * px_stride
+    const float *kx;    // [Wp+16]: ((float)u - cx) / fx, the per-column factor of back_project (:94)
+    const float *ky;    // [H+16]:  ((float)v - cy) / fy
+    float4 *pflist;     // plane-fit scratch: [B][ceil(S/32)][PF_CAP][32] inlier points
     int32_t *fused;
     int2 *list;
     int32_t *nlist;
@@ -71,7 +79,7 @@ enum DsmKernelId
     DSM_K_FUSE = 7,
     DSM_K_INIT_SURFELS = 8,
     DSM_K_SEEDS_EXPORT = 9,
-    DSM_K_RESERVED0 = 10,
+    DSM_K_PIXEL_NORMALS = 10,
     DSM_K_RESERVED1 = 11,
 };
 
@@ -81,6 +89,7 @@ void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s);
 void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_update_seeds(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_commit_seeds(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_plane_fit(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s);

@@ -513,185 +513,238 @@ __global__ void __launch_bounds__(256) k_commit_seeds(const __grid_constant__ Ds
 }
 
 // -------------------------------------------------------------------------------------------
-// K3+K4  backproject_normals + seed_plane_fit
-//   calculate_spaces_kernel (:644-662), calculate_pixels_norms_kernel (:664-712),
-//   calculate_sp_depth_norms_kernel (:792-914), get_huber_norm (:104-188)
+// K3  backproject_normals — calculate_spaces_kernel (:644-662) + calculate_pixels_norms_kernel
+// (:664-712), fused: the reference's 24 B/px fp64 space_map is never materialised.
 //
-// The reference materialises space_map (24 B/px, fp64!) and norm_map (12 B/px) and re-reads them
-// per superpixel.  Here a warp owns one superpixel, recomputes the back-projection and the
-// pixel normal of each member pixel from the depth tile (3 L1/L2-resident loads), and keeps its
-// <= 8 inlier points in registers across the 5 Gauss-Newton steps.  Sums are warp-shuffle tree
-// reductions: this stage does not feed the labels, so it is order-free within the 1e-4 budget
-// (SURVEY.md §7 H2/H5); thresholds and promotions still follow the reference expression by
-// expression.  All lanes carry the (tiny) 4x4 fp64 solve redundantly.
+// Streaming, pixel-parallel: one thread owns 4 consecutive pixels, reads the depth row and the
+// row below with 16-byte loads and writes the three normal planes with 16-byte stores.  The
+// per-column / per-row factors (u-cx)/fx and (v-cy)/fy come from two small tables computed once
+// per context with the same float ops as back_project (:94-95), so a back-projected point is
+// table[u]*d exactly as in the reference.  Zero normal outside rows 1..H-2 / cols 1..W-2 and
+// for the skipped pixels, like the reference's pre-zeroed norm_map (:965).
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void inverse4d(const double *m, double *out)
-{ // adjugate / determinant, same formula as the oracle's Eigen stand-in
-    double inv[16];
-    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
-    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
-    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
-    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
-    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
-    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
-    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
-    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
-    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
-    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
-    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
-    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
-    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
-    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
-    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
-    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
-    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
-    const double inv_det = 1.0 / det;
+__global__ void __launch_bounds__(256) k_pixel_normals(const __grid_constant__ DsmDev d)
+{
+    const int b = blockIdx.z;
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x4 >= d.Wp || y >= d.H) return;
+    const int W = d.W, H = d.H, Wp = d.Wp;
+    const size_t fo = (size_t)b * d.px_stride;
+    const size_t po = fo + (size_t)y * Wp + x4;
+    float nx[4] = {0.f, 0.f, 0.f, 0.f}, ny[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y >= 1 && y <= H - 2 && x4 < W)
+    {
+        const float4 z4 = *reinterpret_cast<const float4 *>(d.depth + po);
+        const float4 zd4 = *reinterpret_cast<const float4 *>(d.depth + po + Wp);
+        const float zr = (x4 + 4 < Wp) ? d.depth[po + 4] : 0.f;
+        const float4 kx4 = *reinterpret_cast<const float4 *>(d.kx + x4);
+        const float kxr = d.kx[x4 + 4];
+        const float ky0 = d.ky[y], ky1 = d.ky[y + 1];
+        const float z[5] = {z4.x, z4.y, z4.z, z4.w, zr};
+        const float zd[4] = {zd4.x, zd4.y, zd4.z, zd4.w};
+        const float kx[5] = {kx4.x, kx4.y, kx4.z, kx4.w, kxr};
 #pragma unroll
-    for (int i = 0; i < 16; i++) out[i] = inv[i] * inv_det;
+        for (int i = 0; i < 4; i++)
+        {
+            const int x = x4 + i;
+            if (x < 1 || x > W - 2) continue;
+            const float mz = z[i], rz = z[i + 1], dz = zd[i];
+            if ((double)mz < 0.1 || (double)rz < 0.1 || (double)dz < 0.1) continue; // (:688)
+            const float mx = kx[i] * mz, my = ky0 * mz;
+            const float rx = kx[i + 1] * rz - mx, ry = ky0 * rz - my, rzz = rz - mz;
+            const float dx = kx[i] * dz - mx, dy = ky1 * dz - my, dzz = dz - mz;
+            float cxn = ry * dzz - rzz * dy;
+            float cyn = rzz * dx - rx * dzz;
+            float czn = rx * dy - ry * dx;
+            const float len = sqrtf(cxn * cxn + cyn * cyn + czn * czn);
+            cxn /= len;
+            cyn /= len;
+            czn /= len;
+            const float view = (cxn * mx + cyn * my + czn * mz) / sqrtf(mx * mx + my * my + mz * mz);
+            if ((double)view > -MAX_ANGLE_COS && (double)view < MAX_ANGLE_COS) continue; // (:706)
+            nx[i] = cxn, ny[i] = cyn, nz[i] = czn;
+        }
+    }
+    *reinterpret_cast<float4 *>(d.nrm + po) = make_float4(nx[0], nx[1], nx[2], nx[3]);
+    *reinterpret_cast<float4 *>(d.nrm + d.nrm_plane + po) = make_float4(ny[0], ny[1], ny[2], ny[3]);
+    *reinterpret_cast<float4 *>(d.nrm + 2 * d.nrm_plane + po) = make_float4(nz[0], nz[1], nz[2], nz[3]);
 }
 
-__global__ void __launch_bounds__(256) k_plane_fit(const __grid_constant__ DsmDev d)
+// -------------------------------------------------------------------------------------------
+// K4  seed_plane_fit — calculate_sp_depth_norms_kernel (:792-914) + get_huber_norm (:104-188)
+//
+// One warp owns 32 consecutive superpixels and works in two phases:
+//  A (warp per seed, 32 seeds in turn): scan the 16x16 window (lane = 2*row+half, 8 px/lane),
+//    count valid depths (> 0.05), find max_dist, classify inliers |mean_depth-d| < 0.4, reduce the
+//    inlier normal / position sums with shuffles, and scan-compact the inlier points into a
+//    global scratch list laid out [k][32 seeds] of float4 so that phase B reads are coalesced.
+//    Lane sl keeps seed sl's summary in registers.
+//  B (thread per seed): the five damped Gauss-Newton steps.  Each lane streams its own seed's
+//    points (one coalesced LDG.128 per point per warp), accumulates the 4x4 normal equations in
+//    fp64 registers -- no cross-lane reduction at all -- and solves them by symmetric
+//    elimination.  Then the superpixel centre is projected onto the plane exactly as (:884-912).
+// This stage does not feed the labels, so sums are order-free within the 1e-4 budget
+// (SURVEY.md §7 H2/H5); thresholds and float/double promotions follow the reference.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void solve4_spd(const double *h, const double *j, double *u)
+{ // h: 10 unique entries xx xy xz xw yy yz yw zz zw ww of an SPD matrix; solves H u = j
+    const double a00 = h[0], a01 = h[1], a02 = h[2], a03 = h[3];
+    const double i0 = 1.0 / a00;
+    const double l10 = a01 * i0, l20 = a02 * i0, l30 = a03 * i0;
+    const double a11 = h[4] - l10 * a01, a12 = h[5] - l10 * a02, a13 = h[6] - l10 * a03;
+    const double a22p = h[7] - l20 * a02, a23p = h[8] - l20 * a03, a33p = h[9] - l30 * a03;
+    const double i1 = 1.0 / a11;
+    const double l21 = a12 * i1, l31 = a13 * i1;
+    const double a22 = a22p - l21 * a12, a23 = a23p - l21 * a13, a33q = a33p - l31 * a13;
+    const double i2 = 1.0 / a22;
+    const double l32 = a23 * i2;
+    const double a33 = a33q - l32 * a23;
+    // forward substitution (L y = j)
+    const double y0 = j[0];
+    const double y1 = j[1] - l10 * y0;
+    const double y2 = j[2] - l20 * y0 - l21 * y1;
+    const double y3 = j[3] - l30 * y0 - l31 * y1 - l32 * y2;
+    // D and back substitution
+    u[3] = y3 / a33;
+    u[2] = y2 * i2 - l32 * u[3];
+    u[1] = y1 * i1 - l21 * u[2] - l31 * u[3];
+    u[0] = y0 * i0 - l10 * u[1] - l20 * u[2] - l30 * u[3];
+}
+
+#define PF_CAP 232 // >= 15*15 possible members of a superpixel, multiple of 8
+
+__global__ void __launch_bounds__(32) k_plane_fit(const __grid_constant__ DsmDev d)
 {
     const int b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + warp;
-    if (s >= d.S) return;
+    const int lane = threadIdx.x;
+    const int seed0 = blockIdx.x * 32;
     const int W = d.W, H = d.H, Wp = d.Wp;
     const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
     const int32_t *labels = d.labels + fo;
     const float *depth = d.depth + fo;
-    const float4 sd = d.seed[so + s]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
-    const float fx = d.fx, fy = d.fy, cx = d.cx, cy = d.cy;
+    const float *nrm = d.nrm + fo;
+    float4 *list = d.pflist + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)(PF_CAP * 32);
 
-    const int sp_x = s % d.spw, sp_y = s / d.spw;
-    const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
-    const int y = y0 + (lane >> 1);
-    const int xs = x0 + 8 * (lane & 1);
+    // per-lane summary of seed (seed0 + lane), filled in during phase A
+    int my_nvalid = 0, my_ninl = 0;
+    float my_maxd = 0.f, my_snx = 0.f, my_sny = 0.f, my_snz = 0.f, my_spx = 0.f, my_spy = 0.f, my_spz = 0.f;
 
-    float max_dist = 0.0f;
-    int nvalid = 0, ninl = 0;
-    float snx = 0.f, sny = 0.f, snz = 0.f; // sum of inlier pixel normals
-    float spx = 0.f, spy = 0.f, spz = 0.f; // sum of inlier points
-    float px[8], py[8], pz[8];
-    unsigned inl = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) px[k] = py[k] = pz[k] = 0.f;
-
-    if (y >= 0 && y < H)
+    const int row = lane >> 1, half = lane & 1;
+    for (int sl = 0; sl < 32; sl++)
     {
+        const int s = seed0 + sl;
+        if (s >= d.S) break; // warp-uniform
+        const float4 sd = d.seed[so + s];
+        const int sp_x = s % d.spw, sp_y = s / d.spw;
+        const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
+        const int y = y0 + row;
+        const int xs = x0 + 8 * half;
+        float dv[8];
+        unsigned inl = 0;
+        int nvalid = 0;
+        float maxd = 0.f, snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
+        float kxv[8];
+        float kyv = 0.f;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; h2++)
+        for (int k = 0; k < 8; k++) dv[k] = 0.f, kxv[k] = 0.f;
+        if (y >= 0 && y < H)
         {
-            const int xq = xs + 4 * h2;
-            if (xq < 0 || xq >= Wp) continue;
-            const int4 l4 = *reinterpret_cast<const int4 *>(labels + (size_t)y * Wp + xq);
-            if (l4.x != s && l4.y != s && l4.z != s && l4.w != s) continue;
-            const float4 z4 = *reinterpret_cast<const float4 *>(depth + (size_t)y * Wp + xq);
-            const int lk[4] = {l4.x, l4.y, l4.z, l4.w};
-            const float zk[4] = {z4.x, z4.y, z4.z, z4.w};
+            kyv = d.ky[y];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int h2 = 0; h2 < 2; h2++)
             {
-                const int x = xq + k;
-                if (lk[k] != s || x >= W) continue; // window is bounded by the flat index only (:816); x<0 cannot occur (xq>=0)
-                const float xd = (float)x - sd.x, yd = (float)y - sd.y;
-                const float dist = xd * xd + yd * yd;
-                if (dist > max_dist) max_dist = dist;
-                const float mz = zk[k];
-                if (!((double)mz > 0.05)) continue; // (:827)
-                nvalid++;
-                // back_project in float (:94-96)
-                const float mx = ((float)x - cx) / fx * mz;
-                const float my = ((float)y - cy) / fy * mz;
-                // pixel normal (:664-712): zero outside rows 1..H-2 / cols 1..W-2 or when skipped
-                float nx = 0.f, ny = 0.f, nz = 0.f;
-                if (x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2)
+                const int xq = xs + 4 * h2;
+                if (xq < 0 || xq >= Wp) continue;
+                const size_t po = (size_t)y * Wp + xq;
+                const int4 l4 = *reinterpret_cast<const int4 *>(labels + po);
+                if (l4.x != s && l4.y != s && l4.z != s && l4.w != s) continue;
+                const float4 z4 = *reinterpret_cast<const float4 *>(depth + po);
+                const float4 k4 = *reinterpret_cast<const float4 *>(d.kx + xq);
+                const int lk[4] = {l4.x, l4.y, l4.z, l4.w};
+                const float zk[4] = {z4.x, z4.y, z4.z, z4.w};
+                const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
                 {
-                    const float rz = depth[(size_t)y * Wp + x + 1];
-                    const float dz = depth[(size_t)(y + 1) * Wp + x];
-                    if (!((double)mz < 0.1 || (double)rz < 0.1 || (double)dz < 0.1))
-                    {
-                        float rx = ((float)(x + 1) - cx) / fx * rz;
-                        float ry = ((float)y - cy) / fy * rz;
-                        float dx = ((float)x - cx) / fx * dz;
-                        float dy = ((float)(y + 1) - cy) / fy * dz;
-                        rx = rx - mx;
-                        ry = ry - my;
-                        const float rzz = rz - mz;
-                        dx = dx - mx;
-                        dy = dy - my;
-                        const float dzz = dz - mz;
-                        float cxn = ry * dzz - rzz * dy;
-                        float cyn = rzz * dx - rx * dzz;
-                        float czn = rx * dy - ry * dx;
-                        const float len = sqrtf(cxn * cxn + cyn * cyn + czn * czn);
-                        cxn /= len;
-                        cyn /= len;
-                        czn /= len;
-                        const float view = (cxn * mx + cyn * my + czn * mz) / sqrtf(mx * mx + my * my + mz * mz);
-                        if (!((double)view > -MAX_ANGLE_COS && (double)view < MAX_ANGLE_COS))
-                        {
-                            nx = cxn;
-                            ny = cyn;
-                            nz = czn;
-                        }
+                    const int x = xq + k;
+                    if (lk[k] != s || x >= W) continue; // window bounded by the flat index only (:816)
+                    const float xd = (float)x - sd.x, yd = (float)y - sd.y;
+                    const float dist = xd * xd + yd * yd;
+                    if (dist > maxd) maxd = dist;
+                    const float mz = zk[k];
+                    if (!((double)mz > 0.05)) continue; // (:827)
+                    nvalid++;
+                    const float r = sd.w - mz;
+                    if ((double)r < HUBER_RANGE && (double)r > -HUBER_RANGE)
+                    { // inlier (:849-860)
+                        inl |= 1u << (h2 * 4 + k);
+                        dv[h2 * 4 + k] = mz;
+                        kxv[h2 * 4 + k] = kk[k];
+                        snx += nrm[po + k];
+                        sny += nrm[d.nrm_plane + po + k];
+                        snz += nrm[2 * d.nrm_plane + po + k];
+                        spx += kk[k] * mz; // back_project in float (:94-96)
+                        spy += kyv * mz;
+                        spz += mz;
                     }
-                }
-                const float r = sd.w - mz;
-                if ((double)r < HUBER_RANGE && (double)r > -HUBER_RANGE)
-                { // inlier (:849-860)
-                    ninl++;
-                    snx += nx;
-                    sny += ny;
-                    snz += nz;
-                    spx += mx;
-                    spy += my;
-                    spz += mz;
-                    px[h2 * 4 + k] = mx;
-                    py[h2 * 4 + k] = my;
-                    pz[h2 * 4 + k] = mz;
-                    inl |= 1u << (h2 * 4 + k);
                 }
             }
         }
+        maxd = warp_max_f(maxd);
+        nvalid = __reduce_add_sync(FULL, nvalid);
+        int ninl;
+        int pos = warp_excl_scan(__popc(inl), lane, ninl);
+        const bool ok = nvalid >= 16 && !((double)((float)ninl / (float)nvalid) < 0.8); // (:841, :862) warp-uniform
+        if (ok)
+        {
+            snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
+            spx = warp_sum_f(spx), spy = warp_sum_f(spy), spz = warp_sum_f(spz);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if ((inl >> k) & 1u)
+                {
+                    list[(size_t)pos * 32 + sl] = make_float4(kxv[k] * dv[k], kyv * dv[k], dv[k], 0.f);
+                    pos++;
+                }
+        }
+        if (lane == sl)
+        {
+            my_nvalid = ok ? nvalid : 0;
+            my_ninl = ninl;
+            my_maxd = maxd;
+            my_snx = snx, my_sny = sny, my_snz = snz;
+            my_spx = spx, my_spy = spy, my_spz = spz;
+        }
     }
-    max_dist = warp_max_f(max_dist);
-    nvalid = __reduce_add_sync(FULL, nvalid);
-    ninl = __reduce_add_sync(FULL, ninl);
+    __syncwarp();
+    __threadfence_block(); // phase B reads the scratch list written by other lanes of this warp
 
+    // ---- phase B: thread per seed
+    const int s = seed0 + lane;
+    if (s >= d.S) return;
+    const float4 sd = d.seed[so + s];
     // default record: plane fit rejected -> zero normal / position / view_cos / size (H6-i), Huber mean depth kept
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 r1 = make_float4(0.f, 0.f, 0.f, sd.w);
     float4 r2 = make_float4(0.f, sd.z, sd.x, sd.y);
-
-    bool ok = nvalid >= 16;                                            // (:841)
-    if (ok && (double)((float)ninl / (float)nvalid) < 0.8) ok = false; // (:862)
-    if (ok)
+    if (my_nvalid > 0)
     {
-        snx = warp_sum_f(snx);
-        sny = warp_sum_f(sny);
-        snz = warp_sum_f(snz);
-        const float len0 = sqrtf(snx * snx + sny * sny + snz * snz);
-        float nx = snx / len0, ny = sny / len0, nz = snz / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
-        // get_huber_norm (:104-188)
-        const float fnin = (float)ninl;
-        const float mxs = warp_sum_f(spx) / fnin, mys = warp_sum_f(spy) / fnin, mzs = warp_sum_f(spz) / fnin;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-        {
-            px[k] -= mxs;
-            py[k] -= mys;
-            pz[k] -= mzs;
-        }
+        const int n = my_ninl;
+        const float len0 = sqrtf(my_snx * my_snx + my_sny * my_sny + my_snz * my_snz);
+        float nx = my_snx / len0, ny = my_sny / len0, nz = my_snz / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
+        const float fn = (float)n;
+        const float mxs = my_spx / fn, mys = my_spy / fn, mzs = my_spz / fn;
+        const float4 *lp = list + lane;
         for (int gn = 0; gn < 5; gn++)
         {
             double j0 = 0, j1 = 0, j2 = 0, j3 = 0;
             double hxx = 0, hxy = 0, hxz = 0, hx = 0, hyy = 0, hyz = 0, hy = 0, hzz = 0, hz = 0, hc = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++)
+#pragma unroll 2
+            for (int k = 0; k < n; k++)
             {
-                if (!((inl >> k) & 1u)) continue;
-                const float qx = px[k], qy = py[k], qz = pz[k];
+                const float4 p = lp[(size_t)k * 32];
+                const float qx = p.x - mxs, qy = p.y - mys, qz = p.z - mzs; // centred points (:121-126)
                 const float r = qx * nx + qy * ny + qz * nz + nb;
                 if ((double)r < HUBER_RANGE && (double)r > -1 * HUBER_RANGE)
                 { // float products accumulated in double (:136-155)
@@ -725,24 +778,14 @@ __global__ void __launch_bounds__(256) k_plane_fit(const __grid_constant__ DsmDe
                     j3 += -1 * HUBER_RANGE;
                 }
             }
-            j0 = warp_sum_d(j0), j1 = warp_sum_d(j1), j2 = warp_sum_d(j2), j3 = warp_sum_d(j3);
-            hxx = warp_sum_d(hxx), hxy = warp_sum_d(hxy), hxz = warp_sum_d(hxz), hx = warp_sum_d(hx);
-            hyy = warp_sum_d(hyy), hyz = warp_sum_d(hyz), hy = warp_sum_d(hy);
-            hzz = warp_sum_d(hzz), hz = warp_sum_d(hz), hc = warp_sum_d(hc);
-            double Hm[16], Hi[16];
-            Hm[0] = hxx + 5, Hm[4] = hxy, Hm[8] = hxz, Hm[12] = hx;
-            Hm[1] = hxy, Hm[5] = hyy + 5, Hm[9] = hyz, Hm[13] = hy;
-            Hm[2] = hxz, Hm[6] = hyz, Hm[10] = hzz + 5, Hm[14] = hz;
-            Hm[3] = hx, Hm[7] = hy, Hm[11] = hz, Hm[15] = hc + 5;
-            inverse4d(Hm, Hi);
-            const double u0 = ((Hi[0] * j0 + Hi[4] * j1) + Hi[8] * j2) + Hi[12] * j3;
-            const double u1 = ((Hi[1] * j0 + Hi[5] * j1) + Hi[9] * j2) + Hi[13] * j3;
-            const double u2 = ((Hi[2] * j0 + Hi[6] * j1) + Hi[10] * j2) + Hi[14] * j3;
-            const double u3 = ((Hi[3] * j0 + Hi[7] * j1) + Hi[11] * j2) + Hi[15] * j3;
-            nx = (float)((double)nx - u0);
-            ny = (float)((double)ny - u1);
-            nz = (float)((double)nz - u2);
-            nb = (float)((double)nb - u3);
+            const double hh[10] = {hxx + 5, hxy, hxz, hx, hyy + 5, hyz, hy, hzz + 5, hz, hc + 5}; // LM damping (:172-175)
+            const double jj[4] = {j0, j1, j2, j3};
+            double u[4];
+            solve4_spd(hh, jj, u);
+            nx = (float)((double)nx - u[0]);
+            ny = (float)((double)ny - u[1]);
+            nz = (float)((double)nz - u[2]);
+            nb = (float)((double)nb - u[3]);
         }
         nb = nb - (nx * mxs + ny * mys + nz * mzs);
         const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
@@ -751,8 +794,8 @@ __global__ void __launch_bounds__(256) k_plane_fit(const __grid_constant__ DsmDe
         nz /= nl;
         nb /= nl;
         // centre of the superpixel projected onto the fitted plane (:884-895)
-        const float axf = (sd.x - cx) / fx * sd.w;
-        const float ayf = (sd.y - cy) / fy * sd.w;
+        const float axf = (sd.x - d.cx) / d.fx * sd.w;
+        const float ayf = (sd.y - d.cy) / d.fy * sd.w;
         double ax = (double)axf, ay = (double)ayf, az = (double)sd.w;
         const float kk = (float)(-1 * (ax * (double)nx + ay * (double)ny + az * (double)nz) - (double)nb);
         ax += (double)(kk * nx);
@@ -769,15 +812,12 @@ __global__ void __launch_bounds__(256) k_plane_fit(const __grid_constant__ DsmDe
         }
         r0 = make_float4(nx, ny, nz, view_cos);
         r1 = make_float4((float)ax, (float)ay, (float)az, mean_depth);
-        r2.x = sqrtf(max_dist);
+        r2.x = sqrtf(my_maxd);
     }
-    if (lane == 0)
-    {
-        float4 *pl = d.plane + (so + s) * 3;
-        pl[0] = r0;
-        pl[1] = r1;
-        pl[2] = r2;
-    }
+    float4 *pl = d.plane + (so + s) * 3;
+    pl[0] = r0;
+    pl[1] = r1;
+    pl[2] = r2;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1014,10 +1054,16 @@ void dsm_launch_commit_seeds(const DsmDev &d, int nb, cudaStream_t s)
     dim3 grid((d.S + 255) / 256, nb);
     k_commit_seeds<<<grid, 256, 0, s>>>(d);
 }
+void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s)
+{
+    dim3 block(64, 4);
+    dim3 grid((d.Wp + 255) / 256, (d.H + 3) / 4, nb);
+    k_pixel_normals<<<grid, block, 0, s>>>(d);
+}
 void dsm_launch_plane_fit(const DsmDev &d, int nb, cudaStream_t s)
 {
-    dim3 grid((d.S + 7) / 8, nb);
-    k_plane_fit<<<grid, 256, 0, s>>>(d);
+    dim3 grid((d.S + 31) / 32, nb);
+    k_plane_fit<<<grid, 32, 0, s>>>(d);
 }
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s)
 {
