@@ -230,10 +230,11 @@ def kernel_alg_bytes(name, P, S, npool, nnew):
         "slic_assign_first": 5 * P + 4 * P + 24 * S,
         "slic_assign": 5 * P + 8 * P + 28 * S,
         "stable_relax": 0,
-        "slic_update": 9 * P + 20 * S + 20 * S,
-        "seed_commit": 24 * S + 28 * S,
+        "slic_gather_depths": 9 * P + 4 * S + 20 * S + 4 * 0.9 * P,
+        "slic_newton": 4 * 0.9 * P + 40 * S + 28 * S,
         "pixel_normals": 4 * P + 12 * P,
-        "seed_plane_fit": 8 * P + 12 * P + 16 * S + 48 * S,
+        "plane_gather_points": 8 * P + 12 * P + 16 * S + 32 * S + 12 * 0.9 * P,
+        "plane_gauss_newton": 12 * 0.9 * P + 48 * S + 48 * S,
         "surfel_fuse": 88 * npool + 48 * S,
         "surfel_init": 52 * S + 44 * nnew,
     }.get(name, 0)
@@ -315,7 +316,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ctx.profile_enable(0x5FF)
+    ctx.profile_enable(0xDFF)
     ctx.profile_reset()
     for _ in range(max(args.warmup, 3)):
         step()

@@ -24,7 +24,7 @@ EXPORTS = [
     "dsm_version", "dsm_strerror", "dsm_last_error", "dsm_create", "dsm_destroy", "dsm_num_seeds",
     "dsm_fuse_frame", "dsm_batch_upload", "dsm_batch_run", "dsm_batch_download", "dsm_sync",
     "dsm_fuse_batch", "dsm_batch_restore_pool", "dsm_get_labels", "dsm_get_seeds",
-    "dsm_debug_stop_after", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
+    "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
 ]
 
 
@@ -75,6 +75,7 @@ def load_library():
     L.dsm_get_labels.argtypes = [vp, ci, vp]
     L.dsm_get_seeds.argtypes = [vp, ci, vp]
     L.dsm_debug_stop_after.argtypes = [vp, ci]
+    L.dsm_debug_invariant_violations.argtypes = [vp, ctypes.POINTER(ci)]
     L.dsm_profile_enable.argtypes = [vp, ctypes.c_uint32]
     L.dsm_profile_reset.argtypes = [vp]
     L.dsm_profile_read.argtypes = [vp, vp, vp]
@@ -183,6 +184,11 @@ class Context:
 
     def debug_stop_after(self, n):
         self._ck(self.lib.dsm_debug_stop_after(self.h, int(n)))
+
+    def invariant_violations(self):
+        c = ctypes.c_int(0)
+        self._ck(self.lib.dsm_debug_invariant_violations(self.h, ctypes.byref(c)))
+        return c.value
 
     # ---- measurement ----
     def profile_enable(self, mask):

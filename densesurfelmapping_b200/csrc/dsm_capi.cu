@@ -50,8 +50,8 @@ struct dsm_ctx
 };
 
 static const char *kKernelNames[DSM_NUM_KERNELS] = {
-    "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_update", "seed_commit",
-    "seed_plane_fit", "surfel_fuse", "surfel_init", "seeds_export", "pixel_normals", "reserved1"};
+    "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_gather_depths", "slic_newton",
+    "plane_gather_points", "surfel_fuse", "surfel_init", "seeds_export", "pixel_normals", "plane_gauss_newton"};
 
 #define CK(call)                                                                                         \
     do                                                                                                   \
@@ -113,9 +113,12 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(d.seed);
     cudaFree(d.inv_md);
     cudaFree(d.tstable);
-    cudaFree(d.cand);
-    cudaFree(d.cflag);
-    cudaFree(d.abortc);
+    cudaFree(d.usum);
+    cudaFree(d.und);
+    cudaFree(d.dlist);
+    cudaFree(d.errflag);
+    cudaFree(d.qlist);
+    cudaFree(d.pfsum);
     cudaFree(d.plane);
     cudaFree(d.fused);
     cudaFree(d.list);
@@ -132,7 +135,6 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(d.nrm);
     cudaFree(ctx->kx);
     cudaFree(ctx->ky);
-    cudaFree(d.pflist);
     cudaFreeHost(ctx->h_pose);
     cudaFreeHost(ctx->h_ofs);
     cudaFreeHost(ctx->h_ref);
@@ -199,9 +201,12 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.seed, (size_t)B * S);
     ALLOC(d.inv_md, (size_t)B * S);
     ALLOC(d.tstable, (size_t)B * S);
-    ALLOC(d.cand, (size_t)B * S);
-    ALLOC(d.cflag, (size_t)B * S);
-    ALLOC(d.abortc, (size_t)B * 16);
+    ALLOC(d.usum, (size_t)B * S);
+    ALLOC(d.und, (size_t)B * S);
+    ALLOC(d.dlist, (size_t)B * 228 * S);
+    ALLOC(d.errflag, (size_t)B);
+    ALLOC(d.qlist, (size_t)3 * B * 228 * S);
+    ALLOC(d.pfsum, (size_t)B * S * 2);
     ALLOC(d.plane, (size_t)B * S * 3);
     ALLOC(d.fused, (size_t)B * S);
     ALLOC(d.list, B * px);
@@ -218,7 +223,6 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.nrm, 3 * (B * px) + 64);
     ALLOC(ctx->kx, (size_t)Wp + 16);
     ALLOC(ctx->ky, (size_t)H + 16);
-    ALLOC(d.pflist, (size_t)B * ((S + 31) / 32) * 232 * 32);
 #undef ALLOC
     d.nrm_plane = B * px;
     if (e == cudaSuccess)
@@ -460,11 +464,12 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
             STEP(DSM_K_ASSIGN, dsm_launch_assign(d, nb, false, st));
             STEP(DSM_K_RELAX, dsm_launch_relax(d, nb, st));
         }
-        STEP(DSM_K_UPDATE_SEEDS, dsm_launch_update_seeds(d, nb, st));
-        STEP(DSM_K_COMMIT_SEEDS, dsm_launch_commit_seeds(d, nb, st));
+        STEP(DSM_K_GATHER_DEPTHS, dsm_launch_gather_depths(d, nb, st));
+        STEP(DSM_K_NEWTON, dsm_launch_newton(d, nb, st));
     }
     STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
-    STEP(DSM_K_PLANE_FIT, dsm_launch_plane_fit(d, nb, st));
+    STEP(DSM_K_GATHER_POINTS, dsm_launch_gather_points(d, nb, st));
+    STEP(DSM_K_GAUSS_NEWTON, dsm_launch_gauss_newton(d, nb, st));
     if (d.max_pool_per_frame > 0)
     {
         STEP(DSM_K_FUSE, dsm_launch_fuse(d, nb, st));
@@ -480,6 +485,20 @@ extern "C" int dsm_debug_stop_after(dsm_ctx *ctx, int n)
 {
     if (!ctx) return DSM_E_INVALID;
     ctx->stop_after = n;
+    return DSM_OK;
+}
+
+extern "C" int dsm_debug_invariant_violations(dsm_ctx *ctx, int *count)
+{
+    if (!ctx || !count) return DSM_E_INVALID;
+    if (!ctx->ran) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int32_t> h((size_t)ctx->nb);
+    CK(cudaMemcpyAsync(h.data(), ctx->d.errflag, (size_t)ctx->nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int c = 0;
+    for (int v : h) c += v;
+    *count = c;
     return DSM_OK;
 }
 
@@ -575,7 +594,7 @@ extern "C" int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds)
     if (!ctx || !seeds || frame < 0 || frame >= ctx->p.max_batch) return DSM_E_INVALID;
     if (!ctx->ran) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < 14) ? 1 : 0, ctx->stream);
+    dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < 15) ? 1 : 0, ctx->stream);
     CK(cudaMemcpyAsync(seeds, ctx->seed_export, (size_t)ctx->S * sizeof(dsm_seed_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());

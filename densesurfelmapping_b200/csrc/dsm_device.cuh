@@ -8,12 +8,13 @@
 //   inv_md  f64 [B][S]          1.0 / mean_depth, hoisted out of calculate_cost (:380)
 //   tstable i32 [B][S]          stable flag + raster time stamp: INT_MAX = stable,
 //                               -1 = unstable, k >= 0 = un-stabled when raster scan reached k
-//   cand    float4 [B][S]       update_seeds results before the chunk-abort commit (H3)
-//   cflag   i32 [B][S]          bit0 new-stable, bit1 processed
-//   abortc  i32 [B][16]         per 10-way chunk: first seed index that hit `return` (:516)
+//   usum    int4 [B][S], und i32 [B][S]   update_seeds integer sums / depth-list lengths
+//   dlist   f32 [B][228][S]     member depths in raster order (K2a -> K2b), [k][seed]
+//   errflag i32 [B]             invariant violations (must stay 0)
 //   nrm     f32 [3][B][H][Wp]   pixel normals (K3 -> K4), 12 B/px instead of the reference's 36 B/px
 //   kx, ky  f32 [Wp+16], [H+16] back-projection factors, computed once per context
-//   pflist  float4 [B][S/32][232][32]  plane-fit inlier points, [k][seed] so thread-per-seed reads coalesce
+//   qlist   f32 [3][B][228][S]  centred plane-fit inlier points (K4a -> K4b), [k][seed]
+//   pfsum   float4 [B][S][2]    per-seed plane-fit summary
 //   plane   float4 [B][S][3]    (n.xyz, view_cos) (posi.xyz, mean_depth) (size, I, x, y)
 //   fused   i32 [B][S]          Superpixel_seed::fused
 //   list    int2 [B][P]         pixels owned by stable seeds: (pitched raster index, winner)
@@ -45,15 +46,17 @@ struct DsmDev
     float4 *seed;
     double *inv_md;
     int32_t *tstable;
-    float4 *cand;
-    int32_t *cflag;
-    int32_t *abortc;
+    int4 *usum;         // update_seeds integer sums per seed: (count, sum x, sum y, sum intensity)
+    int32_t *und;       // number of member depths > 0.1
+    float *dlist;       // [B][DL_CAP][S] member depths in raster order, [k][seed] so thread-per-seed reads coalesce
+    int32_t *errflag;   // [B] count of "impossible" events (non-stable seed without members)
     float4 *plane;
     float *nrm;         // pixel normals, 3 planes of B*px_stride floats (x | y | z)
     size_t nrm_plane;   // B * px_stride
     const float *kx;    // [Wp+16]: ((float)u - cx) / fx, the per-column factor of back_project (:94)
     const float *ky;    // [H+16]:  ((float)v - cy) / fy
-    float4 *pflist;     // plane-fit scratch: [B][ceil(S/32)][PF_CAP][32] inlier points
+    float *qlist;       // plane-fit scratch: 3 planes [B][PF_CAP][S] of centred inlier points
+    float4 *pfsum;      // [B][S][2]: (sum n.xyz, max_dist) (mean.xyz, inlier count or 0 if rejected)
     int32_t *fused;
     int2 *list;
     int32_t *nlist;
@@ -73,24 +76,25 @@ enum DsmKernelId
     DSM_K_ASSIGN_FIRST = 1,
     DSM_K_ASSIGN = 2,
     DSM_K_RELAX = 3,
-    DSM_K_UPDATE_SEEDS = 4,
-    DSM_K_COMMIT_SEEDS = 5,
-    DSM_K_PLANE_FIT = 6,
+    DSM_K_GATHER_DEPTHS = 4,
+    DSM_K_NEWTON = 5,
+    DSM_K_GATHER_POINTS = 6,
     DSM_K_FUSE = 7,
     DSM_K_INIT_SURFELS = 8,
     DSM_K_SEEDS_EXPORT = 9,
     DSM_K_PIXEL_NORMALS = 10,
-    DSM_K_RESERVED1 = 11,
+    DSM_K_GAUSS_NEWTON = 11,
 };
 
 // launchers (dsm_kernels.cu); nb = frames in this batch
 void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s);
 void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_update_seeds(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_commit_seeds(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_plane_fit(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_gather_points(const DsmDev &d, int nb, cudaStream_t s);
+void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, int raw_md, cudaStream_t s);

@@ -21,6 +21,22 @@
 
 #define FULL 0xffffffffu
 
+// Comparisons of a float against a double literal (the reference promotes the float): for a
+// literal c that is not a float, with c_lo/c_hi the neighbouring floats,
+//   (double)x <  c  <=>  x <  c_hi        (double)x >  c  <=>  x >  c_lo
+//   (double)x >= c  <=>  x >= c_hi        (double)x <= c  <=>  x <= c_lo
+// and for -c by symmetry (x > -c <=> x > -c_hi).  Used in the hot loops to keep the FP64 pipe for
+// the arithmetic that really needs it; tests/test_abi.py re-derives every constant.
+#define F_0p4_HI __uint_as_float(0x3ecccccdu)
+#define F_0p4_LO __uint_as_float(0x3eccccccu)
+#define F_0p1_HI __uint_as_float(0x3dcccccdu)
+#define F_0p1_LO __uint_as_float(0x3dccccccu)
+#define F_0p01_HI __uint_as_float(0x3c23d70bu)
+#define F_0p01_LO __uint_as_float(0x3c23d70au)
+#define F_0p05_LO __uint_as_float(0x3d4cccccu)
+#define F_0p2_HI __uint_as_float(0x3e4ccccdu)
+#define F_0p8_HI __uint_as_float(0x3f4ccccdu)
+
 // -------------------------------------------------------------------------------------------
 // small helpers
 // -------------------------------------------------------------------------------------------
@@ -71,14 +87,11 @@ __global__ void __launch_bounds__(256) k_seed_init(const __grid_constant__ DsmDe
 {
     const int b = blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && threadIdx.x < 16)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
     {
-        d.abortc[b * 16 + threadIdx.x] = INT_MAX;
-        if (threadIdx.x == 0)
-        {
-            d.nlist[b] = 0;
-            d.nnew[b] = 0;
-        }
+        d.nlist[b] = 0;
+        d.nnew[b] = 0;
+        d.errflag[b] = 0;
     }
     if (s >= d.S) return;
     const int W = d.W, H = d.H, Wp = d.Wp;
@@ -144,9 +157,15 @@ __device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pi
 {
     const float ax = sd.x - (float)x, ay = sd.y - (float)y;
     const float dist = ax * ax + ay * ay;
-    float n = dist / 16.0f; // (SP_SIZE/2)^2, exact power of two (:374)
+    float n = dist * 0.0625f; // / (SP_SIZE/2)^2, exact power of two (:374)
     const float idf = sd.I - pix_i;
-    n = (float)((double)n + (double)(idf * idf) / 100.0); // (:376)
+    // (double)(idf*idf) / 100.0 (:376), correctly rounded without the division subroutine:
+    // q0 = RN(a*y), r = a - 100*q0 (exact in one FMA), q = RN(q0 + r*y) with y = RN(1/100) is the
+    // correctly rounded quotient (Markstein); checked against x/100.0 on 3.7e8 inputs.
+    const double a = (double)(idf * idf);
+    const double q0 = a * 0.01;
+    const double q = __fma_rn(__fma_rn(-q0, 100.0, a), 0.01, q0);
+    n = (float)((double)n + q);
     nodepth = n;
     withdepth = n;
     if (sd.md > 0 && pix_inv > 0)
@@ -166,8 +185,6 @@ __global__ void __launch_bounds__(256) k_assign(const __grid_constant__ DsmDev d
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int lane = threadIdx.x & 31;
     const bool active = (x4 < d.W) && (y < d.H);
-    // re-arm the chunk-abort slots for the update_seeds pass that follows this one
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0 && threadIdx.x < 16) d.abortc[b * 16 + threadIdx.x] = INT_MAX;
 
     const size_t fo = (size_t)b * d.px_stride;
     const size_t so = (size_t)b * d.S;
@@ -213,8 +230,10 @@ __global__ void __launch_bounds__(256) k_assign(const __grid_constant__ DsmDev d
             const int x = x4 + i;
             if (x >= d.W) continue;
             const float my_i = gi[i];
+            // (:404-405) my_inv = (float)(1.0 / (double)depth) for depth > 0.01.  53 >= 2*24+2 bits, so the
+            // double rounding is innocuous and the IEEE float reciprocal gives the same value.
             float my_inv = 0.0f;
-            if ((double)zi[i] > 0.01) my_inv = (float)(1.0 / (double)zi[i]); // (:404-405)
+            if (zi[i] > F_0p01_LO) my_inv = (zi[i] < 1e30f) ? __fdiv_rn(1.0f, zi[i]) : (float)(1.0 / (double)zi[i]);
             float min_d = 1e6f, min_nd = 1e6f;
             int idx_d = -1, idx_nd = -1;
             bool all_has_depth = true;
@@ -338,140 +357,154 @@ __global__ void __launch_bounds__(1024) k_relax(const __grid_constant__ DsmDev d
 }
 
 // -------------------------------------------------------------------------------------------
-// K2  slic_update — update_seeds_kernel (:468-562)
+// K2  slic_update — update_seeds_kernel (:468-562), as two kernels
 //
-// Block = 32 consecutive seeds.  Phase A (8 warps x 4 seeds): a warp scans the seed's clamped
-// 16x16 window (lane = 2*row + half, 8 pixels per lane = raster order), reduces the exactly
-// representable integer sums with REDUX, and ballot/scan-compacts the member depths (> 0.1) in
-// RASTER ORDER into shared memory.  Phase B (warp 0, lane = seed): the label-affecting float
-// sums — sum_depth (:511) and the Huber-Newton sum_a (:536-549) — are order-sensitive (H2), so
-// each lane walks its seed's list sequentially exactly like the reference.  Results go to a
-// candidate buffer; k_commit_seeds applies the reference's chunk-abort rule (H3).
-// Shared list layout: element k of seed sl at dl[k*32 + ((sl+k)&31)]: conflict-free both for
-// phase A (fixed seed, consecutive k) and phase B (fixed k, 32 seeds).
+// K2a k_gather_depths (warp per seed): scans the seed's clamped 16x16 window (lane = 2*row+half,
+//   8 pixels per lane = raster order), reduces the exactly representable integer sums (count,
+//   sum x, sum y, sum intensity: all < 2^24, so the reference's float accumulation is exact and
+//   order-free) with REDUX, and scan-compacts the member depths (> 0.1) IN RASTER ORDER into a
+//   global list laid out [k][seed].
+// K2b k_newton (thread per seed): the label-affecting float sums -- sum_depth (:511) and the
+//   Huber-Newton sum_a (:536-549) -- are order-sensitive, so one thread walks its
+//   seed's list sequentially exactly like the reference; 32 neighbouring seeds read the [k][seed]
+//   list with coalesced loads and all seeds of a batch are in flight at once, which hides the
+//   dependent-add latency.
+// The reference's early `return` for a non-stable seed without members (:516-517) cannot
+// fire for a supported shape: the pixel at (8sx+4, 8sy+4) has seed s as its ONLY candidate
+// (x%8 == y%8 == 4) and lies inside the counted window, so every seed always owns >= 1 pixel
+// (tests/test_oracle.py::test_every_seed_keeps_its_centre_pixel).  The kernel still counts such an
+// event in errflag so that the parity tests would expose it.
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_update_seeds(const __grid_constant__ DsmDev d)
+#define DL_CAP 228 // >= 15*15 possible members
+
+__global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ DsmDev d)
 {
-    __shared__ float dl[256 * 32];
-    __shared__ int s_cnt[32], s_sx[32], s_sy[32], s_si[32], s_nd[32];
     const int b = blockIdx.y;
-    const int seed0 = blockIdx.x * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = d.W, H = d.H, Wp = d.Wp;
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= d.S) return;
     const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
+    if (d.tstable[so + s] == DSM_STABLE) return; // stable seeds are skipped (:478-479)
+    const int W = d.W, H = d.H, Wp = d.Wp;
     const int32_t *labels = d.labels + fo;
     const float *depth = d.depth + fo;
     const uint8_t *gray = d.gray + fo;
-
-    for (int q = 0; q < 4; q++)
+    const int sp_x = s % d.spw, sp_y = s / d.spw;
+    const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
+    const int xb = x0 > 0 ? x0 : 0, yb = y0 > 0 ? y0 : 0;
+    const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
+    const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
+    const int y = y0 + (lane >> 1);
+    const int xs = x0 + 8 * (lane & 1);
+    unsigned m = 0, mdm = 0;
+    float dv[8];
+    int sumx = 0, sumi = 0;
+    if (y >= yb && y < ye)
     {
-        const int sl = warp * 4 + q;
-        const int s = seed0 + sl;
-        if (s >= d.S || d.tstable[so + s] == DSM_STABLE)
-        { // stable seeds are skipped (:478-479)
-            if (lane == 0) s_cnt[sl] = -1;
-            continue;
-        }
-        const int sp_x = s % d.spw, sp_y = s / d.spw;
-        const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
-        const int xb = x0 > 0 ? x0 : 0, yb = y0 > 0 ? y0 : 0;
-        const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
-        const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
-        const int y = y0 + (lane >> 1);
-        const int xs = x0 + 8 * (lane & 1);
-        unsigned m = 0, mdm = 0;
-        float dv[8];
-        int sumx = 0, sumi = 0;
+        // all six 16-byte loads are issued before any of them is consumed
+        int4 l4[2];
+        float4 z4[2];
+        uchar4 g4[2];
 #pragma unroll
-        for (int k = 0; k < 8; k++) dv[k] = 0.f;
-        if (y >= yb && y < ye)
+        for (int h2 = 0; h2 < 2; h2++)
         {
+            const int xq = xs + 4 * h2;
+            const bool in = xq >= 0 && xq < Wp;
+            const size_t po = (size_t)y * Wp + (in ? xq : 0);
+            l4[h2] = in ? *reinterpret_cast<const int4 *>(labels + po) : make_int4(-1, -1, -1, -1);
+            z4[h2] = in ? *reinterpret_cast<const float4 *>(depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[h2] = in ? *reinterpret_cast<const uchar4 *>(gray + po) : make_uchar4(0, 0, 0, 0);
+        }
 #pragma unroll
-            for (int h2 = 0; h2 < 2; h2++)
+        for (int h2 = 0; h2 < 2; h2++)
+        {
+            const int xq = xs + 4 * h2;
+            const int lk[4] = {l4[h2].x, l4[h2].y, l4[h2].z, l4[h2].w};
+            const float zk[4] = {z4[h2].x, z4[h2].y, z4[h2].z, z4[h2].w};
+            const int gk[4] = {g4[h2].x, g4[h2].y, g4[h2].z, g4[h2].w};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
             {
-                const int xq = xs + 4 * h2;
-                if (xq < 0 || xq >= Wp) continue;
-                const int4 l4 = *reinterpret_cast<const int4 *>(labels + (size_t)y * Wp + xq);
-                if (l4.x != s && l4.y != s && l4.z != s && l4.w != s) continue;
-                const float4 z4 = *reinterpret_cast<const float4 *>(depth + (size_t)y * Wp + xq);
-                const uchar4 g4 = *reinterpret_cast<const uchar4 *>(gray + (size_t)y * Wp + xq);
-                const int lk[4] = {l4.x, l4.y, l4.z, l4.w};
-                const float zk[4] = {z4.x, z4.y, z4.z, z4.w};
-                const int gk[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++)
+                const int x = xq + k;
+                const bool mem = lk[k] == s && x >= xb && x < xe;
+                dv[h2 * 4 + k] = zk[k];
+                if (mem)
                 {
-                    const int x = xq + k;
-                    if (lk[k] == s && x >= xb && x < xe)
-                    {
-                        m |= 1u << (h2 * 4 + k);
-                        sumx += x;
-                        sumi += gk[k];
-                        if ((double)zk[k] > 0.1) mdm |= 1u << (h2 * 4 + k);
-                        dv[h2 * 4 + k] = zk[k];
-                    }
+                    m |= 1u << (h2 * 4 + k);
+                    sumx += x;
+                    sumi += gk[k];
+                    if (zk[k] > F_0p1_LO) mdm |= 1u << (h2 * 4 + k); // (double)depth > 0.1 (:508)
                 }
             }
         }
-        const int cnt_lane = __popc(m);
-        const int cnt = __reduce_add_sync(FULL, cnt_lane);
-        const int tsx = __reduce_add_sync(FULL, sumx);
-        const int tsy = __reduce_add_sync(FULL, cnt_lane * y);
-        const int tsi = __reduce_add_sync(FULL, sumi);
-        int ndt;
-        int pos = warp_excl_scan(__popc(mdm), lane, ndt);
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if ((mdm >> k) & 1u)
-            {
-                dl[pos * 32 + ((sl + pos) & 31)] = dv[k];
-                pos++;
-            }
-        if (lane == 0)
-        {
-            s_cnt[sl] = cnt;
-            s_sx[sl] = tsx;
-            s_sy[sl] = tsy;
-            s_si[sl] = tsi;
-            s_nd[sl] = ndt;
-        }
     }
-    __syncthreads();
-    if (warp != 0) return;
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 8; k++) dv[k] = 0.f;
+    }
+    const int cnt_lane = __popc(m);
+    const int cnt = __reduce_add_sync(FULL, cnt_lane);
+    const int tsx = __reduce_add_sync(FULL, sumx);
+    const int tsy = __reduce_add_sync(FULL, cnt_lane * y);
+    const int tsi = __reduce_add_sync(FULL, sumi);
+    int ndt;
+    int pos = warp_excl_scan(__popc(mdm), lane, ndt);
+    float *dl = d.dlist + (size_t)b * DL_CAP * d.S + s;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if ((mdm >> k) & 1u)
+        {
+            dl[(size_t)pos * d.S] = dv[k];
+            pos++;
+        }
+    if (lane == 0)
+    {
+        d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
+        d.und[so + s] = ndt;
+    }
+}
 
-    // ---- phase B: lane == seed-in-block
-    const int sl = lane;
-    const int s = seed0 + sl;
+__global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d)
+{
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.nlist[b] = 0; // the deferred-pixel list of this pass is consumed
     if (s >= d.S) return;
-    const int n = s_cnt[sl];
-    if (n < 0) return; // stable
+    const size_t so = (size_t)b * d.S;
+    if (d.tstable[so + s] == DSM_STABLE) return; // untouched by update_seeds
+    const int4 su = d.usum[so + s];
+    const int n = su.x;
     if (n == 0)
-    { // the reference `return`s here, abandoning the rest of this thread's chunk (:516-517, H3)
-        atomicMin(&d.abortc[b * 16 + chunk_of(s, d.S)], s);
+    { // unreachable for supported shapes (see above); recorded, never silently ignored
+        atomicAdd(&d.errflag[b], 1);
+        d.tstable[so + s] = -1;
         return;
     }
     const float fn = (float)n; // sums below are < 2^24 so the reference's float accumulation is exact
-    const float mi = (float)s_si[sl] / fn;
-    const float mx = (float)s_sx[sl] / fn;
-    const float my = (float)s_sy[sl] / fn;
+    const float mi = (float)su.w / fn;
+    const float mx = (float)su.y / fn;
+    const float my = (float)su.z / fn;
     const float4 pre = d.seed[so + s];
     // ::fabs(double): float differences, summed in double, rounded once (:527)
     const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
-    const int newstable = ((double)diff < 0.2) ? 1 : 0;
-    const int nd = s_nd[sl];
+    const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
+    const int nd = d.und[so + s];
     float md = 0.0f;
     if (nd > 0)
     {
+        const float *dl = d.dlist + (size_t)b * DL_CAP * d.S + s;
+        const size_t st = (size_t)d.S;
         float sum_d = 0.0f;
-        for (int k = 0; k < nd; k++) sum_d += dl[k * 32 + ((sl + k) & 31)]; // raster order (:511)
+        for (int k = 0; k < nd; k++) sum_d += dl[k * st]; // raster order (:511)
         md = sum_d / (float)nd;
         for (int it = 0; it < 5; it++)
         { // damped Huber-Newton (:534-554)
             float sa = 0.0f, sb = 0.0f;
             for (int k = 0; k < nd; k++)
             {
-                const float r = md - dl[k * 32 + ((sl + k) & 31)];
-                if ((double)r < HUBER_RANGE && (double)r > -HUBER_RANGE)
+                const float r = md - dl[k * st];
+                if (r < F_0p4_HI && r > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
                 {
                     sa += 2 * r;
                     sb += 2;
@@ -481,35 +514,12 @@ __global__ void __launch_bounds__(256) k_update_seeds(const __grid_constant__ Ds
             }
             const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
             md = md + delta;
-            if ((double)delta < 0.01 && (double)delta > -0.01) break;
+            if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
         }
     }
-    d.cand[so + s] = make_float4(mx, my, mi, md);
-    d.cflag[so + s] = newstable;
-}
-
-// -------------------------------------------------------------------------------------------
-// K2c commit — applies update_seeds results subject to the chunk-abort rule (H3), refreshes the
-// hoisted 1/mean_depth, normalises the stable stamps for the next pass and clears the list.
-// -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_commit_seeds(const __grid_constant__ DsmDev d)
-{
-    const int b = blockIdx.y;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.nlist[b] = 0;
-    if (s >= d.S) return;
-    const size_t o = (size_t)b * d.S + s;
-    const int t = d.tstable[o];
-    if (t == DSM_STABLE) return; // untouched by update_seeds
-    int nt = -1;
-    if (s < d.abortc[b * 16 + chunk_of(s, d.S)])
-    {
-        const float4 c = d.cand[o];
-        d.seed[o] = c;
-        d.inv_md[o] = 1.0 / (double)c.w;
-        if (d.cflag[o] & 1) nt = DSM_STABLE;
-    }
-    d.tstable[o] = nt;
+    d.seed[so + s] = make_float4(mx, my, mi, md);
+    d.inv_md[so + s] = 1.0 / (double)md;
+    d.tstable[so + s] = newstable ? DSM_STABLE : -1;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -550,7 +560,7 @@ __global__ void __launch_bounds__(256) k_pixel_normals(const __grid_constant__ D
             const int x = x4 + i;
             if (x < 1 || x > W - 2) continue;
             const float mz = z[i], rz = z[i + 1], dz = zd[i];
-            if ((double)mz < 0.1 || (double)rz < 0.1 || (double)dz < 0.1) continue; // (:688)
+            if (mz < F_0p1_HI || rz < F_0p1_HI || dz < F_0p1_HI) continue; // (double)z < 0.1 (:688)
             const float mx = kx[i] * mz, my = ky0 * mz;
             const float rx = kx[i + 1] * rz - mx, ry = ky0 * rz - my, rzz = rz - mz;
             const float dx = kx[i] * dz - mx, dy = ky1 * dz - my, dzz = dz - mz;
@@ -562,7 +572,7 @@ __global__ void __launch_bounds__(256) k_pixel_normals(const __grid_constant__ D
             cyn /= len;
             czn /= len;
             const float view = (cxn * mx + cyn * my + czn * mz) / sqrtf(mx * mx + my * my + mz * mz);
-            if ((double)view > -MAX_ANGLE_COS && (double)view < MAX_ANGLE_COS) continue; // (:706)
+            if (view > -F_0p1_HI && view < F_0p1_HI) continue; // |view| < 0.1 in double (:706)
             nx[i] = cxn, ny[i] = cyn, nz[i] = czn;
         }
     }
@@ -572,20 +582,23 @@ __global__ void __launch_bounds__(256) k_pixel_normals(const __grid_constant__ D
 }
 
 // -------------------------------------------------------------------------------------------
-// K4  seed_plane_fit — calculate_sp_depth_norms_kernel (:792-914) + get_huber_norm (:104-188)
+// K4  seed_plane_fit — calculate_sp_depth_norms_kernel (:792-914) + get_huber_norm (:104-188),
+// as two kernels
 //
-// One warp owns 32 consecutive superpixels and works in two phases:
-//  A (warp per seed, 32 seeds in turn): scan the 16x16 window (lane = 2*row+half, 8 px/lane),
-//    count valid depths (> 0.05), find max_dist, classify inliers |mean_depth-d| < 0.4, reduce the
-//    inlier normal / position sums with shuffles, and scan-compact the inlier points into a
-//    global scratch list laid out [k][32 seeds] of float4 so that phase B reads are coalesced.
-//    Lane sl keeps seed sl's summary in registers.
-//  B (thread per seed): the five damped Gauss-Newton steps.  Each lane streams its own seed's
-//    points (one coalesced LDG.128 per point per warp), accumulates the 4x4 normal equations in
-//    fp64 registers -- no cross-lane reduction at all -- and solves them by symmetric
-//    elimination.  Then the superpixel centre is projected onto the plane exactly as (:884-912).
-// This stage does not feed the labels, so sums are order-free within the 1e-4 budget
-// (SURVEY.md §7 H2/H5); thresholds and float/double promotions follow the reference.
+// K4a k_gather_points (warp per seed): scans the 16x16 window (lane = 2*row+half, 8 px/lane), counts
+//   valid depths (> 0.05), finds max_dist, classifies inliers |mean_depth-d| < 0.4, reduces the
+//   inlier normal / position sums with shuffles and scan-compacts the CENTRED inlier points
+//   (get_huber_norm centres them first, :111-126) into three global planes laid out [k][seed].
+// K4b k_gauss_newton (thread per seed): the five LM-damped Gauss-Newton steps with no cross-lane
+//   traffic at all: 32 neighbouring seeds stream their lists with coalesced loads.  Algebra: for
+//   the points whose residual is inside the Huber range, sum 2 r q~ = (sum 2 q~ q~^T) theta, i.e. the
+//   in-range part of the Jacobian is H theta.  So H over ALL points is accumulated once (first pass),
+//   every pass only evaluates the float residual r exactly as (:133) to classify, and the (rare)
+//   out-of-range points contribute corrections: H_R = H_all - sum_out 2 q~ q~^T,
+//   J = H_R theta + sum_out +-0.4 q~.  Deviation from the reference: J's in-range part is formed in
+//   fp64 from H instead of summing float products 2*r*q -- a ~1e-7 relative perturbation, inside the
+//   1e-4 budget of this non-label-affecting stage; classification thresholds,
+//   promotions and the projection (:884-912) follow the reference expression by expression.
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void solve4_spd(const double *h, const double *j, double *u)
 { // h: 10 unique entries xx xy xz xw yy yz yw zz zw ww of an SPD matrix; solves H u = j
@@ -600,186 +613,201 @@ __device__ __forceinline__ void solve4_spd(const double *h, const double *j, dou
     const double i2 = 1.0 / a22;
     const double l32 = a23 * i2;
     const double a33 = a33q - l32 * a23;
-    // forward substitution (L y = j)
     const double y0 = j[0];
     const double y1 = j[1] - l10 * y0;
     const double y2 = j[2] - l20 * y0 - l21 * y1;
     const double y3 = j[3] - l30 * y0 - l31 * y1 - l32 * y2;
-    // D and back substitution
     u[3] = y3 / a33;
     u[2] = y2 * i2 - l32 * u[3];
     u[1] = y1 * i1 - l21 * u[2] - l31 * u[3];
     u[0] = y0 * i0 - l10 * u[1] - l20 * u[2] - l30 * u[3];
 }
 
-#define PF_CAP 232 // >= 15*15 possible members of a superpixel, multiple of 8
+#define PF_CAP 228 // >= 15*15 possible members of a superpixel
 
-__global__ void __launch_bounds__(32) k_plane_fit(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ DsmDev d)
 {
     const int b = blockIdx.y;
-    const int lane = threadIdx.x;
-    const int seed0 = blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= d.S) return;
     const int W = d.W, H = d.H, Wp = d.Wp;
     const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
     const int32_t *labels = d.labels + fo;
     const float *depth = d.depth + fo;
     const float *nrm = d.nrm + fo;
-    float4 *list = d.pflist + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)(PF_CAP * 32);
-
-    // per-lane summary of seed (seed0 + lane), filled in during phase A
-    int my_nvalid = 0, my_ninl = 0;
-    float my_maxd = 0.f, my_snx = 0.f, my_sny = 0.f, my_snz = 0.f, my_spx = 0.f, my_spy = 0.f, my_spz = 0.f;
-
-    const int row = lane >> 1, half = lane & 1;
-    for (int sl = 0; sl < 32; sl++)
+    const float4 sd = d.seed[so + s]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
+    const int sp_x = s % d.spw, sp_y = s / d.spw;
+    const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
+    const int y = y0 + (lane >> 1);
+    const int xs = x0 + 8 * (lane & 1);
+    float px[8], py[8], pz[8];
+    unsigned inl = 0;
+    int nvalid = 0;
+    float maxd = 0.f, snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) px[k] = py[k] = pz[k] = 0.f;
+    if (y >= 0 && y < H)
     {
-        const int s = seed0 + sl;
-        if (s >= d.S) break; // warp-uniform
-        const float4 sd = d.seed[so + s];
-        const int sp_x = s % d.spw, sp_y = s / d.spw;
-        const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
-        const int y = y0 + row;
-        const int xs = x0 + 8 * half;
-        float dv[8];
-        unsigned inl = 0;
-        int nvalid = 0;
-        float maxd = 0.f, snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
-        float kxv[8];
-        float kyv = 0.f;
+        const float kyv = d.ky[y];
+        int4 l4[2];
+        float4 z4[2], k4[2];
 #pragma unroll
-        for (int k = 0; k < 8; k++) dv[k] = 0.f, kxv[k] = 0.f;
-        if (y >= 0 && y < H)
+        for (int h2 = 0; h2 < 2; h2++)
         {
-            kyv = d.ky[y];
+            const int xq = xs + 4 * h2;
+            const bool in = xq >= 0 && xq < Wp;
+            const size_t po = (size_t)y * Wp + (in ? xq : 0);
+            l4[h2] = in ? *reinterpret_cast<const int4 *>(labels + po) : make_int4(-1, -1, -1, -1);
+            z4[h2] = in ? *reinterpret_cast<const float4 *>(depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
+            k4[h2] = in ? *reinterpret_cast<const float4 *>(d.kx + xq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-            for (int h2 = 0; h2 < 2; h2++)
+        for (int h2 = 0; h2 < 2; h2++)
+        {
+            const int xq = xs + 4 * h2;
+            const size_t po = (size_t)y * Wp + xq;
+            const int lk[4] = {l4[h2].x, l4[h2].y, l4[h2].z, l4[h2].w};
+            const float zk[4] = {z4[h2].x, z4[h2].y, z4[h2].z, z4[h2].w};
+            const float kk[4] = {k4[h2].x, k4[h2].y, k4[h2].z, k4[h2].w};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
             {
-                const int xq = xs + 4 * h2;
-                if (xq < 0 || xq >= Wp) continue;
-                const size_t po = (size_t)y * Wp + xq;
-                const int4 l4 = *reinterpret_cast<const int4 *>(labels + po);
-                if (l4.x != s && l4.y != s && l4.z != s && l4.w != s) continue;
-                const float4 z4 = *reinterpret_cast<const float4 *>(depth + po);
-                const float4 k4 = *reinterpret_cast<const float4 *>(d.kx + xq);
-                const int lk[4] = {l4.x, l4.y, l4.z, l4.w};
-                const float zk[4] = {z4.x, z4.y, z4.z, z4.w};
-                const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                {
-                    const int x = xq + k;
-                    if (lk[k] != s || x >= W) continue; // window bounded by the flat index only (:816)
-                    const float xd = (float)x - sd.x, yd = (float)y - sd.y;
-                    const float dist = xd * xd + yd * yd;
-                    if (dist > maxd) maxd = dist;
-                    const float mz = zk[k];
-                    if (!((double)mz > 0.05)) continue; // (:827)
-                    nvalid++;
-                    const float r = sd.w - mz;
-                    if ((double)r < HUBER_RANGE && (double)r > -HUBER_RANGE)
-                    { // inlier (:849-860)
-                        inl |= 1u << (h2 * 4 + k);
-                        dv[h2 * 4 + k] = mz;
-                        kxv[h2 * 4 + k] = kk[k];
-                        snx += nrm[po + k];
-                        sny += nrm[d.nrm_plane + po + k];
-                        snz += nrm[2 * d.nrm_plane + po + k];
-                        spx += kk[k] * mz; // back_project in float (:94-96)
-                        spy += kyv * mz;
-                        spz += mz;
-                    }
+                const int x = xq + k;
+                if (lk[k] != s || x >= W) continue; // window bounded by the flat index only (:816)
+                const float xd = (float)x - sd.x, yd = (float)y - sd.y;
+                const float dist = xd * xd + yd * yd;
+                if (dist > maxd) maxd = dist;
+                const float mz = zk[k];
+                if (!(mz > F_0p05_LO)) continue; // (double)depth > 0.05 (:827)
+                nvalid++;
+                const float r = sd.w - mz;
+                if (r < F_0p4_HI && r > -F_0p4_HI)
+                { // inlier (:849-860)
+                    inl |= 1u << (h2 * 4 + k);
+                    snx += nrm[po + k];
+                    sny += nrm[d.nrm_plane + po + k];
+                    snz += nrm[2 * d.nrm_plane + po + k];
+                    const float mx = kk[k] * mz, my = kyv * mz; // back_project in float (:94-96)
+                    px[h2 * 4 + k] = mx, py[h2 * 4 + k] = my, pz[h2 * 4 + k] = mz;
+                    spx += mx;
+                    spy += my;
+                    spz += mz;
                 }
             }
         }
-        maxd = warp_max_f(maxd);
-        nvalid = __reduce_add_sync(FULL, nvalid);
-        int ninl;
-        int pos = warp_excl_scan(__popc(inl), lane, ninl);
-        const bool ok = nvalid >= 16 && !((double)((float)ninl / (float)nvalid) < 0.8); // (:841, :862) warp-uniform
-        if (ok)
-        {
-            snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
-            spx = warp_sum_f(spx), spy = warp_sum_f(spy), spz = warp_sum_f(spz);
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if ((inl >> k) & 1u)
-                {
-                    list[(size_t)pos * 32 + sl] = make_float4(kxv[k] * dv[k], kyv * dv[k], dv[k], 0.f);
-                    pos++;
-                }
-        }
-        if (lane == sl)
-        {
-            my_nvalid = ok ? nvalid : 0;
-            my_ninl = ninl;
-            my_maxd = maxd;
-            my_snx = snx, my_sny = sny, my_snz = snz;
-            my_spx = spx, my_spy = spy, my_spz = spz;
-        }
     }
-    __syncwarp();
-    __threadfence_block(); // phase B reads the scratch list written by other lanes of this warp
+    maxd = warp_max_f(maxd);
+    nvalid = __reduce_add_sync(FULL, nvalid);
+    int ninl;
+    int pos = warp_excl_scan(__popc(inl), lane, ninl);
+    const bool ok = nvalid >= 16 && !((float)ninl / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
+    float4 P0 = make_float4(0.f, 0.f, 0.f, maxd), P1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+    if (ok)
+    {
+        snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
+        const float fn = (float)ninl;
+        const float mxs = warp_sum_f(spx) / fn, mys = warp_sum_f(spy) / fn, mzs = warp_sum_f(spz) / fn; // (:117-119)
+        const size_t plane = (size_t)d.B * PF_CAP * d.S;
+        float *ql = d.qlist + (size_t)b * PF_CAP * d.S + s;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if ((inl >> k) & 1u)
+            {
+                const size_t o = (size_t)pos * d.S;
+                ql[o] = px[k] - mxs; // centred points (:121-126)
+                ql[plane + o] = py[k] - mys;
+                ql[2 * plane + o] = pz[k] - mzs;
+                pos++;
+            }
+        P0 = make_float4(snx, sny, snz, maxd);
+        P1 = make_float4(mxs, mys, mzs, __int_as_float(ninl));
+    }
+    if (lane == 0)
+    {
+        d.pfsum[(so + s) * 2] = P0;
+        d.pfsum[(so + s) * 2 + 1] = P1;
+    }
+}
 
-    // ---- phase B: thread per seed
-    const int s = seed0 + lane;
+__global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ DsmDev d)
+{
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= d.S) return;
+    const size_t so = (size_t)b * d.S;
     const float4 sd = d.seed[so + s];
+    const float4 P0 = d.pfsum[(so + s) * 2], P1 = d.pfsum[(so + s) * 2 + 1];
+    const int n = __float_as_int(P1.w);
     // default record: plane fit rejected -> zero normal / position / view_cos / size (H6-i), Huber mean depth kept
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 r1 = make_float4(0.f, 0.f, 0.f, sd.w);
     float4 r2 = make_float4(0.f, sd.z, sd.x, sd.y);
-    if (my_nvalid > 0)
+    if (n > 0)
     {
-        const int n = my_ninl;
-        const float len0 = sqrtf(my_snx * my_snx + my_sny * my_sny + my_snz * my_snz);
-        float nx = my_snx / len0, ny = my_sny / len0, nz = my_snz / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
-        const float fn = (float)n;
-        const float mxs = my_spx / fn, mys = my_spy / fn, mzs = my_spz / fn;
-        const float4 *lp = list + lane;
+        const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
+        float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
+        const float mxs = P1.x, mys = P1.y, mzs = P1.z;
+        const size_t plane = (size_t)d.B * PF_CAP * d.S, st = (size_t)d.S;
+        const float *qx = d.qlist + (size_t)b * PF_CAP * d.S + s;
+        const float *qy = qx + plane, *qz = qy + plane;
+        double hall[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // xx xy xz xw yy yz yw zz zw ww over ALL points
         for (int gn = 0; gn < 5; gn++)
         {
-            double j0 = 0, j1 = 0, j2 = 0, j3 = 0;
-            double hxx = 0, hxy = 0, hxz = 0, hx = 0, hyy = 0, hyz = 0, hy = 0, hzz = 0, hz = 0, hc = 0;
-#pragma unroll 2
-            for (int k = 0; k < n; k++)
+            double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // same, over the points outside the Huber range
+            double jo[4] = {0, 0, 0, 0};
+            auto point = [&](float ax, float ay, float az)
             {
-                const float4 p = lp[(size_t)k * 32];
-                const float qx = p.x - mxs, qy = p.y - mys, qz = p.z - mzs; // centred points (:121-126)
-                const float r = qx * nx + qy * ny + qz * nz + nb;
-                if ((double)r < HUBER_RANGE && (double)r > -1 * HUBER_RANGE)
-                { // float products accumulated in double (:136-155)
-                    j0 += (double)(2 * r * qx);
-                    j1 += (double)(2 * r * qy);
-                    j2 += (double)(2 * r * qz);
-                    j3 += (double)(2 * r);
-                    hxx += (double)(2 * qx * qx);
-                    hxy += (double)(2 * qx * qy);
-                    hxz += (double)(2 * qx * qz);
-                    hx += (double)(2 * qx);
-                    hyy += (double)(2 * qy * qy);
-                    hyz += (double)(2 * qy * qz);
-                    hy += (double)(2 * qy);
-                    hzz += (double)(2 * qz * qz);
-                    hz += (double)(2 * qz);
-                    hc += 2;
-                }
-                else if ((double)r >= HUBER_RANGE)
+                const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
+                const bool inr = r < F_0p4_HI && r > -F_0p4_HI;  // (:134)
+                if (gn == 0 || !inr)
                 {
-                    j0 += HUBER_RANGE * (double)qx;
-                    j1 += HUBER_RANGE * (double)qy;
-                    j2 += HUBER_RANGE * (double)qz;
-                    j3 += HUBER_RANGE;
+                    const double t0 = (double)(2 * ax * ax), t1 = (double)(2 * ax * ay), t2 = (double)(2 * ax * az), t3 = (double)(2 * ax);
+                    const double t4 = (double)(2 * ay * ay), t5 = (double)(2 * ay * az), t6 = (double)(2 * ay);
+                    const double t7 = (double)(2 * az * az), t8 = (double)(2 * az);
+                    if (gn == 0)
+                    {
+                        hall[0] += t0, hall[1] += t1, hall[2] += t2, hall[3] += t3, hall[4] += t4;
+                        hall[5] += t5, hall[6] += t6, hall[7] += t7, hall[8] += t8, hall[9] += 2;
+                    }
+                    if (!inr)
+                    {
+                        ho[0] += t0, ho[1] += t1, ho[2] += t2, ho[3] += t3, ho[4] += t4;
+                        ho[5] += t5, ho[6] += t6, ho[7] += t7, ho[8] += t8, ho[9] += 2;
+                        if (r >= F_0p4_HI)
+                        { // (double)r >= 0.4 (:157-163)
+                            jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
+                            jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                        }
+                        else if (r <= -F_0p4_HI)
+                        { // (double)r <= -0.4 (:164-170)
+                            jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
+                            jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
+                        }
+                    }
                 }
-                else if ((double)r <= -1 * HUBER_RANGE)
-                {
-                    j0 += -1 * HUBER_RANGE * (double)qx;
-                    j1 += -1 * HUBER_RANGE * (double)qy;
-                    j2 += -1 * HUBER_RANGE * (double)qz;
-                    j3 += -1 * HUBER_RANGE;
-                }
+            };
+            int k = 0;
+            for (; k + 4 <= n; k += 4)
+            { // four points in flight: 12 coalesced loads issued before the first is consumed
+                const float a0 = qx[k * st], a1 = qx[(k + 1) * st], a2 = qx[(k + 2) * st], a3 = qx[(k + 3) * st];
+                const float b0 = qy[k * st], b1 = qy[(k + 1) * st], b2 = qy[(k + 2) * st], b3 = qy[(k + 3) * st];
+                const float c0 = qz[k * st], c1 = qz[(k + 1) * st], c2 = qz[(k + 2) * st], c3 = qz[(k + 3) * st];
+                point(a0, b0, c0);
+                point(a1, b1, c1);
+                point(a2, b2, c2);
+                point(a3, b3, c3);
             }
-            const double hh[10] = {hxx + 5, hxy, hxz, hx, hyy + 5, hyz, hy, hzz + 5, hz, hc + 5}; // LM damping (:172-175)
-            const double jj[4] = {j0, j1, j2, j3};
+            for (; k < n; k++) point(qx[k * st], qy[k * st], qz[k * st]);
+            double hh[10], jj[4];
+#pragma unroll
+            for (int i = 0; i < 10; i++) hh[i] = hall[i] - ho[i];
+            const double tx = (double)nx, ty = (double)ny, tz = (double)nz, tb = (double)nb;
+            jj[0] = ((hh[0] * tx + hh[1] * ty) + hh[2] * tz) + hh[3] * tb + jo[0];
+            jj[1] = ((hh[1] * tx + hh[4] * ty) + hh[5] * tz) + hh[6] * tb + jo[1];
+            jj[2] = ((hh[2] * tx + hh[5] * ty) + hh[7] * tz) + hh[8] * tb + jo[2];
+            jj[3] = ((hh[3] * tx + hh[6] * ty) + hh[8] * tz) + hh[9] * tb + jo[3];
+            hh[0] += 5, hh[4] += 5, hh[7] += 5, hh[9] += 5; // LM damping (:172-175)
             double u[4];
             solve4_spd(hh, jj, u);
             nx = (float)((double)nx - u[0]);
@@ -812,7 +840,7 @@ __global__ void __launch_bounds__(32) k_plane_fit(const __grid_constant__ DsmDev
         }
         r0 = make_float4(nx, ny, nz, view_cos);
         r1 = make_float4((float)ax, (float)ay, (float)az, mean_depth);
-        r2.x = sqrtf(my_maxd);
+        r2.x = sqrtf(P0.w);
     }
     float4 *pl = d.plane + (so + s) * 3;
     pl[0] = r0;
@@ -1044,15 +1072,15 @@ void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s)
         k_assign<false><<<grid, block, 0, s>>>(d);
 }
 void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s) { k_relax<<<nb, 1024, 0, s>>>(d); }
-void dsm_launch_update_seeds(const DsmDev &d, int nb, cudaStream_t s)
+void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s)
 {
-    dim3 grid((d.S + 31) / 32, nb);
-    k_update_seeds<<<grid, 256, 0, s>>>(d);
+    dim3 grid((d.S + 7) / 8, nb);
+    k_gather_depths<<<grid, 256, 0, s>>>(d);
 }
-void dsm_launch_commit_seeds(const DsmDev &d, int nb, cudaStream_t s)
+void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s)
 {
-    dim3 grid((d.S + 255) / 256, nb);
-    k_commit_seeds<<<grid, 256, 0, s>>>(d);
+    dim3 grid((d.S + 127) / 128, nb);
+    k_newton<<<grid, 128, 0, s>>>(d);
 }
 void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s)
 {
@@ -1060,10 +1088,15 @@ void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s)
     dim3 grid((d.Wp + 255) / 256, (d.H + 3) / 4, nb);
     k_pixel_normals<<<grid, block, 0, s>>>(d);
 }
-void dsm_launch_plane_fit(const DsmDev &d, int nb, cudaStream_t s)
+void dsm_launch_gather_points(const DsmDev &d, int nb, cudaStream_t s)
 {
-    dim3 grid((d.S + 31) / 32, nb);
-    k_plane_fit<<<grid, 32, 0, s>>>(d);
+    dim3 grid((d.S + 7) / 8, nb);
+    k_gather_points<<<grid, 256, 0, s>>>(d);
+}
+void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s)
+{
+    dim3 grid((d.S + 127) / 128, nb);
+    k_gauss_newton<<<grid, 128, 0, s>>>(d);
 }
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s)
 {

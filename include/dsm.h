@@ -148,6 +148,9 @@ int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds_s);   /* superpixel
 /* debug: enqueue only the first n kernels of the schedule on the next dsm_batch_run (n <= 0: all).
  * Lets the parity tests localise a mismatch to one pass; never used on the product path. */
 int dsm_debug_stop_after(dsm_ctx *ctx, int n_kernels);
+/* debug: number of "cannot happen" events the kernels counted in the last batch (a non-stable seed
+ * without members); the parity tests assert it is 0. */
+int dsm_debug_invariant_violations(dsm_ctx *ctx, int *count);
 
 /* ---- measurement hooks ----
  * Per-kernel CUDA-event timing on the context's stream.  mask selects kernels (bit k = kernel

@@ -62,3 +62,18 @@ def test_synthetic_generator_is_deterministic():
     assert 0.005 < (a[1] == 0).mean() < 0.05  # ~1 % holes + the hole block
     p = synth.pose_stream(3).reshape(4, 4).T
     assert np.allclose(p[:3, :3] @ p[:3, :3].T, np.eye(3), atol=1e-6)
+
+
+def test_float_bounds_for_double_literal_compares():
+    """csrc/dsm_kernels.cu replaces `(double)x < c` by `x < c_hi` (and `> c` by `> c_lo`) in hot loops;
+    every F_<c>_HI / _LO constant must be the float neighbour of the double literal c."""
+    src = open(os.path.join(ROOT, "densesurfelmapping_b200", "csrc", "dsm_kernels.cu")).read()
+    found = re.findall(r"#define F_(\d+)p(\d+)_(HI|LO) __uint_as_float\(0x([0-9a-f]+)u\)", src)
+    assert len(found) >= 8
+    for ip, fp, kind, hexv in found:
+        c = float(f"{ip}.{fp}")
+        f = np.array([int(hexv, 16)], dtype=np.uint32).view(np.float32)[0]
+        if kind == "HI":  # smallest float >= c (c itself is not a float)
+            assert float(f) > c and float(np.nextafter(f, np.float32(0))) < c, (c, kind, float(f))
+        else:             # largest float <= c
+            assert float(f) < c and float(np.nextafter(f, np.float32(10))) > c, (c, kind, float(f))

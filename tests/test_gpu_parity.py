@@ -32,6 +32,7 @@ def _stream(capi, cam, n_frames, flat=False, ref_div=2):
         nbad = int((lab_o != lab_g).sum())
         assert nbad == 0, f"frame {t}: {nbad} label mismatches (first at {np.argwhere(lab_o != lab_g)[:4].tolist()})"
         check_seeds(ctx.seeds(), orc.seeds())
+        assert ctx.invariant_violations() == 0
         check_surfels(lg, lo, f"frame {t} local")
         check_surfels(ng, no, f"frame {t} new")
         # carry the ORACLE's pool into both so that one tolerance-sized drift cannot compound
