@@ -186,6 +186,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->px = px;
     DsmDev &d = ctx->d;
     d.W = W, d.H = H, d.Wp = Wp, d.spw = spw, d.sph = sph, d.S = S, d.B = B;
+    d.Sp = (S + 31) / 32 * 32;
     d.fx = params->fx, d.fy = params->fy, d.cx = params->cx, d.cy = params->cy;
     d.fuse_far = params->fuse_far, d.fuse_near = params->fuse_near;
     d.camera_f = (float)((fabs((double)params->fx) + fabs((double)params->fy)) / 2.0); // (:250)
@@ -203,9 +204,9 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.tstable, (size_t)B * S);
     ALLOC(d.usum, (size_t)B * S);
     ALLOC(d.und, (size_t)B * S);
-    ALLOC(d.dlist, (size_t)B * 228 * S);
+    ALLOC(d.dlist, (size_t)B * 228 * ((S + 31) / 32 * 32));
     ALLOC(d.errflag, (size_t)B);
-    ALLOC(d.qlist, (size_t)3 * B * 228 * S);
+    ALLOC(d.qlist, (size_t)3 * B * 228 * ((S + 31) / 32 * 32));
     ALLOC(d.pfsum, (size_t)B * S * 2);
     ALLOC(d.plane, (size_t)B * S * 3);
     ALLOC(d.fused, (size_t)B * S);

@@ -36,6 +36,7 @@ struct DsmDev
 {
     // geometry
     int W, H, Wp, spw, sph, S, B;
+    int Sp; // S rounded up to 32: row stride of the [k][seed] scratch lists
     float fx, fy, cx, cy, fuse_far, fuse_near, camera_f;
     // per-frame strides in elements
     size_t px_stride; // H*Wp

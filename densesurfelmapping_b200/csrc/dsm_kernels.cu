@@ -377,14 +377,9 @@ __global__ void __launch_bounds__(1024) k_relax(const __grid_constant__ DsmDev d
 // -------------------------------------------------------------------------------------------
 #define DL_CAP 228 // >= 15*15 possible members
 
-__global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ DsmDev d)
+__device__ __forceinline__ void gather_depths_seed(const DsmDev &d, int b, int s, int warp, int lane, float *tile, int &s_rows)
 {
-    const int b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + warp;
-    if (s >= d.S) return;
     const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
-    if (d.tstable[so + s] == DSM_STABLE) return; // stable seeds are skipped (:478-479)
     const int W = d.W, H = d.H, Wp = d.Wp;
     const int32_t *labels = d.labels + fo;
     const float *depth = d.depth + fo;
@@ -450,19 +445,39 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     const int tsi = __reduce_add_sync(FULL, sumi);
     int ndt;
     int pos = warp_excl_scan(__popc(mdm), lane, ndt);
-    float *dl = d.dlist + (size_t)b * DL_CAP * d.S + s;
 #pragma unroll
     for (int k = 0; k < 8; k++)
         if ((mdm >> k) & 1u)
         {
-            dl[(size_t)pos * d.S] = dv[k];
+            tile[pos * 8 + warp] = dv[k];
             pos++;
         }
     if (lane == 0)
     {
         d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
         d.und[so + s] = ndt;
+        atomicMax(&s_rows, ndt);
     }
+}
+
+__global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ DsmDev d)
+{
+    // tile[k][seed-in-block]: the 8 warps (one seed each) compact into shared memory, then the block
+    // copies the tile out as full 32-byte sectors of the [k][seed] global list (a direct scatter
+    // would cost one L2 write request per element)
+    __shared__ float tile[DL_CAP * 8];
+    __shared__ int s_rows;
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + warp;
+    if (threadIdx.x == 0) s_rows = 0;
+    __syncthreads();
+    if (s < d.S && d.tstable[(size_t)b * d.S + s] != DSM_STABLE) // stable seeds are skipped (:478-479)
+        gather_depths_seed(d, b, s, warp, lane, tile, s_rows);
+    __syncthreads();
+    const int rows = s_rows;
+    float *dst = d.dlist + (size_t)b * DL_CAP * d.Sp + blockIdx.x * 8;
+    for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp + (threadIdx.x & 7)] = tile[r * 8 + (threadIdx.x & 7)];
 }
 
 __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d)
@@ -493,17 +508,30 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
     float md = 0.0f;
     if (nd > 0)
     {
-        const float *dl = d.dlist + (size_t)b * DL_CAP * d.S + s;
-        const size_t st = (size_t)d.S;
+        const float *dl = d.dlist + (size_t)b * DL_CAP * d.Sp + s;
+        const size_t st = (size_t)d.Sp;
+        // The adds are a serial dependence chain (that IS the reference's rounding order), but the
+        // loads are independent: fetch 8 list entries at a time so 8 requests are in flight per lane.
         float sum_d = 0.0f;
-        for (int k = 0; k < nd; k++) sum_d += dl[k * st]; // raster order (:511)
+        {
+            int k = 0;
+            for (; k + 8 <= nd; k += 8)
+            {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = dl[(k + j) * st];
+#pragma unroll
+                for (int j = 0; j < 8; j++) sum_d += v[j]; // raster order (:511)
+            }
+            for (; k < nd; k++) sum_d += dl[k * st];
+        }
         md = sum_d / (float)nd;
         for (int it = 0; it < 5; it++)
         { // damped Huber-Newton (:534-554)
             float sa = 0.0f, sb = 0.0f;
-            for (int k = 0; k < nd; k++)
+            auto term = [&](float v)
             {
-                const float r = md - dl[k * st];
+                const float r = md - v;
                 if (r < F_0p4_HI && r > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
                 {
                     sa += 2 * r;
@@ -511,7 +539,17 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
                 }
                 else
                     sa = (float)((double)sa + (r > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
+            };
+            int k = 0;
+            for (; k + 8 <= nd; k += 8)
+            {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = dl[(k + j) * st];
+#pragma unroll
+                for (int j = 0; j < 8; j++) term(v[j]);
             }
+            for (; k < nd; k++) term(dl[k * st]);
             const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
             md = md + delta;
             if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
@@ -625,12 +663,8 @@ __device__ __forceinline__ void solve4_spd(const double *h, const double *j, dou
 
 #define PF_CAP 228 // >= 15*15 possible members of a superpixel
 
-__global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ DsmDev d)
+__device__ __forceinline__ void gather_points_seed(const DsmDev &d, int b, int s, int warp, int lane, float *tile, int &s_rows)
 {
-    const int b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + warp;
-    if (s >= d.S) return;
     const int W = d.W, H = d.H, Wp = d.Wp;
     const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
     const int32_t *labels = d.labels + fo;
@@ -708,18 +742,16 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
         snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
         const float fn = (float)ninl;
         const float mxs = warp_sum_f(spx) / fn, mys = warp_sum_f(spy) / fn, mzs = warp_sum_f(spz) / fn; // (:117-119)
-        const size_t plane = (size_t)d.B * PF_CAP * d.S;
-        float *ql = d.qlist + (size_t)b * PF_CAP * d.S + s;
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if ((inl >> k) & 1u)
             {
-                const size_t o = (size_t)pos * d.S;
-                ql[o] = px[k] - mxs; // centred points (:121-126)
-                ql[plane + o] = py[k] - mys;
-                ql[2 * plane + o] = pz[k] - mzs;
+                tile[pos * 8 + warp] = px[k] - mxs; // centred points (:121-126)
+                tile[PF_CAP * 8 + pos * 8 + warp] = py[k] - mys;
+                tile[2 * PF_CAP * 8 + pos * 8 + warp] = pz[k] - mzs;
                 pos++;
             }
+        if (lane == 0) atomicMax(&s_rows, ninl);
         P0 = make_float4(snx, sny, snz, maxd);
         P1 = make_float4(mxs, mys, mzs, __int_as_float(ninl));
     }
@@ -727,6 +759,31 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
     {
         d.pfsum[(so + s) * 2] = P0;
         d.pfsum[(so + s) * 2 + 1] = P1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ DsmDev d)
+{
+    // tile[plane][k][seed-in-block]: compacted in shared memory, copied out as full 32-byte sectors
+    __shared__ float tile[3 * PF_CAP * 8];
+    __shared__ int s_rows;
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + warp;
+    if (threadIdx.x == 0) s_rows = 0;
+    __syncthreads();
+    if (s < d.S) gather_points_seed(d, b, s, warp, lane, tile, s_rows);
+    __syncthreads();
+    const int rows = s_rows;
+    const size_t plane = (size_t)d.B * PF_CAP * d.Sp;
+    float *dst = d.qlist + (size_t)b * PF_CAP * d.Sp + blockIdx.x * 8;
+    for (int r = threadIdx.x >> 3; r < rows; r += 32)
+    {
+        const int c = threadIdx.x & 7;
+        const size_t o = (size_t)r * d.Sp + c;
+        dst[o] = tile[r * 8 + c];
+        dst[plane + o] = tile[PF_CAP * 8 + r * 8 + c];
+        dst[2 * plane + o] = tile[2 * PF_CAP * 8 + r * 8 + c];
     }
 }
 
@@ -748,8 +805,8 @@ __global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ Ds
         const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
         float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
         const float mxs = P1.x, mys = P1.y, mzs = P1.z;
-        const size_t plane = (size_t)d.B * PF_CAP * d.S, st = (size_t)d.S;
-        const float *qx = d.qlist + (size_t)b * PF_CAP * d.S + s;
+        const size_t plane = (size_t)d.B * PF_CAP * d.Sp, st = (size_t)d.Sp;
+        const float *qx = d.qlist + (size_t)b * PF_CAP * d.Sp + s;
         const float *qy = qx + plane, *qz = qy + plane;
         double hall[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // xx xy xz xw yy yz yw zz zw ww over ALL points
         for (int gn = 0; gn < 5; gn++)
