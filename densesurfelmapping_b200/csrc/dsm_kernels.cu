@@ -377,89 +377,10 @@ __global__ void __launch_bounds__(1024) k_relax(const __grid_constant__ DsmDev d
 // -------------------------------------------------------------------------------------------
 #define DL_CAP 228 // >= 15*15 possible members
 
-__device__ __forceinline__ void gather_depths_seed(const DsmDev &d, int b, int s, int warp, int lane, float *tile, int &s_rows)
-{
-    const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
-    const int W = d.W, H = d.H, Wp = d.Wp;
-    const int32_t *labels = d.labels + fo;
-    const float *depth = d.depth + fo;
-    const uint8_t *gray = d.gray + fo;
-    const int sp_x = s % d.spw, sp_y = s / d.spw;
-    const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
-    const int xb = x0 > 0 ? x0 : 0, yb = y0 > 0 ? y0 : 0;
-    const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
-    const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
-    const int y = y0 + (lane >> 1);
-    const int xs = x0 + 8 * (lane & 1);
-    unsigned m = 0, mdm = 0;
-    float dv[8];
-    int sumx = 0, sumi = 0;
-    if (y >= yb && y < ye)
-    {
-        // all six 16-byte loads are issued before any of them is consumed
-        int4 l4[2];
-        float4 z4[2];
-        uchar4 g4[2];
-#pragma unroll
-        for (int h2 = 0; h2 < 2; h2++)
-        {
-            const int xq = xs + 4 * h2;
-            const bool in = xq >= 0 && xq < Wp;
-            const size_t po = (size_t)y * Wp + (in ? xq : 0);
-            l4[h2] = in ? *reinterpret_cast<const int4 *>(labels + po) : make_int4(-1, -1, -1, -1);
-            z4[h2] = in ? *reinterpret_cast<const float4 *>(depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
-            g4[h2] = in ? *reinterpret_cast<const uchar4 *>(gray + po) : make_uchar4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int h2 = 0; h2 < 2; h2++)
-        {
-            const int xq = xs + 4 * h2;
-            const int lk[4] = {l4[h2].x, l4[h2].y, l4[h2].z, l4[h2].w};
-            const float zk[4] = {z4[h2].x, z4[h2].y, z4[h2].z, z4[h2].w};
-            const int gk[4] = {g4[h2].x, g4[h2].y, g4[h2].z, g4[h2].w};
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                const int x = xq + k;
-                const bool mem = lk[k] == s && x >= xb && x < xe;
-                dv[h2 * 4 + k] = zk[k];
-                if (mem)
-                {
-                    m |= 1u << (h2 * 4 + k);
-                    sumx += x;
-                    sumi += gk[k];
-                    if (zk[k] > F_0p1_LO) mdm |= 1u << (h2 * 4 + k); // (double)depth > 0.1 (:508)
-                }
-            }
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int k = 0; k < 8; k++) dv[k] = 0.f;
-    }
-    const int cnt_lane = __popc(m);
-    const int cnt = __reduce_add_sync(FULL, cnt_lane);
-    const int tsx = __reduce_add_sync(FULL, sumx);
-    const int tsy = __reduce_add_sync(FULL, cnt_lane * y);
-    const int tsi = __reduce_add_sync(FULL, sumi);
-    int ndt;
-    int pos = warp_excl_scan(__popc(mdm), lane, ndt);
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        if ((mdm >> k) & 1u)
-        {
-            tile[pos * 8 + warp] = dv[k];
-            pos++;
-        }
-    if (lane == 0)
-    {
-        d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
-        d.und[so + s] = ndt;
-        atomicMax(&s_rows, ndt);
-    }
-}
-
+// Lane layout of the two window-scan kernels: the 16x16 window is read in two passes of 8 rows;
+// in a pass lane = 4*row + quarter owns 4 consecutive pixels (one 16-byte load per array), so a
+// load instruction touches 8 cache lines and (pass, lane, k) lexicographic order == raster order.
+// Grid: x = groups of 8 seed columns, y = seed row, z = frame -- no integer division anywhere.
 __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ DsmDev d)
 {
     // tile[k][seed-in-block]: the 8 warps (one seed each) compact into shared memory, then the block
@@ -467,17 +388,100 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     // would cost one L2 write request per element)
     __shared__ float tile[DL_CAP * 8];
     __shared__ int s_rows;
-    const int b = blockIdx.y;
+    const int b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + warp;
+    const int sp_x = blockIdx.x * 8 + warp, sp_y = blockIdx.y;
+    const int s = sp_y * d.spw + sp_x;
     if (threadIdx.x == 0) s_rows = 0;
     __syncthreads();
-    if (s < d.S && d.tstable[(size_t)b * d.S + s] != DSM_STABLE) // stable seeds are skipped (:478-479)
-        gather_depths_seed(d, b, s, warp, lane, tile, s_rows);
+    const int W = d.W, H = d.H, Wp = d.Wp;
+    const size_t so = (size_t)b * d.S;
+    const bool live = sp_x < d.spw && d.tstable[so + (sp_x < d.spw ? s : 0)] != DSM_STABLE; // stable seeds are skipped (:478-479)
+    if (live) // warp-uniform
+    {
+        const size_t fo = (size_t)b * d.px_stride;
+        const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
+        const int xb = x0 > 0 ? x0 : 0, yb = y0 > 0 ? y0 : 0;
+        const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
+        const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
+        const int xq = x0 + 4 * (lane & 3);
+        const bool colin = xq >= 0 && xq < Wp;
+        int4 l4[2];
+        float4 z4[2];
+        uchar4 g4[2];
+        int yy[2];
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++)
+        { // all six loads are issued before any of them is consumed
+            const int y = y0 + 8 * ps + (lane >> 2);
+            yy[ps] = y;
+            const bool in = colin && y >= yb && y < ye;
+            const size_t po = fo + (size_t)(in ? y * Wp + xq : 0);
+            l4[ps] = in ? *reinterpret_cast<const int4 *>(d.labels + po) : make_int4(-1, -1, -1, -1);
+            z4[ps] = in ? *reinterpret_cast<const float4 *>(d.depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[ps] = in ? *reinterpret_cast<const uchar4 *>(d.gray + po) : make_uchar4(0, 0, 0, 0);
+        }
+        unsigned mdm = 0; // bit 4*ps+k: member with depth > 0.1
+        int cnt2 = 0;     // member count, pass 0 in the low half-word, pass 1 in the high one
+        int sumx = 0, sumy = 0, sumi = 0;
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++)
+        {
+            const int lk[4] = {l4[ps].x, l4[ps].y, l4[ps].z, l4[ps].w};
+            const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
+            const int gk[4] = {g4[ps].x, g4[ps].y, g4[ps].z, g4[ps].w};
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int x = xq + k;
+                const bool mem = lk[k] == s && x >= xb && x < xe;
+                c += mem ? 1 : 0;
+                sumx += mem ? x : 0;
+                sumi += mem ? gk[k] : 0;
+                if (mem && zk[k] > F_0p1_LO) mdm |= 1u << (4 * ps + k); // (double)depth > 0.1 (:508)
+            }
+            cnt2 += c;
+            sumy += c * yy[ps];
+        }
+        const int cnt = __reduce_add_sync(FULL, cnt2);
+        const int tsx = __reduce_add_sync(FULL, sumx);
+        const int tsy = __reduce_add_sync(FULL, sumy);
+        const int tsi = __reduce_add_sync(FULL, sumi);
+        // one scan for both passes: pass-0 count in the low half-word, pass-1 count in the high one
+        const int c2 = __popc(mdm & 0xfu) | (__popc(mdm >> 4) << 16);
+        int tot2;
+        const int ex2 = warp_excl_scan(c2, lane, tot2);
+        const int n0 = tot2 & 0xffff, ndt = n0 + (tot2 >> 16);
+        int pos = ex2 & 0xffff;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const float zk = k == 0 ? z4[0].x : k == 1 ? z4[0].y : k == 2 ? z4[0].z : z4[0].w;
+            if ((mdm >> k) & 1u) tile[(pos++) * 8 + warp] = zk;
+        }
+        pos = n0 + (ex2 >> 16);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const float zk = k == 0 ? z4[1].x : k == 1 ? z4[1].y : k == 2 ? z4[1].z : z4[1].w;
+            if ((mdm >> (4 + k)) & 1u) tile[(pos++) * 8 + warp] = zk;
+        }
+        if (lane == 0)
+        {
+            d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
+            d.und[so + s] = ndt;
+            atomicMax(&s_rows, ndt);
+        }
+    }
     __syncthreads();
     const int rows = s_rows;
-    float *dst = d.dlist + (size_t)b * DL_CAP * d.Sp + blockIdx.x * 8;
-    for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp + (threadIdx.x & 7)] = tile[r * 8 + (threadIdx.x & 7)];
+    const int c = threadIdx.x & 7;
+    if (blockIdx.x * 8 + c < d.spw)
+    {
+        float *dst = d.dlist + (size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c;
+        for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp] = tile[r * 8 + c];
+    }
 }
 
 __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d)
@@ -663,53 +667,60 @@ __device__ __forceinline__ void solve4_spd(const double *h, const double *j, dou
 
 #define PF_CAP 228 // >= 15*15 possible members of a superpixel
 
-__device__ __forceinline__ void gather_points_seed(const DsmDev &d, int b, int s, int warp, int lane, float *tile, int &s_rows)
+__global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ DsmDev d)
 {
+    // tile[plane][k][seed-in-block]: compacted in shared memory, copied out as full 32-byte sectors
+    __shared__ float tile[3 * PF_CAP * 8];
+    __shared__ int s_rows;
+    const int b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sp_x = blockIdx.x * 8 + warp, sp_y = blockIdx.y;
+    const int s = sp_y * d.spw + sp_x;
+    if (threadIdx.x == 0) s_rows = 0;
+    __syncthreads();
     const int W = d.W, H = d.H, Wp = d.Wp;
-    const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
-    const int32_t *labels = d.labels + fo;
-    const float *depth = d.depth + fo;
-    const float *nrm = d.nrm + fo;
-    const float4 sd = d.seed[so + s]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
-    const int sp_x = s % d.spw, sp_y = s / d.spw;
-    const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
-    const int y = y0 + (lane >> 1);
-    const int xs = x0 + 8 * (lane & 1);
-    float px[8], py[8], pz[8];
-    unsigned inl = 0;
-    int nvalid = 0;
-    float maxd = 0.f, snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) px[k] = py[k] = pz[k] = 0.f;
-    if (y >= 0 && y < H)
+    const size_t so = (size_t)b * d.S;
+    if (sp_x < d.spw) // warp-uniform
     {
-        const float kyv = d.ky[y];
+        const size_t fo = (size_t)b * d.px_stride;
+        const float4 sd = d.seed[so + s]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
+        const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
+        const int xq = x0 + 4 * (lane & 3);
+        const bool colin = xq >= 0 && xq < Wp;
+        const float4 k4 = colin ? *reinterpret_cast<const float4 *>(d.kx + xq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float kxv[4] = {k4.x, k4.y, k4.z, k4.w};
         int4 l4[2];
-        float4 z4[2], k4[2];
+        float4 z4[2];
+        float kyv[2];
+        int yy[2];
+        size_t pof[2];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; h2++)
+        for (int ps = 0; ps < 2; ps++)
         {
-            const int xq = xs + 4 * h2;
-            const bool in = xq >= 0 && xq < Wp;
-            const size_t po = (size_t)y * Wp + (in ? xq : 0);
-            l4[h2] = in ? *reinterpret_cast<const int4 *>(labels + po) : make_int4(-1, -1, -1, -1);
-            z4[h2] = in ? *reinterpret_cast<const float4 *>(depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
-            k4[h2] = in ? *reinterpret_cast<const float4 *>(d.kx + xq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int y = y0 + 8 * ps + (lane >> 2);
+            yy[ps] = y;
+            const bool in = colin && y >= 0 && y < H;
+            const size_t po = fo + (size_t)(in ? y * Wp + xq : 0);
+            pof[ps] = po;
+            l4[ps] = in ? *reinterpret_cast<const int4 *>(d.labels + po) : make_int4(-1, -1, -1, -1);
+            z4[ps] = in ? *reinterpret_cast<const float4 *>(d.depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
+            kyv[ps] = in ? d.ky[y] : 0.f;
         }
+        unsigned inl = 0; // bit 4*ps+k: inlier
+        int nvalid = 0;
+        float maxd = 0.f, snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; h2++)
+        for (int ps = 0; ps < 2; ps++)
         {
-            const int xq = xs + 4 * h2;
-            const size_t po = (size_t)y * Wp + xq;
-            const int lk[4] = {l4[h2].x, l4[h2].y, l4[h2].z, l4[h2].w};
-            const float zk[4] = {z4[h2].x, z4[h2].y, z4[h2].z, z4[h2].w};
-            const float kk[4] = {k4[h2].x, k4[h2].y, k4[h2].z, k4[h2].w};
+            const int lk[4] = {l4[ps].x, l4[ps].y, l4[ps].z, l4[ps].w};
+            const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
+            unsigned mi = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++)
             {
                 const int x = xq + k;
                 if (lk[k] != s || x >= W) continue; // window bounded by the flat index only (:816)
-                const float xd = (float)x - sd.x, yd = (float)y - sd.y;
+                const float xd = (float)x - sd.x, yd = (float)yy[ps] - sd.y;
                 const float dist = xd * xd + yd * yd;
                 if (dist > maxd) maxd = dist;
                 const float mz = zk[k];
@@ -718,72 +729,77 @@ __device__ __forceinline__ void gather_points_seed(const DsmDev &d, int b, int s
                 const float r = sd.w - mz;
                 if (r < F_0p4_HI && r > -F_0p4_HI)
                 { // inlier (:849-860)
-                    inl |= 1u << (h2 * 4 + k);
-                    snx += nrm[po + k];
-                    sny += nrm[d.nrm_plane + po + k];
-                    snz += nrm[2 * d.nrm_plane + po + k];
-                    const float mx = kk[k] * mz, my = kyv * mz; // back_project in float (:94-96)
-                    px[h2 * 4 + k] = mx, py[h2 * 4 + k] = my, pz[h2 * 4 + k] = mz;
-                    spx += mx;
-                    spy += my;
+                    mi |= 1u << k;
+                    spx += kxv[k] * mz; // back_project in float (:94-96)
+                    spy += kyv[ps] * mz;
                     spz += mz;
                 }
             }
+            if (mi)
+            { // pixel normals of this 4-pixel group: three 16-byte loads instead of up to 12 scalar ones
+                const float4 a = *reinterpret_cast<const float4 *>(d.nrm + pof[ps]);
+                const float4 bb = *reinterpret_cast<const float4 *>(d.nrm + d.nrm_plane + pof[ps]);
+                const float4 c = *reinterpret_cast<const float4 *>(d.nrm + 2 * d.nrm_plane + pof[ps]);
+                const float ax[4] = {a.x, a.y, a.z, a.w}, ay[4] = {bb.x, bb.y, bb.z, bb.w}, az[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((mi >> k) & 1u) snx += ax[k], sny += ay[k], snz += az[k];
+                inl |= mi << (4 * ps);
+            }
+        }
+        maxd = warp_max_f(maxd);
+        nvalid = __reduce_add_sync(FULL, nvalid);
+        const int c2 = __popc(inl & 0xfu) | (__popc(inl >> 4) << 16);
+        int tot2;
+        const int ex2 = warp_excl_scan(c2, lane, tot2);
+        const int n0 = tot2 & 0xffff, ninl = n0 + (tot2 >> 16);
+        const bool ok = nvalid >= 16 && !((float)ninl / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
+        float4 P0 = make_float4(0.f, 0.f, 0.f, maxd), P1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        if (ok)
+        {
+            snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
+            const float fn = (float)ninl;
+            const float mxs = warp_sum_f(spx) / fn, mys = warp_sum_f(spy) / fn, mzs = warp_sum_f(spz) / fn; // (:117-119)
+#pragma unroll
+            for (int ps = 0; ps < 2; ps++)
+            {
+                int pos = ps == 0 ? (ex2 & 0xffff) : n0 + (ex2 >> 16);
+                const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((inl >> (4 * ps + k)) & 1u)
+                    {
+                        const int t = pos * 8 + warp;
+                        tile[t] = kxv[k] * zk[k] - mxs; // centred points (:121-126)
+                        tile[PF_CAP * 8 + t] = kyv[ps] * zk[k] - mys;
+                        tile[2 * PF_CAP * 8 + t] = zk[k] - mzs;
+                        pos++;
+                    }
+            }
+            P0 = make_float4(snx, sny, snz, maxd);
+            P1 = make_float4(mxs, mys, mzs, __int_as_float(ninl));
+            if (lane == 0) atomicMax(&s_rows, ninl);
+        }
+        if (lane == 0)
+        {
+            d.pfsum[(so + s) * 2] = P0;
+            d.pfsum[(so + s) * 2 + 1] = P1;
         }
     }
-    maxd = warp_max_f(maxd);
-    nvalid = __reduce_add_sync(FULL, nvalid);
-    int ninl;
-    int pos = warp_excl_scan(__popc(inl), lane, ninl);
-    const bool ok = nvalid >= 16 && !((float)ninl / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
-    float4 P0 = make_float4(0.f, 0.f, 0.f, maxd), P1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-    if (ok)
-    {
-        snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
-        const float fn = (float)ninl;
-        const float mxs = warp_sum_f(spx) / fn, mys = warp_sum_f(spy) / fn, mzs = warp_sum_f(spz) / fn; // (:117-119)
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if ((inl >> k) & 1u)
-            {
-                tile[pos * 8 + warp] = px[k] - mxs; // centred points (:121-126)
-                tile[PF_CAP * 8 + pos * 8 + warp] = py[k] - mys;
-                tile[2 * PF_CAP * 8 + pos * 8 + warp] = pz[k] - mzs;
-                pos++;
-            }
-        if (lane == 0) atomicMax(&s_rows, ninl);
-        P0 = make_float4(snx, sny, snz, maxd);
-        P1 = make_float4(mxs, mys, mzs, __int_as_float(ninl));
-    }
-    if (lane == 0)
-    {
-        d.pfsum[(so + s) * 2] = P0;
-        d.pfsum[(so + s) * 2 + 1] = P1;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ DsmDev d)
-{
-    // tile[plane][k][seed-in-block]: compacted in shared memory, copied out as full 32-byte sectors
-    __shared__ float tile[3 * PF_CAP * 8];
-    __shared__ int s_rows;
-    const int b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + warp;
-    if (threadIdx.x == 0) s_rows = 0;
-    __syncthreads();
-    if (s < d.S) gather_points_seed(d, b, s, warp, lane, tile, s_rows);
     __syncthreads();
     const int rows = s_rows;
-    const size_t plane = (size_t)d.B * PF_CAP * d.Sp;
-    float *dst = d.qlist + (size_t)b * PF_CAP * d.Sp + blockIdx.x * 8;
-    for (int r = threadIdx.x >> 3; r < rows; r += 32)
+    const int c = threadIdx.x & 7;
+    if (blockIdx.x * 8 + c < d.spw)
     {
-        const int c = threadIdx.x & 7;
-        const size_t o = (size_t)r * d.Sp + c;
-        dst[o] = tile[r * 8 + c];
-        dst[plane + o] = tile[PF_CAP * 8 + r * 8 + c];
-        dst[2 * plane + o] = tile[2 * PF_CAP * 8 + r * 8 + c];
+        const size_t plane = (size_t)d.B * PF_CAP * d.Sp;
+        float *dst = d.qlist + (size_t)b * PF_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c;
+        for (int r = threadIdx.x >> 3; r < rows; r += 32)
+        {
+            const size_t o = (size_t)r * d.Sp;
+            dst[o] = tile[r * 8 + c];
+            dst[plane + o] = tile[PF_CAP * 8 + r * 8 + c];
+            dst[2 * plane + o] = tile[2 * PF_CAP * 8 + r * 8 + c];
+        }
     }
 }
 
@@ -1131,7 +1147,7 @@ void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s)
 void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s) { k_relax<<<nb, 1024, 0, s>>>(d); }
 void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s)
 {
-    dim3 grid((d.S + 7) / 8, nb);
+    dim3 grid((d.spw + 7) / 8, d.sph, nb);
     k_gather_depths<<<grid, 256, 0, s>>>(d);
 }
 void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s)
@@ -1147,7 +1163,7 @@ void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s)
 }
 void dsm_launch_gather_points(const DsmDev &d, int nb, cudaStream_t s)
 {
-    dim3 grid((d.S + 7) / 8, nb);
+    dim3 grid((d.spw + 7) / 8, d.sph, nb);
     k_gather_points<<<grid, 256, 0, s>>>(d);
 }
 void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s)
