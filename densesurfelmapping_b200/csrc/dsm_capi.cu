@@ -36,6 +36,11 @@ struct dsm_ctx
     float *pose, *ipose;
     dsm_seed_t *seed_export;
     float *kx, *ky;
+    // end-to-end pipeline (dsm_fuse_batch): packed staging + copy streams + per-chunk events
+    uint8_t *gray_packed; // [B][H][W]
+    float *depth_packed;  // [B][H][W]
+    cudaStream_t s_h2d, s_d2h;
+    cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
     // pinned host staging for the small per-batch tables
     float *h_pose; // [B][32]: pose then inverse
     int32_t *h_ofs;
@@ -51,7 +56,7 @@ struct dsm_ctx
 
 static const char *kKernelNames[DSM_NUM_KERNELS] = {
     "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_gather_depths", "slic_newton",
-    "plane_gather_points", "surfel_fuse", "surfel_init", "seeds_export", "pixel_normals", "plane_gauss_newton"};
+    "plane_gather_points", "surfel_fuse", "surfel_init", "repack", "pixel_normals", "plane_gauss_newton"};
 
 #define CK(call)                                                                                         \
     do                                                                                                   \
@@ -135,6 +140,16 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(d.nrm);
     cudaFree(ctx->kx);
     cudaFree(ctx->ky);
+    cudaFree(ctx->gray_packed);
+    cudaFree(ctx->depth_packed);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int i = 0; i < 8; i++)
+    {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     cudaFreeHost(ctx->h_pose);
     cudaFreeHost(ctx->h_ofs);
     cudaFreeHost(ctx->h_ref);
@@ -170,6 +185,11 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->n_pool = 0;
     ctx->uploaded = ctx->ran = false;
     ctx->stop_after = 0;
+    ctx->s_h2d = ctx->s_d2h = nullptr;
+    ctx->ev_start = nullptr;
+    for (int i = 0; i < 8; i++) ctx->ev_h2d[i] = ctx->ev_done[i] = nullptr;
+    ctx->gray_packed = nullptr;
+    ctx->depth_packed = nullptr;
     ctx->own_stream = (cuda_stream == nullptr);
     ctx->stream = (cudaStream_t)cuda_stream;
     if (ctx->own_stream && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -224,8 +244,19 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.nrm, 3 * (B * px) + 64);
     ALLOC(ctx->kx, (size_t)Wp + 16);
     ALLOC(ctx->ky, (size_t)H + 16);
+    ALLOC(ctx->gray_packed, (size_t)B * H * W + 64);
+    ALLOC(ctx->depth_packed, (size_t)B * H * W + 64);
 #undef ALLOC
     d.nrm_plane = B * px;
+    d.frame0 = 0;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++)
+    {
+        e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming);
     if (e == cudaSuccess)
     { // back-projection factor tables: the same float ops as back_project (fusion_functions.cpp:94-95)
         std::vector<float> hx((size_t)Wp + 16), hy((size_t)H + 16);
@@ -413,9 +444,15 @@ extern "C" int dsm_batch_upload(dsm_ctx *ctx, int n, const int32_t *ref, const u
     int rc = upload_tables(ctx, n, ref, poses, ofs, 0);
     if (rc != DSM_OK) return rc;
     const int W = ctx->p.width, H = ctx->p.height;
-    // [n][H][W] packed -> [n][H][Wp] pitched, one strided copy each
-    CK(cudaMemcpy2DAsync(ctx->gray, ctx->Wp, gray, W, W, (size_t)n * H, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(ctx->depth, (size_t)ctx->Wp * 4, depth, (size_t)W * 4, (size_t)W * 4, (size_t)n * H, cudaMemcpyHostToDevice, ctx->stream));
+    // [n][H][W] packed: one contiguous copy each, then the repack kernel lays out the pitched format
+    CK(cudaMemcpyAsync(ctx->gray_packed, gray, (size_t)n * H * W, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->depth_packed, depth, (size_t)n * H * W * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        DsmDev d = ctx->d;
+        d.frame0 = 0;
+        ProfScope p(ctx, DSM_K_REPACK);
+        dsm_launch_repack(d, n, ctx->gray_packed, ctx->depth_packed, ctx->stream);
+    }
     if (ctx->n_pool > 0)
     {
         CK(cudaMemcpyAsync(ctx->d.pool, local, (size_t)ctx->n_pool * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -437,14 +474,14 @@ extern "C" int dsm_batch_restore_pool(dsm_ctx *ctx)
     return DSM_OK;
 }
 
-// The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79).
-extern "C" int dsm_batch_run(dsm_ctx *ctx)
+// The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79),
+// enqueued for the frame slots [f0, f0 + nf).
+static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame)
 {
-    if (!ctx) return DSM_E_INVALID;
-    if (!ctx->uploaded) return DSM_E_STATE;
-    CK(cudaSetDevice(ctx->device));
-    const DsmDev &d = ctx->d;
-    const int nb = ctx->nb;
+    DsmDev d = ctx->d;
+    d.frame0 = f0;
+    d.max_pool_per_frame = max_pool_per_frame;
+    const int nb = nf;
     cudaStream_t st = ctx->stream;
     int budget = ctx->stop_after > 0 ? ctx->stop_after : 1 << 30;
 #define STEP(ID, CALL)                  \
@@ -471,13 +508,23 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
     STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
     STEP(DSM_K_GATHER_POINTS, dsm_launch_gather_points(d, nb, st));
     STEP(DSM_K_GAUSS_NEWTON, dsm_launch_gauss_newton(d, nb, st));
-    if (d.max_pool_per_frame > 0)
+    if (max_pool_per_frame > 0)
     {
         STEP(DSM_K_FUSE, dsm_launch_fuse(d, nb, st));
     }
     STEP(DSM_K_INIT_SURFELS, dsm_launch_init_surfels(d, nb, st));
 #undef STEP
     CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+extern "C" int dsm_batch_run(dsm_ctx *ctx)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (!ctx->uploaded) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int rc = enqueue_schedule(ctx, 0, ctx->nb, ctx->d.max_pool_per_frame);
+    if (rc != DSM_OK) return rc;
     ctx->ran = true;
     return DSM_OK;
 }
@@ -526,17 +573,70 @@ extern "C" int dsm_sync(dsm_ctx *ctx)
     return DSM_OK;
 }
 
+// End-to-end batch call with host buffers.  The batch is cut into chunks of frames; chunk c's H2D
+// (copy stream), kernels (compute stream) and D2H (second copy stream) overlap with the neighbouring
+// chunks, so the call costs about max(PCIe time, kernel time) instead of their sum.  Host buffers
+// should be pinned for the copies to be truly asynchronous (pageable memory works, staged by the driver).
 extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uint8_t *gray, const float *depth,
                               const float *poses, dsm_surfel_t *local, const int32_t *ofs,
                               dsm_surfel_t *new_out, int32_t *n_new)
 {
-    int rc = dsm_batch_upload(ctx, n, ref, gray, depth, poses, local, ofs);
+    if (!ctx || !ref || !gray || !depth || !poses || !ofs) return DSM_E_INVALID;
+    if (n < 1 || n > ctx->p.max_batch) return DSM_E_INVALID;
+    if (ofs[n] > 0 && !local) return DSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = upload_tables(ctx, n, ref, poses, ofs, 0); // small tables, on the compute stream
     if (rc != DSM_OK) return rc;
-    rc = dsm_batch_run(ctx);
-    if (rc != DSM_OK) return rc;
-    rc = dsm_batch_download(ctx, local, new_out, n_new);
-    if (rc != DSM_OK) return rc;
-    return dsm_sync(ctx);
+    const int W = ctx->p.width, H = ctx->p.height, S = ctx->S;
+    const size_t fpx = (size_t)H * W;
+    const int nchunks = n >= 16 ? 4 : (n >= 4 ? 2 : 1);
+    const int per = (n + nchunks - 1) / nchunks;
+    // copies must not start before earlier work on the compute stream (previous users of the buffers) is done
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
+    int nc = 0;
+    for (int f0 = 0; f0 < n; f0 += per, nc++)
+    {
+        const int nf = (n - f0 < per) ? n - f0 : per;
+        const int p0 = ofs[f0], p1 = ofs[f0 + nf];
+        int maxper = 0;
+        for (int b = f0; b < f0 + nf; b++) maxper = (ofs[b + 1] - ofs[b] > maxper) ? ofs[b + 1] - ofs[b] : maxper;
+        // H2D of this chunk
+        CK(cudaMemcpyAsync(ctx->gray_packed + (size_t)f0 * fpx, gray + (size_t)f0 * fpx, (size_t)nf * fpx, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpyAsync(ctx->depth_packed + (size_t)f0 * fpx, depth + (size_t)f0 * fpx, (size_t)nf * fpx * sizeof(float), cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (p1 > p0)
+            CK(cudaMemcpyAsync(ctx->d.pool + p0, local + p0, (size_t)(p1 - p0) * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_h2d[nc], ctx->s_h2d));
+        // kernels
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[nc], 0));
+        {
+            DsmDev d = ctx->d;
+            d.frame0 = f0;
+            ProfScope p(ctx, DSM_K_REPACK);
+            dsm_launch_repack(d, nf, ctx->gray_packed + (size_t)f0 * fpx, ctx->depth_packed + (size_t)f0 * fpx, ctx->stream);
+        }
+        rc = enqueue_schedule(ctx, f0, nf, maxper);
+        if (rc != DSM_OK) return rc;
+        CK(cudaEventRecord(ctx->ev_done[nc], ctx->stream));
+        // D2H of this chunk
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[nc], 0));
+        if (p1 > p0)
+            CK(cudaMemcpyAsync(local + p0, ctx->d.pool + p0, (size_t)(p1 - p0) * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (new_out)
+            CK(cudaMemcpyAsync(new_out + (size_t)f0 * S, ctx->d.newsurf + (size_t)f0 * S, (size_t)nf * S * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (n_new)
+            CK(cudaMemcpyAsync(n_new + f0, ctx->d.nnew + f0, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
+    ctx->nb = n;
+    ctx->uploaded = true;
+    ctx->ran = true;
+    CK(cudaStreamSynchronize(ctx->s_h2d));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    CK(cudaGetLastError());
+    return DSM_OK;
 }
 
 extern "C" int dsm_fuse_frame(dsm_ctx *ctx, int ref_idx, const uint8_t *gray, size_t gray_pitch,

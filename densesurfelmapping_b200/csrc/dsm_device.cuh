@@ -36,6 +36,7 @@ struct DsmDev
 {
     // geometry
     int W, H, Wp, spw, sph, S, B;
+    int frame0; // first frame slot this launch works on (chunked copy/compute overlap)
     int Sp; // S rounded up to 32: row stride of the [k][seed] scratch lists
     float fx, fy, cx, cy, fuse_far, fuse_near, camera_f;
     // per-frame strides in elements
@@ -82,12 +83,13 @@ enum DsmKernelId
     DSM_K_GATHER_POINTS = 6,
     DSM_K_FUSE = 7,
     DSM_K_INIT_SURFELS = 8,
-    DSM_K_SEEDS_EXPORT = 9,
+    DSM_K_REPACK = 9,
     DSM_K_PIXEL_NORMALS = 10,
     DSM_K_GAUSS_NEWTON = 11,
 };
 
 // launchers (dsm_kernels.cu); nb = frames in this batch
+void dsm_launch_repack(const DsmDev &d, int nb, const uint8_t *gray_packed, const float *depth_packed, cudaStream_t s);
 void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s);
 void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s);

@@ -80,12 +80,43 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total)
 }
 
 // -------------------------------------------------------------------------------------------
+// Kin  repack — the caller's tightly packed [n][H][W] gray / depth arrive by ONE contiguous H2D copy
+// each (a strided 2-D copy of 1226-byte rows runs at less than half the PCIe rate) and are laid
+// out here into the 16-byte-aligned pitched device format every other kernel relies on.
+// One thread per 4 output pixels; reads are unaligned scalars (coalesced), writes are vectors.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_repack(const __grid_constant__ DsmDev d, const uint8_t *gray_packed, const float *depth_packed)
+{
+    const int b = d.frame0 + blockIdx.z; // device frame slot; the packed source holds this chunk's frames from 0
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x4 >= d.Wp || y >= d.H) return;
+    const size_t src = ((size_t)blockIdx.z * d.H + y) * d.W + x4;
+    const size_t dst = (size_t)b * d.px_stride + (size_t)y * d.Wp + x4;
+    uchar4 g = make_uchar4(0, 0, 0, 0);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x4 + 3 < d.W)
+    {
+        g = make_uchar4(gray_packed[src], gray_packed[src + 1], gray_packed[src + 2], gray_packed[src + 3]);
+        z = make_float4(depth_packed[src], depth_packed[src + 1], depth_packed[src + 2], depth_packed[src + 3]);
+    }
+    else
+    {
+        if (x4 < d.W) g.x = gray_packed[src], z.x = depth_packed[src];
+        if (x4 + 1 < d.W) g.y = gray_packed[src + 1], z.y = depth_packed[src + 1];
+        if (x4 + 2 < d.W) g.z = gray_packed[src + 2], z.z = depth_packed[src + 2];
+    }
+    *reinterpret_cast<uchar4 *>(const_cast<uint8_t *>(d.gray) + dst) = g;
+    *reinterpret_cast<float4 *>(const_cast<float *>(d.depth) + dst) = z;
+}
+
+// -------------------------------------------------------------------------------------------
 // K0  seed_init   — initialize_seeds_kernel (:577-629) + the per-frame clears (:963-965)
 // one thread per seed
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_seed_init(const __grid_constant__ DsmDev d)
 {
-    const int b = blockIdx.y;
+    const int b = d.frame0 + blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
@@ -180,7 +211,7 @@ __device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pi
 template <bool FIRST>
 __global__ void __launch_bounds__(256) k_assign(const __grid_constant__ DsmDev d)
 {
-    const int b = blockIdx.z;
+    const int b = d.frame0 + blockIdx.z;
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int lane = threadIdx.x & 31;
@@ -329,7 +360,7 @@ __global__ void __launch_bounds__(256) k_assign(const __grid_constant__ DsmDev d
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_relax(const __grid_constant__ DsmDev d)
 {
-    const int b = blockIdx.x;
+    const int b = d.frame0 + blockIdx.x;
     const int n = d.nlist[b];
     if (n == 0) return;
     const size_t fo = (size_t)b * d.px_stride;
@@ -388,7 +419,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     // would cost one L2 write request per element)
     __shared__ float tile[DL_CAP * 8];
     __shared__ int s_rows;
-    const int b = blockIdx.z;
+    const int b = d.frame0 + blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sp_x = blockIdx.x * 8 + warp, sp_y = blockIdx.y;
     const int s = sp_y * d.spw + sp_x;
@@ -486,7 +517,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
 
 __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d)
 {
-    const int b = blockIdx.y;
+    const int b = d.frame0 + blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) d.nlist[b] = 0; // the deferred-pixel list of this pass is consumed
     if (s >= d.S) return;
@@ -577,7 +608,7 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pixel_normals(const __grid_constant__ DsmDev d)
 {
-    const int b = blockIdx.z;
+    const int b = d.frame0 + blockIdx.z;
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
     const int y = blockIdx.y * 4 + threadIdx.y;
     if (x4 >= d.Wp || y >= d.H) return;
@@ -672,7 +703,7 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
     // tile[plane][k][seed-in-block]: compacted in shared memory, copied out as full 32-byte sectors
     __shared__ float tile[3 * PF_CAP * 8];
     __shared__ int s_rows;
-    const int b = blockIdx.z;
+    const int b = d.frame0 + blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sp_x = blockIdx.x * 8 + warp, sp_y = blockIdx.y;
     const int s = sp_y * d.spw + sp_x;
@@ -805,7 +836,7 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
 
 __global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ DsmDev d)
 {
-    const int b = blockIdx.y;
+    const int b = d.frame0 + blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= d.S) return;
     const size_t so = (size_t)b * d.S;
@@ -947,7 +978,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK) k_fuse(const __grid_constant__ Dsm
 {
     __shared__ float sm[FUSE_BLOCK * 11];
     __shared__ float s_pose[32];
-    const int b = blockIdx.y;
+    const int b = d.frame0 + blockIdx.y;
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
     const int first = begin + blockIdx.x * FUSE_BLOCK;
     if (first >= end) return;
@@ -1047,7 +1078,7 @@ __global__ void __launch_bounds__(1024) k_init_surfels(const __grid_constant__ D
     __shared__ int s_warp[32];
     __shared__ int s_running;
     __shared__ float s_pose[16];
-    const int b = blockIdx.x;
+    const int b = d.frame0 + blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t so = (size_t)b * d.S;
     if (threadIdx.x < 16) s_pose[threadIdx.x] = d.pose[b * 16 + threadIdx.x];
@@ -1130,6 +1161,12 @@ __global__ void k_seeds_export(const __grid_constant__ DsmDev d, int b, dsm_seed
 // -------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------
+void dsm_launch_repack(const DsmDev &d, int nb, const uint8_t *gray_packed, const float *depth_packed, cudaStream_t s)
+{
+    dim3 block(64, 4);
+    dim3 grid((d.Wp + 255) / 256, (d.H + 3) / 4, nb);
+    k_repack<<<grid, block, 0, s>>>(d, gray_packed, depth_packed);
+}
 void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s)
 {
     dim3 grid((d.S + 255) / 256, nb);
