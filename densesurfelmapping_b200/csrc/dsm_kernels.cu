@@ -118,42 +118,54 @@ __global__ void __launch_bounds__(256) k_seed_init(const __grid_constant__ DsmDe
 {
     const int b = d.frame0 + blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         d.nlist[b] = 0;
         d.nnew[b] = 0;
         d.errflag[b] = 0;
     }
-    if (s >= d.S) return;
     const int W = d.W, H = d.H, Wp = d.Wp;
     const uint8_t *gray = d.gray + (size_t)b * d.px_stride;
     const float *depth = d.depth + (size_t)b * d.px_stride;
-    const int sp_x = s % d.spw, sp_y = s / d.spw;
+    const bool live = s < d.S;
+    const int sp_x = live ? s % d.spw : 0, sp_y = live ? s / d.spw : 0;
     int ix = sp_x * DSM_SP + DSM_SP / 2, iy = sp_y * DSM_SP + DSM_SP / 2;
     ix = ix < W - 1 ? ix : W - 1;
     iy = iy < H - 1 ? iy : H - 1;
-    float md = depth[iy * Wp + ix];
-    if ((double)md < 0.01)
-    { // first depth > 0.01 in raster order of the clamped END-EXCLUSIVE window (:602-625)
-        int xb = sp_x * DSM_SP + DSM_SP / 2 - DSM_SP, yb = sp_y * DSM_SP + DSM_SP / 2 - DSM_SP;
+    float md = live ? depth[iy * Wp + ix] : 1.0f;
+    // seeds sitting on a hole: first depth > 0.01 in raster order of the clamped END-EXCLUSIVE window
+    // (:602-625).  The warp serves its hole seeds one at a time, 32 window pixels per step.
+    unsigned todo = __ballot_sync(FULL, live && (double)md < 0.01);
+    while (todo)
+    {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int hx = __shfl_sync(FULL, sp_x, src), hy = __shfl_sync(FULL, sp_y, src);
+        int xb = hx * DSM_SP + DSM_SP / 2 - DSM_SP, yb = hy * DSM_SP + DSM_SP / 2 - DSM_SP;
         int xe = xb + DSM_SP * 2, ye = yb + DSM_SP * 2;
         xb = xb > 0 ? xb : 0;
         yb = yb > 0 ? yb : 0;
         xe = xe < W - 1 ? xe : W - 1;
         ye = ye < H - 1 ? ye : H - 1;
-        bool found = false;
-        for (int j = yb; j < ye && !found; j++)
-            for (int i = xb; i < xe; i++)
+        const int ww = xe - xb, n = ww * (ye - yb);
+        float found = 0.f;
+        bool got = false;
+        for (int base = 0; base < n && !got; base += 32)
+        {
+            const int i = base + lane;
+            float t = 0.f;
+            if (i < n) t = depth[(yb + i / ww) * Wp + xb + i % ww];
+            const unsigned hit = __ballot_sync(FULL, (double)t > 0.01);
+            if (hit)
             {
-                float t = depth[j * Wp + i];
-                if ((double)t > 0.01)
-                {
-                    md = t;
-                    found = true;
-                    break;
-                }
+                found = __shfl_sync(FULL, t, __ffs(hit) - 1);
+                got = true;
             }
+        }
+        if (got && lane == src) md = found;
     }
+    if (!live) return;
     const size_t o = (size_t)b * d.S + s;
     d.seed[o] = make_float4((float)ix, (float)iy, (float)gray[iy * Wp + ix], md);
     d.inv_md[o] = 1.0 / (double)md; // only consumed when md > 0 (:378)
@@ -856,53 +868,70 @@ __global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ Ds
         const float *qx = d.qlist + (size_t)b * PF_CAP * d.Sp + s;
         const float *qy = qx + plane, *qz = qy + plane;
         double hall[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // xx xy xz xw yy yz yw zz zw ww over ALL points
+        // Pass skipping: a pass over the points is only needed to find out which of them fall outside the
+        // Huber range.  With rmax >= max|r_i| of the last evaluated parameters, qmax = max|q_i| and the step
+        // (dn, db) just taken, |r_i(new)| <= rmax + qmax*|dn| + |db|.  If that bound (plus a rounding
+        // slack far above the float error of evaluating r) stays below the range, every point is
+        // provably in range, so H_R = H_all and J = H_all*theta without touching memory.  Results are
+        // bit-identical to evaluating the pass.
+        float rmax = 0.f, qmax2 = 0.f;
+        bool need_pass = true;
         for (int gn = 0; gn < 5; gn++)
         {
             double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // same, over the points outside the Huber range
             double jo[4] = {0, 0, 0, 0};
-            auto point = [&](float ax, float ay, float az)
+            if (need_pass)
             {
-                const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
-                const bool inr = r < F_0p4_HI && r > -F_0p4_HI;  // (:134)
-                if (gn == 0 || !inr)
+                float rm = 0.f;
+                bool rnan = false;
+                auto point = [&](float ax, float ay, float az)
                 {
-                    const double t0 = (double)(2 * ax * ax), t1 = (double)(2 * ax * ay), t2 = (double)(2 * ax * az), t3 = (double)(2 * ax);
-                    const double t4 = (double)(2 * ay * ay), t5 = (double)(2 * ay * az), t6 = (double)(2 * ay);
-                    const double t7 = (double)(2 * az * az), t8 = (double)(2 * az);
-                    if (gn == 0)
+                    const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
+                    const bool inr = r < F_0p4_HI && r > -F_0p4_HI;  // (:134)
+                    rm = fmaxf(rm, fabsf(r));
+                    rnan |= !(r == r);
+                    if (gn == 0 || !inr)
                     {
-                        hall[0] += t0, hall[1] += t1, hall[2] += t2, hall[3] += t3, hall[4] += t4;
-                        hall[5] += t5, hall[6] += t6, hall[7] += t7, hall[8] += t8, hall[9] += 2;
-                    }
-                    if (!inr)
-                    {
-                        ho[0] += t0, ho[1] += t1, ho[2] += t2, ho[3] += t3, ho[4] += t4;
-                        ho[5] += t5, ho[6] += t6, ho[7] += t7, ho[8] += t8, ho[9] += 2;
-                        if (r >= F_0p4_HI)
-                        { // (double)r >= 0.4 (:157-163)
-                            jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
-                            jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                        const double t0 = (double)(2 * ax * ax), t1 = (double)(2 * ax * ay), t2 = (double)(2 * ax * az), t3 = (double)(2 * ax);
+                        const double t4 = (double)(2 * ay * ay), t5 = (double)(2 * ay * az), t6 = (double)(2 * ay);
+                        const double t7 = (double)(2 * az * az), t8 = (double)(2 * az);
+                        if (gn == 0)
+                        {
+                            hall[0] += t0, hall[1] += t1, hall[2] += t2, hall[3] += t3, hall[4] += t4;
+                            hall[5] += t5, hall[6] += t6, hall[7] += t7, hall[8] += t8, hall[9] += 2;
+                            qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
                         }
-                        else if (r <= -F_0p4_HI)
-                        { // (double)r <= -0.4 (:164-170)
-                            jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
-                            jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
+                        if (!inr)
+                        {
+                            ho[0] += t0, ho[1] += t1, ho[2] += t2, ho[3] += t3, ho[4] += t4;
+                            ho[5] += t5, ho[6] += t6, ho[7] += t7, ho[8] += t8, ho[9] += 2;
+                            if (r >= F_0p4_HI)
+                            { // (double)r >= 0.4 (:157-163)
+                                jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
+                                jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                            }
+                            else if (r <= -F_0p4_HI)
+                            { // (double)r <= -0.4 (:164-170)
+                                jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
+                                jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
+                            }
                         }
                     }
+                };
+                int k = 0;
+                for (; k + 4 <= n; k += 4)
+                { // four points in flight: 12 coalesced loads issued before the first is consumed
+                    const float a0 = qx[k * st], a1 = qx[(k + 1) * st], a2 = qx[(k + 2) * st], a3 = qx[(k + 3) * st];
+                    const float b0 = qy[k * st], b1 = qy[(k + 1) * st], b2 = qy[(k + 2) * st], b3 = qy[(k + 3) * st];
+                    const float c0 = qz[k * st], c1 = qz[(k + 1) * st], c2 = qz[(k + 2) * st], c3 = qz[(k + 3) * st];
+                    point(a0, b0, c0);
+                    point(a1, b1, c1);
+                    point(a2, b2, c2);
+                    point(a3, b3, c3);
                 }
-            };
-            int k = 0;
-            for (; k + 4 <= n; k += 4)
-            { // four points in flight: 12 coalesced loads issued before the first is consumed
-                const float a0 = qx[k * st], a1 = qx[(k + 1) * st], a2 = qx[(k + 2) * st], a3 = qx[(k + 3) * st];
-                const float b0 = qy[k * st], b1 = qy[(k + 1) * st], b2 = qy[(k + 2) * st], b3 = qy[(k + 3) * st];
-                const float c0 = qz[k * st], c1 = qz[(k + 1) * st], c2 = qz[(k + 2) * st], c3 = qz[(k + 3) * st];
-                point(a0, b0, c0);
-                point(a1, b1, c1);
-                point(a2, b2, c2);
-                point(a3, b3, c3);
+                for (; k < n; k++) point(qx[k * st], qy[k * st], qz[k * st]);
+                rmax = rnan ? __int_as_float(0x7f800000) : rm; // a NaN residual forces every later pass
             }
-            for (; k < n; k++) point(qx[k * st], qy[k * st], qz[k * st]);
             double hh[10], jj[4];
 #pragma unroll
             for (int i = 0; i < 10; i++) hh[i] = hall[i] - ho[i];
@@ -914,10 +943,16 @@ __global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ Ds
             hh[0] += 5, hh[4] += 5, hh[7] += 5, hh[9] += 5; // LM damping (:172-175)
             double u[4];
             solve4_spd(hh, jj, u);
+            const float ox = nx, oy = ny, oz = nz, ob = nb;
             nx = (float)((double)nx - u[0]);
             ny = (float)((double)ny - u[1]);
             nz = (float)((double)nz - u[2]);
             nb = (float)((double)nb - u[3]);
+            // can the next pass be skipped?
+            const float dx = nx - ox, dy = ny - oy, dz = nz - oz;
+            const float bound = rmax + sqrtf(qmax2) * sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + fabsf(nb - ob) + 1e-3f;
+            need_pass = !(bound < 0.39f); // NaN-safe: any NaN keeps evaluating
+            rmax = bound;
         }
         nb = nb - (nx * mxs + ny * mys + nz * mzs);
         const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
@@ -1073,62 +1108,76 @@ __global__ void __launch_bounds__(FUSE_BLOCK) k_fuse(const __grid_constant__ Dsm
 // ballot + block scan so new_surfels come out in seed-index order exactly like the reference's
 // serial push_back loop.
 // -------------------------------------------------------------------------------------------
+#define INIT_PER_THREAD 8
 __global__ void __launch_bounds__(1024) k_init_surfels(const __grid_constant__ DsmDev d)
 {
     __shared__ int s_warp[32];
-    __shared__ int s_running;
+    __shared__ int s_total;
     __shared__ float s_pose[16];
     const int b = d.frame0 + blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t so = (size_t)b * d.S;
     if (threadIdx.x < 16) s_pose[threadIdx.x] = d.pose[b * 16 + threadIdx.x];
-    if (threadIdx.x == 0) s_running = 0;
-    __syncthreads();
     const int ref = d.refidx[b];
     dsm_surfel_t *out = d.newsurf + so;
-    for (int base = 0; base < d.S; base += 1024)
+    int running = 0;
+    // a thread owns INIT_PER_THREAD CONSECUTIVE seeds, so one block scan per 8192 seeds gives every
+    // thread the seed-index-ordered output position of its first emitted surfel
+    for (int base = 0; base < d.S; base += 1024 * INIT_PER_THREAD)
     {
-        const int s = base + threadIdx.x;
-        bool emit = false;
-        float4 r0, r1, r2;
-        if (s < d.S)
+        const int s0 = base + threadIdx.x * INIT_PER_THREAD;
+        unsigned emit = 0;
+#pragma unroll
+        for (int j = 0; j < INIT_PER_THREAD; j++)
         {
-            const float4 *pl = d.plane + (so + s) * 3;
-            r0 = pl[0], r1 = pl[1], r2 = pl[2];
-            emit = !(r1.w == 0) && !d.fused[so + s] && !((double)r0.w < MAX_ANGLE_COS) && !(r0.x == 0 && r0.y == 0 && r0.z == 0);
+            const int s = s0 + j;
+            if (s < d.S)
+            {
+                const float4 *pl = d.plane + (so + s) * 3;
+                const float4 r0 = pl[0];
+                const float md = pl[1].w;
+                const bool e = !(md == 0) && !d.fused[so + s] && !((double)r0.w < MAX_ANGLE_COS) &&
+                               !(r0.x == 0 && r0.y == 0 && r0.z == 0);
+                emit |= (e ? 1u : 0u) << j;
+            }
         }
-        const unsigned bal = __ballot_sync(FULL, emit);
-        const int rank = __popc(bal & ((1u << lane) - 1));
-        if (lane == 0) s_warp[warp] = __popc(bal);
+        const int cnt = __popc(emit);
+        int wtot;
+        const int wex = warp_excl_scan(cnt, lane, wtot);
+        if (lane == 31) s_warp[warp] = wtot;
         __syncthreads();
-        int wofs = 0, tot = 0;
-        for (int w = 0; w < 32; w++)
+        if (warp == 0)
         {
-            const int c = s_warp[w];
-            if (w < warp) wofs += c;
-            tot += c;
-        }
-        const int run = s_running;
-        if (emit)
-        {
-            float pw[4], nw[3];
-            mat4_mul(s_pose, r1.x, r1.y, r1.z, 1.0f, pw);
-            mat3_mul(s_pose, r0.x, r0.y, r0.z, nw);
-            dsm_surfel_t e;
-            e.px = pw[0], e.py = pw[1], e.pz = pw[2];
-            e.nx = nw[0], e.ny = nw[1], e.nz = nw[2];
-            e.size = (float)((double)r2.x * fabs((double)(r1.w / (d.camera_f * r0.w))));
-            e.color = r2.y;
-            e.weight = get_weight(r1.w);
-            e.update_times = 1;
-            e.last_update = ref;
-            out[run + wofs + rank] = e;
+            int t;
+            const int e = warp_excl_scan(s_warp[lane], lane, t);
+            s_warp[lane] = e;
+            if (lane == 0) s_total = t;
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_running = run + tot;
+        int pos = running + s_warp[warp] + wex;
+#pragma unroll
+        for (int j = 0; j < INIT_PER_THREAD; j++)
+            if ((emit >> j) & 1u)
+            {
+                const float4 *pl = d.plane + (so + s0 + j) * 3; // second read hits L1/L2
+                const float4 r0 = pl[0], r1 = pl[1], r2 = pl[2];
+                float pw[4], nw[3];
+                mat4_mul(s_pose, r1.x, r1.y, r1.z, 1.0f, pw);
+                mat3_mul(s_pose, r0.x, r0.y, r0.z, nw);
+                dsm_surfel_t e;
+                e.px = pw[0], e.py = pw[1], e.pz = pw[2];
+                e.nx = nw[0], e.ny = nw[1], e.nz = nw[2];
+                e.size = (float)((double)r2.x * fabs((double)(r1.w / (d.camera_f * r0.w))));
+                e.color = r2.y;
+                e.weight = get_weight(r1.w);
+                e.update_times = 1;
+                e.last_update = ref;
+                out[pos++] = e;
+            }
+        running += s_total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) d.nnew[b] = s_running;
+    if (threadIdx.x == 0) d.nnew[b] = running;
 }
 
 // -------------------------------------------------------------------------------------------
