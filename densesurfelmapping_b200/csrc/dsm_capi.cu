@@ -39,7 +39,7 @@ struct dsm_ctx
     // end-to-end pipeline (dsm_fuse_batch): packed staging + copy streams + per-chunk events
     uint8_t *gray_packed; // [B][H][W]
     float *depth_packed;  // [B][H][W]
-    cudaStream_t s_h2d, s_d2h;
+    cudaStream_t s_h2d, s_d2h, s_comp[4];
     cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
     // pinned host staging for the small per-batch tables
     float *h_pose; // [B][32]: pose then inverse
@@ -144,6 +144,8 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(ctx->depth_packed);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int i = 0; i < 4; i++)
+        if (ctx->s_comp[i]) cudaStreamDestroy(ctx->s_comp[i]);
     for (int i = 0; i < 8; i++)
     {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
@@ -186,6 +188,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->uploaded = ctx->ran = false;
     ctx->stop_after = 0;
     ctx->s_h2d = ctx->s_d2h = nullptr;
+    for (int i = 0; i < 4; i++) ctx->s_comp[i] = nullptr;
     ctx->ev_start = nullptr;
     for (int i = 0; i < 8; i++) ctx->ev_h2d[i] = ctx->ev_done[i] = nullptr;
     ctx->gray_packed = nullptr;
@@ -251,6 +254,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     d.frame0 = 0;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->s_comp[i], cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; i++)
     {
         e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
@@ -331,20 +335,21 @@ struct ProfScope
     int id;
     cudaEvent_t e0, e1;
     bool on;
-    ProfScope(dsm_ctx *c, int k) : ctx(c), id(k), on((c->prof_mask >> k) & 1u)
+    cudaStream_t st;
+    ProfScope(dsm_ctx *c, int k, cudaStream_t stream = nullptr) : ctx(c), id(k), on((c->prof_mask >> k) & 1u), st(stream ? stream : c->stream)
     {
         if (on)
         {
             e0 = prof_event(ctx);
             e1 = prof_event(ctx);
-            cudaEventRecord(e0, ctx->stream);
+            cudaEventRecord(e0, st);
         }
     }
     ~ProfScope()
     {
         if (on)
         {
-            cudaEventRecord(e1, ctx->stream);
+            cudaEventRecord(e1, st);
             ctx->prof_pending.push_back(ProfRec{id, e0, e1});
         }
     }
@@ -476,18 +481,17 @@ extern "C" int dsm_batch_restore_pool(dsm_ctx *ctx)
 
 // The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79),
 // enqueued for the frame slots [f0, f0 + nf).
-static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame)
+static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame, cudaStream_t st)
 {
     DsmDev d = ctx->d;
     d.frame0 = f0;
     d.max_pool_per_frame = max_pool_per_frame;
     const int nb = nf;
-    cudaStream_t st = ctx->stream;
     int budget = ctx->stop_after > 0 ? ctx->stop_after : 1 << 30;
 #define STEP(ID, CALL)                  \
     if (budget-- > 0)                   \
     {                                   \
-        ProfScope p(ctx, ID);           \
+        ProfScope p(ctx, ID, st);       \
         CALL;                           \
     }
     STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
@@ -523,7 +527,7 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
     if (!ctx) return DSM_E_INVALID;
     if (!ctx->uploaded) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    int rc = enqueue_schedule(ctx, 0, ctx->nb, ctx->d.max_pool_per_frame);
+    int rc = enqueue_schedule(ctx, 0, ctx->nb, ctx->d.max_pool_per_frame, ctx->stream);
     if (rc != DSM_OK) return rc;
     ctx->ran = true;
     return DSM_OK;
@@ -596,6 +600,7 @@ extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uin
     CK(cudaEventRecord(ctx->ev_start, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
     CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
+    for (int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(ctx->s_comp[i], ctx->ev_start, 0));
     int nc = 0;
     for (int f0 = 0; f0 < n; f0 += per, nc++)
     {
@@ -609,17 +614,19 @@ extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uin
         if (p1 > p0)
             CK(cudaMemcpyAsync(ctx->d.pool + p0, local + p0, (size_t)(p1 - p0) * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->s_h2d));
         CK(cudaEventRecord(ctx->ev_h2d[nc], ctx->s_h2d));
-        // kernels
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[nc], 0));
+        // kernels: each chunk on its own compute stream, so the latency-bound per-seed kernels of one
+        // chunk overlap the wide kernels of its neighbours instead of leaving SMs idle
+        cudaStream_t cs = nchunks > 1 ? ctx->s_comp[nc & 3] : ctx->stream;
+        CK(cudaStreamWaitEvent(cs, ctx->ev_h2d[nc], 0));
         {
             DsmDev d = ctx->d;
             d.frame0 = f0;
-            ProfScope p(ctx, DSM_K_REPACK);
-            dsm_launch_repack(d, nf, ctx->gray_packed + (size_t)f0 * fpx, ctx->depth_packed + (size_t)f0 * fpx, ctx->stream);
+            ProfScope p(ctx, DSM_K_REPACK, cs);
+            dsm_launch_repack(d, nf, ctx->gray_packed + (size_t)f0 * fpx, ctx->depth_packed + (size_t)f0 * fpx, cs);
         }
-        rc = enqueue_schedule(ctx, f0, nf, maxper);
+        rc = enqueue_schedule(ctx, f0, nf, maxper, cs);
         if (rc != DSM_OK) return rc;
-        CK(cudaEventRecord(ctx->ev_done[nc], ctx->stream));
+        CK(cudaEventRecord(ctx->ev_done[nc], cs));
         // D2H of this chunk
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[nc], 0));
         if (p1 > p0)
@@ -633,6 +640,7 @@ extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uin
     ctx->uploaded = true;
     ctx->ran = true;
     CK(cudaStreamSynchronize(ctx->s_h2d));
+    for (int i = 0; i < 4; i++) CK(cudaStreamSynchronize(ctx->s_comp[i]));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->s_d2h));
     CK(cudaGetLastError());
