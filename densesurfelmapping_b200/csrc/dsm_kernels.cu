@@ -40,6 +40,10 @@
 // -------------------------------------------------------------------------------------------
 // small helpers
 // -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts_f32(unsigned addr, float v)
+{ // st.shared with a precomputed 32-bit shared-window address (keeps the address math out of the hot loops)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
 __device__ __forceinline__ int chunk_of(int s, int S)
 { // which of the reference's 10 static chunks seed s falls in (:471-475)
     int step = S / DSM_THREAD_NUM;
@@ -221,7 +225,7 @@ __device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pi
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(256) k_assign(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDev d)
 {
     const int b = d.frame0 + blockIdx.z;
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
@@ -443,6 +447,9 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     if (live) // warp-uniform
     {
         const size_t fo = (size_t)b * d.px_stride;
+        const int32_t *lab = d.labels + fo; // per-frame bases once; 32-bit element offsets below
+        const float *dep = d.depth + fo;
+        const uint8_t *gry = d.gray + fo;
         const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
         const int xb = x0 > 0 ? x0 : 0, yb = y0 > 0 ? y0 : 0;
         const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
@@ -459,10 +466,11 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
             const int y = y0 + 8 * ps + (lane >> 2);
             yy[ps] = y;
             const bool in = colin && y >= yb && y < ye;
-            const size_t po = fo + (size_t)(in ? y * Wp + xq : 0);
-            l4[ps] = in ? *reinterpret_cast<const int4 *>(d.labels + po) : make_int4(-1, -1, -1, -1);
-            z4[ps] = in ? *reinterpret_cast<const float4 *>(d.depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
-            g4[ps] = in ? *reinterpret_cast<const uchar4 *>(d.gray + po) : make_uchar4(0, 0, 0, 0);
+            const unsigned po = in ? (unsigned)(y * Wp + xq) : 0u;
+            l4[ps] = *reinterpret_cast<const int4 *>(lab + po); // out-of-window lanes read element 0 and are masked below
+            z4[ps] = *reinterpret_cast<const float4 *>(dep + po);
+            g4[ps] = *reinterpret_cast<const uchar4 *>(gry + po);
+            if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
         }
         unsigned mdm = 0; // bit 4*ps+k: member with depth > 0.1
         int cnt2 = 0;     // member count, pass 0 in the low half-word, pass 1 in the high one
@@ -496,19 +504,22 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
         int tot2;
         const int ex2 = warp_excl_scan(c2, lane, tot2);
         const int n0 = tot2 & 0xffff, ndt = n0 + (tot2 >> 16);
-        int pos = ex2 & 0xffff;
+        const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
+        unsigned a0 = tbase + 32u * (ex2 & 0xffff), a1 = tbase + 32u * (n0 + (ex2 >> 16)); // 32 bytes per list row
+        const float za[4] = {z4[0].x, z4[0].y, z4[0].z, z4[0].w}, zb[4] = {z4[1].x, z4[1].y, z4[1].z, z4[1].w};
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
-            const float zk = k == 0 ? z4[0].x : k == 1 ? z4[0].y : k == 2 ? z4[0].z : z4[0].w;
-            if ((mdm >> k) & 1u) tile[(pos++) * 8 + warp] = zk;
-        }
-        pos = n0 + (ex2 >> 16);
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-        {
-            const float zk = k == 0 ? z4[1].x : k == 1 ? z4[1].y : k == 2 ? z4[1].z : z4[1].w;
-            if ((mdm >> (4 + k)) & 1u) tile[(pos++) * 8 + warp] = zk;
+            if ((mdm >> k) & 1u)
+            {
+                sts_f32(a0, za[k]);
+                a0 += 32u;
+            }
+            if ((mdm >> (4 + k)) & 1u)
+            {
+                sts_f32(a1, zb[k]);
+                a1 += 32u;
+            }
         }
         if (lane == 0)
         {
@@ -726,28 +737,32 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
     if (sp_x < d.spw) // warp-uniform
     {
         const size_t fo = (size_t)b * d.px_stride;
+        const int32_t *lab = d.labels + fo; // per-frame bases once; 32-bit element offsets below
+        const float *dep = d.depth + fo;
+        const float *nrx = d.nrm + fo, *nry = nrx + d.nrm_plane, *nrz = nry + d.nrm_plane;
         const float4 sd = d.seed[so + s]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
         const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
         const int xq = x0 + 4 * (lane & 3);
         const bool colin = xq >= 0 && xq < Wp;
-        const float4 k4 = colin ? *reinterpret_cast<const float4 *>(d.kx + xq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 k4 = *reinterpret_cast<const float4 *>(d.kx + (colin ? xq : 0));
         const float kxv[4] = {k4.x, k4.y, k4.z, k4.w};
         int4 l4[2];
         float4 z4[2];
         float kyv[2];
         int yy[2];
-        size_t pof[2];
+        unsigned pof[2];
 #pragma unroll
         for (int ps = 0; ps < 2; ps++)
         {
             const int y = y0 + 8 * ps + (lane >> 2);
             yy[ps] = y;
             const bool in = colin && y >= 0 && y < H;
-            const size_t po = fo + (size_t)(in ? y * Wp + xq : 0);
+            const unsigned po = in ? (unsigned)(y * Wp + xq) : 0u;
             pof[ps] = po;
-            l4[ps] = in ? *reinterpret_cast<const int4 *>(d.labels + po) : make_int4(-1, -1, -1, -1);
-            z4[ps] = in ? *reinterpret_cast<const float4 *>(d.depth + po) : make_float4(0.f, 0.f, 0.f, 0.f);
-            kyv[ps] = in ? d.ky[y] : 0.f;
+            l4[ps] = *reinterpret_cast<const int4 *>(lab + po); // out-of-window lanes read element 0 and are masked below
+            z4[ps] = *reinterpret_cast<const float4 *>(dep + po);
+            kyv[ps] = d.ky[in ? y : 0];
+            if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
         }
         unsigned inl = 0; // bit 4*ps+k: inlier
         int nvalid = 0;
@@ -780,9 +795,9 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
             }
             if (mi)
             { // pixel normals of this 4-pixel group: three 16-byte loads instead of up to 12 scalar ones
-                const float4 a = *reinterpret_cast<const float4 *>(d.nrm + pof[ps]);
-                const float4 bb = *reinterpret_cast<const float4 *>(d.nrm + d.nrm_plane + pof[ps]);
-                const float4 c = *reinterpret_cast<const float4 *>(d.nrm + 2 * d.nrm_plane + pof[ps]);
+                const float4 a = *reinterpret_cast<const float4 *>(nrx + pof[ps]);
+                const float4 bb = *reinterpret_cast<const float4 *>(nry + pof[ps]);
+                const float4 c = *reinterpret_cast<const float4 *>(nrz + pof[ps]);
                 const float ax[4] = {a.x, a.y, a.z, a.w}, ay[4] = {bb.x, bb.y, bb.z, bb.w}, az[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
@@ -803,20 +818,20 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
             snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
             const float fn = (float)ninl;
             const float mxs = warp_sum_f(spx) / fn, mys = warp_sum_f(spy) / fn, mzs = warp_sum_f(spz) / fn; // (:117-119)
+            const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
 #pragma unroll
             for (int ps = 0; ps < 2; ps++)
             {
-                int pos = ps == 0 ? (ex2 & 0xffff) : n0 + (ex2 >> 16);
+                unsigned a = tbase + 32u * (ps == 0 ? (ex2 & 0xffff) : n0 + (ex2 >> 16)); // 32 bytes per list row
                 const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if ((inl >> (4 * ps + k)) & 1u)
                     {
-                        const int t = pos * 8 + warp;
-                        tile[t] = kxv[k] * zk[k] - mxs; // centred points (:121-126)
-                        tile[PF_CAP * 8 + t] = kyv[ps] * zk[k] - mys;
-                        tile[2 * PF_CAP * 8 + t] = zk[k] - mzs;
-                        pos++;
+                        sts_f32(a, kxv[k] * zk[k] - mxs); // centred points (:121-126)
+                        sts_f32(a + 4u * PF_CAP * 8, kyv[ps] * zk[k] - mys);
+                        sts_f32(a + 8u * PF_CAP * 8, zk[k] - mzs);
+                        a += 32u;
                     }
             }
             P0 = make_float4(snx, sny, snz, maxd);
