@@ -23,7 +23,8 @@ NUM_KERNELS = 12
 EXPORTS = [
     "dsm_version", "dsm_strerror", "dsm_last_error", "dsm_create", "dsm_destroy", "dsm_num_seeds",
     "dsm_fuse_frame", "dsm_batch_upload", "dsm_batch_run", "dsm_batch_download", "dsm_sync",
-    "dsm_fuse_batch", "dsm_batch_restore_pool", "dsm_get_labels", "dsm_get_seeds",
+    "dsm_fuse_batch", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
+    "dsm_pool_transform", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
 ]
 
@@ -72,6 +73,11 @@ def load_library():
     L.dsm_sync.argtypes = [vp]
     L.dsm_fuse_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
     L.dsm_batch_restore_pool.argtypes = [vp]
+    L.dsm_pool_upload.argtypes = [vp, vp, ci]
+    L.dsm_fuse_frame_resident.argtypes = [vp, ci, vp, cs, vp, cs, vp, ctypes.POINTER(ci)]
+    L.dsm_pool_transform.argtypes = [vp, vp]
+    L.dsm_pool_size.argtypes = [vp, ctypes.POINTER(ci)]
+    L.dsm_pool_download.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
     L.dsm_get_labels.argtypes = [vp, ci, vp]
     L.dsm_get_seeds.argtypes = [vp, ci, vp]
     L.dsm_debug_stop_after.argtypes = [vp, ci]
@@ -170,6 +176,36 @@ class Context:
         self.batch_upload(ref_idx, gray, depth, poses, local, offsets)
         self.batch_run()
         return self.batch_download()
+
+    # ---- GPU-resident pool (stream mode) ----
+    def pool_upload(self, local):
+        local = np.ascontiguousarray(local, dtype=SURFEL_DTYPE)
+        self._ck(self.lib.dsm_pool_upload(self.h, _ptr(local) if len(local) else None, len(local)))
+
+    def fuse_frame_resident(self, ref_idx, gray, depth, pose, want_count=False):
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        pose = np.ascontiguousarray(pose, dtype=np.float32).reshape(16)
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_fuse_frame_resident(self.h, int(ref_idx), _ptr(gray), gray.strides[0], _ptr(depth), depth.strides[0],
+                                                  _ptr(pose), ctypes.byref(n) if want_count else None))
+        return n.value if want_count else None
+
+    def pool_transform(self, W_colmajor):
+        w = np.ascontiguousarray(W_colmajor, dtype=np.float32).reshape(16)
+        self._ck(self.lib.dsm_pool_transform(self.h, _ptr(w)))
+
+    def pool_size(self):
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_pool_size(self.h, ctypes.byref(n)))
+        return n.value
+
+    def pool_download(self):
+        n = self.pool_size()
+        out = np.zeros(n, dtype=SURFEL_DTYPE)
+        c = ctypes.c_int(0)
+        self._ck(self.lib.dsm_pool_download(self.h, _ptr(out) if n else None, n, ctypes.byref(c)))
+        return out[:c.value]
 
     # ---- parity readback ----
     def labels(self, frame=0):

@@ -40,6 +40,11 @@ struct dsm_ctx
     uint8_t *gray_packed; // [B][H][W]
     float *depth_packed;  // [B][H][W]
     cudaStream_t s_h2d, s_d2h, s_comp[4];
+    // resident pool (stream mode)
+    int res_upper;      // host-side upper bound of the resident pool size (exact after a sync)
+    bool res_active;
+    int *blkcnt, *blkofs, *newofs;
+    float *wmat;        // device copy of the 4x4 of dsm_pool_transform
     cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
     // pinned host staging for the small per-batch tables
     float *h_pose; // [B][32]: pose then inverse
@@ -141,6 +146,10 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(ctx->kx);
     cudaFree(ctx->ky);
     cudaFree(ctx->gray_packed);
+    cudaFree(ctx->blkcnt);
+    cudaFree(ctx->blkofs);
+    cudaFree(ctx->newofs);
+    cudaFree(ctx->wmat);
     cudaFree(ctx->depth_packed);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -192,6 +201,10 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->ev_start = nullptr;
     for (int i = 0; i < 8; i++) ctx->ev_h2d[i] = ctx->ev_done[i] = nullptr;
     ctx->gray_packed = nullptr;
+    ctx->res_upper = 0;
+    ctx->res_active = false;
+    ctx->blkcnt = ctx->blkofs = ctx->newofs = nullptr;
+    ctx->wmat = nullptr;
     ctx->depth_packed = nullptr;
     ctx->own_stream = (cuda_stream == nullptr);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -249,6 +262,10 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(ctx->ky, (size_t)H + 16);
     ALLOC(ctx->gray_packed, (size_t)B * H * W + 64);
     ALLOC(ctx->depth_packed, (size_t)B * H * W + 64);
+    ALLOC(ctx->blkcnt, npool / 256 + 2);
+    ALLOC(ctx->blkofs, npool / 256 + 2);
+    ALLOC(ctx->newofs, 2);
+    ALLOC(ctx->wmat, 16);
 #undef ALLOC
     d.nrm_plane = B * px;
     d.frame0 = 0;
@@ -466,6 +483,7 @@ extern "C" int dsm_batch_upload(dsm_ctx *ctx, int n, const int32_t *ref, const u
     ctx->nb = n;
     ctx->uploaded = true;
     ctx->ran = false;
+    ctx->res_active = false;
     return DSM_OK;
 }
 
@@ -682,6 +700,115 @@ extern "C" int dsm_fuse_frame(dsm_ctx *ctx, int ref_idx, const uint8_t *gray, si
         CK(cudaStreamSynchronize(ctx->stream));
     }
     CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+// ---- GPU-resident pool (stream mode) ----
+extern "C" int dsm_pool_upload(dsm_ctx *ctx, const dsm_surfel_t *local, int n)
+{
+    if (!ctx || n < 0 || (n > 0 && !local)) return DSM_E_INVALID;
+    if (n > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n > 0) CK(cudaMemcpyAsync(ctx->d.pool, local, (size_t)n * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_ofs[0] = 0;
+    ctx->h_ofs[1] = n;
+    CK(cudaMemcpyAsync(ctx->poolofs, ctx->h_ofs, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->res_upper = n;
+    ctx->res_active = true;
+    ctx->n_pool = n;
+    return DSM_OK;
+}
+
+extern "C" int dsm_pool_size(dsm_ctx *ctx, int *n)
+{
+    if (!ctx || !n) return DSM_E_INVALID;
+    if (!ctx->res_active) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int32_t h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->poolofs, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n = h[1];
+    ctx->res_upper = h[1];
+    return DSM_OK;
+}
+
+extern "C" int dsm_pool_download(dsm_ctx *ctx, dsm_surfel_t *out, int cap, int *n)
+{
+    if (!ctx || !n || cap < 0 || (cap > 0 && !out)) return DSM_E_INVALID;
+    int rc = dsm_pool_size(ctx, n);
+    if (rc != DSM_OK) return rc;
+    const int c = *n < cap ? *n : cap;
+    if (c > 0)
+    {
+        CK(cudaMemcpyAsync(out, ctx->d.pool, (size_t)c * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return DSM_OK;
+}
+
+extern "C" int dsm_pool_transform(dsm_ctx *ctx, const float Wm[16])
+{
+    if (!ctx || !Wm) return DSM_E_INVALID;
+    if (!ctx->res_active) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->wmat, Wm, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    DsmDev d = ctx->d;
+    d.frame0 = 0;
+    dsm_launch_pool_transform(d, 0, ctx->res_upper, ctx->wmat, ctx->stream);
+    CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+extern "C" int dsm_fuse_frame_resident(dsm_ctx *ctx, int ref_idx, const uint8_t *gray, size_t gray_pitch,
+                                       const float *depth, size_t depth_pitch, const float pose[16], int *n_new)
+{
+    if (!ctx || !gray || !depth || !pose) return DSM_E_INVALID;
+    if (!ctx->res_active) return DSM_E_STATE;
+    const int W = ctx->p.width, H = ctx->p.height;
+    if (gray_pitch < (size_t)W || depth_pitch < (size_t)W * 4) return DSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->res_upper + ctx->S > ctx->p.max_local_surfels)
+    { // the bound may be loose: fetch the exact size before giving up
+        int n = 0;
+        int rc = dsm_pool_size(ctx, &n);
+        if (rc != DSM_OK) return rc;
+        if (n + ctx->S > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
+    }
+    // the small pinned tables are reused per call
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_pose, pose, 16 * sizeof(float));
+    inverse4f(pose, ctx->h_pose + 16);
+    ctx->h_ref[0] = ref_idx;
+    CK(cudaMemcpyAsync(ctx->pose, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ipose, ctx->h_pose + 16, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->refidx, ctx->h_ref, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->gray, ctx->Wp, gray, gray_pitch, W, H, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->depth, (size_t)ctx->Wp * 4, depth, depth_pitch, (size_t)W * 4, H, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->nb = 1;
+    ctx->uploaded = true;
+    int rc = enqueue_schedule(ctx, 0, 1, ctx->res_upper, ctx->stream);
+    if (rc != DSM_OK) return rc;
+    ctx->ran = true;
+    // post-step of SurfelMap::fuse_map on the device: compact into the alternate buffer, then swap
+    {
+        DsmDev d = ctx->d;
+        d.frame0 = 0;
+        dsm_launch_pool_compact(d, 0, ctx->res_upper, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
+        CK(cudaMemcpyAsync(ctx->poolofs + 1, ctx->newofs + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        dsm_surfel_t *t = ctx->d.pool;
+        ctx->d.pool = ctx->pool_snap;
+        ctx->pool_snap = t;
+    }
+    ctx->res_upper += ctx->S; // every seed can add at most one surfel; dsm_pool_size() tightens it
+    CK(cudaGetLastError());
+    if (n_new)
+    {
+        int32_t c = 0;
+        CK(cudaMemcpyAsync(&c, ctx->d.nnew, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *n_new = c;
+    }
     return DSM_OK;
 }
 

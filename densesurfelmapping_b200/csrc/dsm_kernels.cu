@@ -1196,6 +1196,121 @@ __global__ void __launch_bounds__(1024) k_init_surfels(const __grid_constant__ D
 }
 
 // -------------------------------------------------------------------------------------------
+// GPU-resident pool: what SurfelMap does to `local_surfels` between and
+// after the hot-path calls, kept on the device so a stream never round-trips its pool.
+//
+// k_pool_count / k_pool_scan / k_pool_scatter / k_pool_append — the post-fusion step of
+//   SurfelMap::fuse_map (surfel_map.cpp:1077-1109): drop surfels with update_times == 0, add the
+//   newly initialised ones.  The reference recycles freed slots from the highest index and swaps
+//   the rest with the back, which is inherently sequential; here it is a deterministic ordered
+//   compaction (live surfels keep their order, new ones follow), so the resulting pool equals the
+//   reference's AS A SET (nothing on the path depends on pool order).
+// k_pool_transform — warp_active_surfels_cpu_kernel (surfel_map.cpp:750-789): p <- W p, n <- R_W n
+//   for every surfel of the pool after a loop closure.  Pure streaming over the 44-byte records,
+//   staged through shared memory like k_fuse.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pool_count(const __grid_constant__ DsmDev d, int b, int *blkcnt)
+{
+    const int begin = d.poolofs[b], end = d.poolofs[b + 1];
+    const int i = begin + blockIdx.x * 256 + threadIdx.x;
+    const bool live = i < end && d.pool[i].update_times != 0;
+    const int c = __syncthreads_count(live);
+    if (threadIdx.x == 0) blkcnt[blockIdx.x] = (begin + blockIdx.x * 256 < end) ? c : 0;
+}
+
+__global__ void __launch_bounds__(1024) k_pool_scan(const __grid_constant__ DsmDev d, int b, const int *blkcnt, int *blkofs, int *newofs)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    const int begin = d.poolofs[b], end = d.poolofs[b + 1];
+    const int nblk = (end - begin + 255) / 256;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += 1024)
+    {
+        const int i = base + threadIdx.x;
+        const int v = i < nblk ? blkcnt[i] : 0;
+        int wtot;
+        const int wex = warp_excl_scan(v, lane, wtot);
+        if (lane == 31) s_warp[warp] = wtot;
+        __syncthreads();
+        const int run = s_run;
+        int wofs = 0, tot = 0;
+        for (int w = 0; w < 32; w++)
+        {
+            const int c = s_warp[w];
+            if (w < warp) wofs += c;
+            tot += c;
+        }
+        if (i < nblk) blkofs[i] = run + wofs + wex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run = run + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        newofs[0] = s_run;                // live surfels kept
+        newofs[1] = s_run + d.nnew[b];    // new pool size
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pool_scatter(const __grid_constant__ DsmDev d, int b, const int *blkofs, dsm_surfel_t *dst)
+{
+    __shared__ int s_warp[8];
+    const int begin = d.poolofs[b], end = d.poolofs[b + 1];
+    const int i = begin + blockIdx.x * 256 + threadIdx.x;
+    if (begin + blockIdx.x * 256 >= end) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    dsm_surfel_t e;
+    bool live = false;
+    if (i < end)
+    {
+        e = d.pool[i];
+        live = e.update_times != 0;
+    }
+    const unsigned bal = __ballot_sync(FULL, live);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wofs = 0;
+    for (int w = 0; w < warp; w++) wofs += s_warp[w];
+    if (live) dst[blkofs[blockIdx.x] + wofs + __popc(bal & ((1u << lane) - 1))] = e;
+}
+
+__global__ void __launch_bounds__(256) k_pool_append(const __grid_constant__ DsmDev d, int b, const int *newofs, dsm_surfel_t *dst)
+{
+    const int n = d.nnew[b];
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j < n) dst[newofs[0] + j] = d.newsurf[(size_t)b * d.S + j];
+}
+
+#define XF_BLOCK 256
+__global__ void __launch_bounds__(XF_BLOCK) k_pool_transform(const __grid_constant__ DsmDev d, int b, const float *Wm)
+{
+    __shared__ float sm[XF_BLOCK * 11];
+    __shared__ float s_w[16];
+    const int begin = d.poolofs[b], end = d.poolofs[b + 1];
+    const int first = begin + blockIdx.x * XF_BLOCK;
+    if (first >= end) return;
+    const int cnt = min(XF_BLOCK, end - first);
+    float *g = reinterpret_cast<float *>(d.pool + first);
+    for (int i = threadIdx.x; i < cnt * 11; i += XF_BLOCK) sm[i] = g[i];
+    if (threadIdx.x < 16) s_w[threadIdx.x] = Wm[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < cnt)
+    {
+        float *e = sm + threadIdx.x * 11;
+        float pw[4], nw[3];
+        mat4_mul(s_w, e[0], e[1], e[2], 1.0f, pw);
+        mat3_mul(s_w, e[3], e[4], e[5], nw);
+        e[0] = pw[0], e[1] = pw[1], e[2] = pw[2];
+        e[3] = nw[0], e[4] = nw[1], e[5] = nw[2];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 11; i += XF_BLOCK) g[i] = sm[i];
+}
+
+// -------------------------------------------------------------------------------------------
 // parity readback: rebuild the reference's 60-byte Superpixel_seed records for one frame
 // -------------------------------------------------------------------------------------------
 __global__ void k_seeds_export(const __grid_constant__ DsmDev d, int b, dsm_seed_t *out, int raw_md)
@@ -1282,4 +1397,18 @@ void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s) { k_init_s
 void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, int raw_md, cudaStream_t s)
 {
     k_seeds_export<<<(d.S + 255) / 256, 256, 0, s>>>(d, frame, out_dev, raw_md);
+}
+
+void dsm_launch_pool_compact(const DsmDev &d, int frame, int upper, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, cudaStream_t s)
+{
+    const int nblk = (upper + 255) / 256;
+    if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt);
+    k_pool_scan<<<1, 1024, 0, s>>>(d, frame, blkcnt, blkofs, newofs);
+    if (nblk > 0) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst);
+    k_pool_append<<<(d.S + 255) / 256, 256, 0, s>>>(d, frame, newofs, dst);
+}
+void dsm_launch_pool_transform(const DsmDev &d, int frame, int upper, const float *Wm_dev, cudaStream_t s)
+{
+    if (upper <= 0) return;
+    k_pool_transform<<<(upper + XF_BLOCK - 1) / XF_BLOCK, XF_BLOCK, 0, s>>>(d, frame, Wm_dev);
 }

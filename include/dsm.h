@@ -141,6 +141,28 @@ int dsm_fuse_batch(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_in
  * taken at the last dsm_batch_upload. */
 int dsm_batch_restore_pool(dsm_ctx *ctx);
 
+/* ---- GPU-resident pool for a sequential stream ----
+ * The pool of ONE stream lives on the device between frames (frame slot 0 of the context), so per
+ * frame only the image pair and the pose cross PCIe.  Semantics mirror what SurfelMap does around
+ * the hot-path call:
+ *   dsm_pool_upload            local_surfels := given array
+ *   dsm_fuse_frame_resident    fuse_initialize_map on the resident pool, THEN the post-step of
+ *                              SurfelMap::fuse_map (surfel_map.cpp:1077-1109): dead surfels dropped,
+ *                              new surfels added.  The resulting pool equals the reference's as a
+ *                              SET (the reference's slot recycling order is not reproduced).
+ *                              *n_new (optional) = number of new surfels; passing it synchronises.
+ *   dsm_pool_transform         warp_active_surfels_cpu_kernel (surfel_map.cpp:750-789):
+ *                              p <- W p, n <- R_W n for every pool surfel after a loop closure
+ *                              (W = T_loop * T_cam^-1 computed by the caller in fp64, cast to f32).
+ *   dsm_pool_size / dsm_pool_download   read back (synchronise). */
+int dsm_pool_upload(dsm_ctx *ctx, const dsm_surfel_t *local, int n_local);
+int dsm_fuse_frame_resident(dsm_ctx *ctx, int reference_frame_index,
+                            const uint8_t *gray, size_t gray_pitch, const float *depth, size_t depth_pitch,
+                            const float pose_colmajor[16], int *n_new);
+int dsm_pool_transform(dsm_ctx *ctx, const float W_colmajor[16]);
+int dsm_pool_size(dsm_ctx *ctx, int *n_local);
+int dsm_pool_download(dsm_ctx *ctx, dsm_surfel_t *out, int cap, int *n_local);
+
 /* ---- parity / debug readback (what the reference keeps private: fusion_functions.h:34-37) ---- */
 int dsm_get_labels(dsm_ctx *ctx, int frame, int32_t *labels_hw);   /* superpixel_index, [H][W] */
 int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds_s);   /* superpixel_seeds, [S] */

@@ -750,6 +750,54 @@ static int initialize_surfels(ctx_t *c, int ref_idx, const float *pose, surfel_t
     return n;
 }
 
+/* ---- the caller-side steps the GPU-resident pool mode takes over ----
+ * These two follow surfel_fusion/src/surfel_map.cpp, which cannot be compiled here (ROS/PCL), so they
+ * are restatements only: "parity unpinned" against the reference binary for these two functions. */
+
+/* SurfelMap::fuse_map post-step (surfel_map.cpp:1077-1109): recycle deleted slots from the highest
+ * index for the new surfels, push_back the rest, then swap-with-back the leftover deleted slots.
+ * local must have room for n_local + n_new elements.  Returns the new size. */
+int dsmor_fuse_map_poststep(void *local_v, int n_local, const void *fresh_v, int n_new)
+{
+    surfel_t *local = (surfel_t *)local_v;
+    const surfel_t *fresh = (const surfel_t *)fresh_v;
+    int *deleted = (int *)malloc(sizeof(int) * (size_t)(n_local > 0 ? n_local : 1));
+    int nd = 0, size = n_local;
+    for (int i = 0; i < n_local; i++)
+        if (local[i].update_times == 0) deleted[nd++] = i;
+    for (int i = 0; i < n_new; i++)
+    {
+        if (fresh[i].update_times != 0)
+        {
+            if (nd > 0)
+                local[deleted[--nd]] = fresh[i];
+            else
+                local[size++] = fresh[i];
+        }
+    }
+    while (nd > 0)
+    {
+        local[deleted[--nd]] = local[size - 1];
+        size--;
+    }
+    free(deleted);
+    return size;
+}
+
+/* warp_active_surfels_cpu_kernel (surfel_map.cpp:750-789): p <- W p (homogeneous), n <- R_W n */
+void dsmor_warp_active(void *surfels_v, int n, const float *W)
+{
+    surfel_t *e = (surfel_t *)surfels_v;
+    for (int i = 0; i < n; i++)
+    {
+        float p[4], nn[3];
+        mat4_mul_vec4(W, e[i].px, e[i].py, e[i].pz, 1.0f, p);
+        mat3_mul_vec3(W, e[i].nx, e[i].ny, e[i].nz, nn);
+        e[i].px = p[0], e[i].py = p[1], e[i].pz = p[2];
+        e[i].nx = nn[0], e[i].ny = nn[1], e[i].nz = nn[2];
+    }
+}
+
 /* ================= exported test entry points (same shape as oracle/ref_driver.cpp) ================= */
 void dsmor_superpixels(void *p, const uint8_t *gray, const float *depth)
 {

@@ -137,6 +137,28 @@ class Restatement(_Base):
         return self.labels(), self.seeds()
 
 
+def fuse_map_poststep(local, new):
+    """SurfelMap::fuse_map post-step (surfel_map.cpp:1077-1109) via the restatement; returns the new pool."""
+    lib = _lib("libdsm_oracle.so")
+    lib.dsmor_fuse_map_poststep.restype = ctypes.c_int
+    lib.dsmor_fuse_map_poststep.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    buf = np.zeros(len(local) + len(new) + 1, dtype=SURFEL_DTYPE)
+    buf[:len(local)] = local
+    new = np.ascontiguousarray(new, dtype=SURFEL_DTYPE)
+    n = lib.dsmor_fuse_map_poststep(buf.ctypes.data, len(local), new.ctypes.data if len(new) else None, len(new))
+    return buf[:n].copy()
+
+
+def warp_active(surfels, W_colmajor):
+    """warp_active_surfels_cpu_kernel (surfel_map.cpp:750-789) via the restatement."""
+    lib = _lib("libdsm_oracle.so")
+    lib.dsmor_warp_active.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    out = np.array(surfels, dtype=SURFEL_DTYPE, copy=True)
+    w = np.ascontiguousarray(W_colmajor, dtype=np.float32).reshape(16)
+    lib.dsmor_warp_active(out.ctypes.data if len(out) else None, len(out), w.ctypes.data)
+    return out
+
+
 def have_reference():
     return os.path.exists(os.path.join(REFDIR, "libdsm_ref_serial.so"))
 

@@ -1,0 +1,101 @@
+"""GPU-resident pool mode: device-side post-fusion compaction/append and the
+loop-closure pool transform, against the restated caller-side steps of SurfelMap."""
+import numpy as np
+import pytest
+
+import pyoracle
+from densesurfelmapping_b200 import synth
+from densesurfelmapping_b200.elements import SURFEL_DTYPE
+from util import check_surfels, oracle_for
+
+pytestmark = pytest.mark.gpu
+
+
+def match_as_sets(got, want, tol=1e-4):
+    """Pools are equal as sets: same size, and a one-to-one nearest-neighbour matching within tolerance."""
+    assert len(got) == len(want), f"pool size {len(got)} != {len(want)}"
+    if len(got) == 0:
+        return
+    key = lambda a: np.lexsort((a["pz"], a["py"], a["px"], a["last_update"], a["update_times"]))
+    g, w = got[key(got)], want[key(want)]
+    # lexsort on floats can differ in the last bits; repair by nearest neighbour inside equal-integer groups
+    pg = np.stack([g["px"], g["py"], g["pz"]], -1).astype(np.float64)
+    pw = np.stack([w["px"], w["py"], w["pz"]], -1).astype(np.float64)
+    bad = np.nonzero(np.linalg.norm(pg - pw, axis=1) > tol * np.maximum(np.linalg.norm(pw, axis=1), 1.0))[0]
+    if len(bad):
+        used = set()
+        for i in bad:
+            dist = np.linalg.norm(pw[bad] - pg[i], axis=1)
+            j = int(np.argmin(dist))
+            assert dist[j] <= tol * max(np.linalg.norm(pg[i]), 1.0) and j not in used, f"surfel {i} has no partner"
+            used.add(j)
+            g[i], w_i = g[i], w[bad[j]]
+            check_surfels(g[i:i + 1], np.array([w_i]), "set member")
+        ok = np.setdiff1d(np.arange(len(g)), bad)
+        check_surfels(g[ok], w[ok], "pool (sorted)")
+    else:
+        check_surfels(g, w, "pool (sorted)")
+
+
+def test_resident_stream_matches_reference_flow():
+    """Per frame: hot path on the resident pool + device compaction/append == oracle fuse + fuse_map post-step."""
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=100000)
+    orc = oracle_for(cam)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    ctx.pool_upload(pool)
+    for t in range(4):
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(cam, 300 + t, pose)
+        lo, no = orc.fuse(t // 2 + (7 if t == 3 else 0), gray, depth, pose, pool)  # the jump in ref idx kills unstable surfels
+        want = pyoracle.fuse_map_poststep(lo, no)
+        ctx.pool_upload(pool)  # re-sync to the oracle's pool so one tolerance-sized drift cannot flip a decision later
+        n_new = ctx.fuse_frame_resident(t // 2 + (7 if t == 3 else 0), gray, depth, pose, want_count=True)
+        assert n_new == len(no)
+        got = ctx.pool_download()
+        match_as_sets(got, want)
+        assert (got["update_times"] > 0).all()
+        pool = want
+    assert (lo["update_times"] == 0).sum() > 0, "test never exercised the kill path"
+    ctx.close()
+
+
+def test_resident_stream_free_running():
+    """No re-sync: 6 frames carried entirely on the device stay within tolerance of the oracle flow."""
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=100000)
+    orc = oracle_for(cam)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    ctx.pool_upload(pool)
+    for t in range(6):
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(cam, 400 + t, pose)
+        lo, no = orc.fuse(t // 2, gray, depth, pose, pool)
+        pool = pyoracle.fuse_map_poststep(lo, no)
+        ctx.fuse_frame_resident(t // 2, gray, depth, pose)
+    got = ctx.pool_download()
+    assert abs(len(got) - len(pool)) <= max(2, len(pool) // 500)
+    if len(got) == len(pool):
+        match_as_sets(got, pool, tol=1e-3)
+    ctx.close()
+
+
+def test_pool_transform_loop_closure():
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    gray, depth = synth.make_frame(cam, 0)
+    orc = oracle_for(cam)
+    _, pool = orc.fuse(0, gray, depth, synth.identity_pose(), np.zeros(0, SURFEL_DTYPE))
+    a = np.deg2rad(2.0)
+    Wm = np.eye(4)
+    Wm[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+    Wm[:3, 3] = [0.5, -0.1, 0.25]
+    w = np.ascontiguousarray(Wm.T.astype(np.float32).reshape(16))
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=len(pool) + 10)
+    ctx.pool_upload(pool)
+    ctx.pool_transform(w)
+    got = ctx.pool_download()
+    check_surfels(got, pyoracle.warp_active(pool, w), "warped pool")
+    ctx.close()
