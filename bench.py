@@ -240,6 +240,74 @@ def kernel_alg_bytes(name, P, S, npool, nnew):
     }.get(name, 0)
 
 
+def run_extras(cam, local_rank, stream):
+    """Secondary measurements reported next to the headline (not part of `value`):
+    - stream: BASELINE configs[1], a sequential 1226x370 stream on the GPU-resident pool
+      (dsm_fuse_frame_resident: per frame H2D of the image pair + all kernels + device-side compaction);
+    - pool_transform: the loop-closure re-deformation kernel, a pure streaming kernel."""
+    import torch
+    from densesurfelmapping_b200 import capi, synth
+    from densesurfelmapping_b200.elements import SURFEL_DTYPE
+    out = {}
+    T = 24
+    cache = f"/tmp/dsm_bench_stream_{cam.width}x{cam.height}_{T}.npz"
+    try:
+        z = np.load(cache)
+        G, D, Pz = z["g"], z["d"], z["p"]
+    except Exception:
+        fr = [synth.make_frame(cam, 5000 + t, synth.pose_stream(t)) for t in range(T)]
+        G, D = np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr])
+        Pz = np.stack([synth.pose_stream(t) for t in range(T)])
+        try:
+            np.savez(cache, g=G, d=D, p=Pz)
+        except Exception:
+            pass
+    tg, td = torch.from_numpy(G).pin_memory(), torch.from_numpy(D).pin_memory()
+    hg, hd = tg.numpy(), td.numpy()
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=4_000_000, device=local_rank, cuda_stream=stream.cuda_stream)
+    ctx.pool_upload(np.zeros(0, SURFEL_DTYPE))
+    warm = 6
+    for t in range(warm):
+        ctx.fuse_frame_resident(t // 4, hg[t], hd[t], Pz[t])
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(warm, T):
+        ctx.fuse_frame_resident(t // 4, hg[t], hd[t], Pz[t])
+    e1.record()
+    ctx.sync()
+    ms = e0.elapsed_time(e1)
+    out["stream"] = {"workload": f"sequential synthetic 1226x370 stream (BASELINE configs[1]), GPU-resident pool, {T - warm} timed frames",
+                     "frames_per_s": (T - warm) / (ms * 1e-3), "ms_per_frame": ms / (T - warm), "final_pool_surfels": ctx.pool_size(),
+                     "h2d_bytes_per_frame": int(cam.width * cam.height * 5 + 140), "api": "dsm_fuse_frame_resident (C ABI, pinned host frames)"}
+    # loop-closure transform on a large pool
+    n = 4_000_000
+    rng = np.random.RandomState(7)
+    big = np.zeros(n, SURFEL_DTYPE)
+    for f in ("px", "py", "pz", "nx", "ny", "nz"):
+        big[f] = rng.standard_normal(n).astype(np.float32)
+    big["update_times"] = 1
+    ctx.pool_upload(big)
+    a = np.deg2rad(2.0)
+    Wm = np.eye(4)
+    Wm[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+    Wm[:3, 3] = [0.5, 0.0, 0.25]
+    w = np.ascontiguousarray(Wm.T.astype(np.float32).reshape(16))
+    for _ in range(3):
+        ctx.pool_transform(w)
+    ctx.sync()
+    e0.record()
+    for _ in range(10):
+        ctx.pool_transform(w)
+    e1.record()
+    ctx.sync()
+    ms = e0.elapsed_time(e1) / 10
+    out["pool_transform"] = {"surfels": n, "ms": ms, "algorithmic_GBps": 48 * n / (ms * 1e-3) / 1e9, "moved_GBps": 88 * n / (ms * 1e-3) / 1e9,
+                             "note": "48 B/surfel compulsory (p,n read+write); the 44-byte ABI records are moved whole (88 B/surfel)"}
+    ctx.close()
+    return out
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -421,6 +489,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                                   "frac": path_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
             "kernel_ms_per_step": kernel_ms, "kernel_ms_per_launch": per_launch_ms,
         }
+        if world == 1:
+            line["extras"] = run_extras(cam, local_rank, stream)
         if world == 1 and not args.no_cpu:
             pools_cpu = [pool_np[offsets[b]:offsets[b + 1]] for b in range(B)]
             arm = cpu_reference_fps(cam, cur, pools_cpu, [0] * B, budget_s=20.0, label="~10-30 s of CPU work")
