@@ -264,7 +264,7 @@ def run_extras(cam, local_rank, stream):
             pass
     tg, td = torch.from_numpy(G).pin_memory(), torch.from_numpy(D).pin_memory()
     hg, hd = tg.numpy(), td.numpy()
-    ctx = capi.Context(cam, max_batch=1, max_local_surfels=4_000_000, device=local_rank, cuda_stream=stream.cuda_stream)
+    ctx = capi.Context(cam, max_batch=2, max_local_surfels=4_000_000, device=local_rank, cuda_stream=stream.cuda_stream)
     ctx.pool_upload(np.zeros(0, SURFEL_DTYPE))
     warm = 6
     for t in range(warm):

@@ -43,6 +43,8 @@ struct dsm_ctx
     // resident pool (stream mode)
     int res_upper;      // host-side upper bound of the resident pool size (exact after a sync)
     bool res_active;
+    int res_frame;      // frames fused in resident mode so far (selects the frame slot)
+    int32_t *res_ofs;   // device [2]: {0, resident pool size}
     int *blkcnt, *blkofs, *newofs;
     float *wmat;        // device copy of the 4x4 of dsm_pool_transform
     cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
@@ -150,6 +152,7 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(ctx->blkofs);
     cudaFree(ctx->newofs);
     cudaFree(ctx->wmat);
+    cudaFree(ctx->res_ofs);
     cudaFree(ctx->depth_packed);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -203,6 +206,8 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->gray_packed = nullptr;
     ctx->res_upper = 0;
     ctx->res_active = false;
+    ctx->res_frame = 0;
+    ctx->res_ofs = nullptr;
     ctx->blkcnt = ctx->blkofs = ctx->newofs = nullptr;
     ctx->wmat = nullptr;
     ctx->depth_packed = nullptr;
@@ -266,6 +271,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(ctx->blkofs, npool / 256 + 2);
     ALLOC(ctx->newofs, 2);
     ALLOC(ctx->wmat, 16);
+    ALLOC(ctx->res_ofs, 2);
 #undef ALLOC
     d.nrm_plane = B * px;
     d.frame0 = 0;
@@ -704,16 +710,28 @@ extern "C" int dsm_fuse_frame(dsm_ctx *ctx, int ref_idx, const uint8_t *gray, si
 }
 
 // ---- GPU-resident pool (stream mode) ----
+// The resident pool is described by res_ofs = {0, n} on the device.  Frames alternate between two
+// frame slots (when max_batch >= 2) so that the H2D copy of frame t+1 overlaps the kernels of frame t.
+static DsmDev resident_view(dsm_ctx *ctx, int slot)
+{
+    DsmDev d = ctx->d;
+    d.frame0 = slot;
+    d.poolofs = ctx->res_ofs - slot; // kernels read poolofs[b], poolofs[b+1] with b == slot
+    return d;
+}
+
 extern "C" int dsm_pool_upload(dsm_ctx *ctx, const dsm_surfel_t *local, int n)
 {
     if (!ctx || n < 0 || (n > 0 && !local)) return DSM_E_INVALID;
     if (n > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
     CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->s_h2d));
     CK(cudaStreamSynchronize(ctx->stream));
     if (n > 0) CK(cudaMemcpyAsync(ctx->d.pool, local, (size_t)n * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h_ofs[0] = 0;
     ctx->h_ofs[1] = n;
-    CK(cudaMemcpyAsync(ctx->poolofs, ctx->h_ofs, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->res_ofs, ctx->h_ofs, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // `local` may be pageable / reused by the caller
     ctx->res_upper = n;
     ctx->res_active = true;
     ctx->n_pool = n;
@@ -726,7 +744,7 @@ extern "C" int dsm_pool_size(dsm_ctx *ctx, int *n)
     if (!ctx->res_active) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
     int32_t h[2] = {0, 0};
-    CK(cudaMemcpyAsync(h, ctx->poolofs, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h, ctx->res_ofs, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *n = h[1];
     ctx->res_upper = h[1];
@@ -753,9 +771,7 @@ extern "C" int dsm_pool_transform(dsm_ctx *ctx, const float Wm[16])
     if (!ctx->res_active) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->wmat, Wm, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    DsmDev d = ctx->d;
-    d.frame0 = 0;
-    dsm_launch_pool_transform(d, 0, ctx->res_upper, ctx->wmat, ctx->stream);
+    dsm_launch_pool_transform(resident_view(ctx, 0), 0, ctx->res_upper, ctx->wmat, ctx->stream);
     CK(cudaGetLastError());
     return DSM_OK;
 }
@@ -775,37 +791,68 @@ extern "C" int dsm_fuse_frame_resident(dsm_ctx *ctx, int ref_idx, const uint8_t 
         if (rc != DSM_OK) return rc;
         if (n + ctx->S > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
     }
-    // the small pinned tables are reused per call
-    CK(cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->h_pose, pose, 16 * sizeof(float));
-    inverse4f(pose, ctx->h_pose + 16);
-    ctx->h_ref[0] = ref_idx;
-    CK(cudaMemcpyAsync(ctx->pose, ctx->h_pose, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->ipose, ctx->h_pose + 16, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->refidx, ctx->h_ref, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(ctx->gray, ctx->Wp, gray, gray_pitch, W, H, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(ctx->depth, (size_t)ctx->Wp * 4, depth, depth_pitch, (size_t)W * 4, H, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->nb = 1;
+    const int nslots = ctx->p.max_batch >= 2 ? 2 : 1;
+    const int slot = ctx->res_frame % nslots;
+    ctx->res_frame++;
+    const size_t fpx = (size_t)H * W;
+    // this slot's pinned tables / image buffers were last used two frames ago: make sure that copy and
+    // those kernels are done (normally long finished, so these do not stall)
+    CK(cudaEventSynchronize(ctx->ev_h2d[slot]));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[slot], 0));
+    memcpy(ctx->h_pose + (size_t)slot * 32, pose, 16 * sizeof(float));
+    inverse4f(pose, ctx->h_pose + (size_t)slot * 32 + 16);
+    ctx->h_ref[slot] = ref_idx;
+    CK(cudaMemcpyAsync(ctx->pose + slot * 16, ctx->h_pose + (size_t)slot * 32, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(ctx->ipose + slot * 16, ctx->h_pose + (size_t)slot * 32 + 16, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(ctx->refidx + slot, ctx->h_ref + slot, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+    const bool packed = gray_pitch == (size_t)W && depth_pitch == (size_t)W * 4;
+    if (packed)
+    { // one contiguous copy per image, repacked to the pitched layout on the device
+        CK(cudaMemcpyAsync(ctx->gray_packed + (size_t)slot * fpx, gray, fpx, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpyAsync(ctx->depth_packed + (size_t)slot * fpx, depth, fpx * sizeof(float), cudaMemcpyHostToDevice, ctx->s_h2d));
+    }
+    else
+    {
+        CK(cudaMemcpy2DAsync(ctx->gray + (size_t)slot * ctx->px, ctx->Wp, gray, gray_pitch, W, H, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpy2DAsync(ctx->depth + (size_t)slot * ctx->px, (size_t)ctx->Wp * 4, depth, depth_pitch, (size_t)W * 4, H, cudaMemcpyHostToDevice, ctx->s_h2d));
+    }
+    CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->s_h2d));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+    const DsmDev dv = resident_view(ctx, slot);
+    if (packed)
+    {
+        ProfScope p(ctx, DSM_K_REPACK);
+        dsm_launch_repack(dv, 1, ctx->gray_packed + (size_t)slot * fpx, ctx->depth_packed + (size_t)slot * fpx, ctx->stream);
+    }
+    ctx->nb = slot + 1;
     ctx->uploaded = true;
-    int rc = enqueue_schedule(ctx, 0, 1, ctx->res_upper, ctx->stream);
-    if (rc != DSM_OK) return rc;
+    {
+        // enqueue_schedule takes its view from ctx->d: temporarily present the resident pool table
+        const int32_t *saved = ctx->d.poolofs;
+        ctx->d.poolofs = dv.poolofs;
+        int rc = enqueue_schedule(ctx, slot, 1, ctx->res_upper, ctx->stream);
+        ctx->d.poolofs = saved;
+        if (rc != DSM_OK) return rc;
+    }
     ctx->ran = true;
     // post-step of SurfelMap::fuse_map on the device: compact into the alternate buffer, then swap
+    dsm_launch_pool_compact(dv, slot, ctx->res_upper, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
+    CK(cudaMemcpyAsync(ctx->res_ofs + 1, ctx->newofs + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
     {
-        DsmDev d = ctx->d;
-        d.frame0 = 0;
-        dsm_launch_pool_compact(d, 0, ctx->res_upper, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
-        CK(cudaMemcpyAsync(ctx->poolofs + 1, ctx->newofs + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
         dsm_surfel_t *t = ctx->d.pool;
         ctx->d.pool = ctx->pool_snap;
         ctx->pool_snap = t;
     }
     ctx->res_upper += ctx->S; // every seed can add at most one surfel; dsm_pool_size() tightens it
     CK(cudaGetLastError());
+    // the caller may reuse its image buffers as soon as we return: wait for THIS frame's copy only
+    // (the kernels keep running and overlap the next call's copy)
+    CK(cudaEventSynchronize(ctx->ev_h2d[slot]));
     if (n_new)
     {
         int32_t c = 0;
-        CK(cudaMemcpyAsync(&c, ctx->d.nnew, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&c, ctx->d.nnew + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         *n_new = c;
     }

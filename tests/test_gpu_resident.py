@@ -41,7 +41,7 @@ def test_resident_stream_matches_reference_flow():
     """Per frame: hot path on the resident pool + device compaction/append == oracle fuse + fuse_map post-step."""
     from densesurfelmapping_b200 import capi
     cam = synth.VGA
-    ctx = capi.Context(cam, max_batch=1, max_local_surfels=100000)
+    ctx = capi.Context(cam, max_batch=2, max_local_surfels=100000)
     orc = oracle_for(cam)
     pool = np.zeros(0, SURFEL_DTYPE)
     ctx.pool_upload(pool)
@@ -65,7 +65,7 @@ def test_resident_stream_free_running():
     """No re-sync: 6 frames carried entirely on the device stay within tolerance of the oracle flow."""
     from densesurfelmapping_b200 import capi
     cam = synth.VGA
-    ctx = capi.Context(cam, max_batch=1, max_local_surfels=100000)
+    ctx = capi.Context(cam, max_batch=2, max_local_surfels=100000)
     orc = oracle_for(cam)
     pool = np.zeros(0, SURFEL_DTYPE)
     ctx.pool_upload(pool)
