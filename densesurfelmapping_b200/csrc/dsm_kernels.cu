@@ -570,44 +570,69 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
         const size_t st = (size_t)d.Sp;
         // The adds are a serial dependence chain (that IS the reference's rounding order), but the
         // loads are independent: fetch 8 list entries at a time so 8 requests are in flight per lane.
+        // The list stays in registers for the first 32 entries (most seeds' whole first pass).
         float sum_d = 0.0f;
         {
+            const float *pp = dl;
             int k = 0;
-            for (; k + 8 <= nd; k += 8)
+            for (; k + 8 <= nd; k += 8, pp += 8 * st)
             {
                 float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = dl[(k + j) * st];
+                for (int j = 0; j < 8; j++) v[j] = pp[j * st];
 #pragma unroll
                 for (int j = 0; j < 8; j++) sum_d += v[j]; // raster order (:511)
             }
-            for (; k < nd; k++) sum_d += dl[k * st];
+            for (; k < nd; k++, pp += st) sum_d += *pp;
         }
         md = sum_d / (float)nd;
         for (int it = 0; it < 5; it++)
         { // damped Huber-Newton (:534-554)
             float sa = 0.0f, sb = 0.0f;
-            auto term = [&](float v)
+            const float *pp = dl;
+            int k = 0;
+            for (; k + 8 <= nd; k += 8, pp += 8 * st)
             {
-                const float r = md - v;
-                if (r < F_0p4_HI && r > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
+                float r[8];
+                bool allin = true;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    r[j] = md - pp[j * st];
+                    allin &= r[j] < F_0p4_HI && r[j] > -F_0p4_HI; // (double)r < 0.4 && (double)r > -0.4
+                }
+                if (allin)
+                { // common case: every residual inside the Huber range -> pure float chain
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sa += 2 * r[j];
+                    sb += 16; // eight exact +2 steps
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                    {
+                        if (r[j] < F_0p4_HI && r[j] > -F_0p4_HI)
+                        {
+                            sa += 2 * r[j];
+                            sb += 2;
+                        }
+                        else
+                            sa = (float)((double)sa + (r[j] > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
+                    }
+                }
+            }
+            for (; k < nd; k++, pp += st)
+            {
+                const float r = md - *pp;
+                if (r < F_0p4_HI && r > -F_0p4_HI)
                 {
                     sa += 2 * r;
                     sb += 2;
                 }
                 else
                     sa = (float)((double)sa + (r > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
-            };
-            int k = 0;
-            for (; k + 8 <= nd; k += 8)
-            {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = dl[(k + j) * st];
-#pragma unroll
-                for (int j = 0; j < 8; j++) term(v[j]);
             }
-            for (; k < nd; k++) term(dl[k * st]);
             const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
             md = md + delta;
             if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
