@@ -315,6 +315,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     from densesurfelmapping_b200.elements import SURFEL_DTYPE
 
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a few hundred ms to come up: start it long before the timed region
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cam = synth.KITTI
@@ -386,9 +389,6 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up; per-kernel breakdown measured during the warm-up steps
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ctx.profile_enable(0xDFF)
     ctx.profile_reset()
     for _ in range(max(args.warmup, 3)):
