@@ -375,13 +375,31 @@ def run_gpu_arm(args, rank, world, local_rank):
     if world > 1 and rank == 0:
         gather_new = [torch.empty_like(d_new) for _ in range(world)]
         gather_pool = [torch.empty_like(d_pool) for _ in range(world)]
+    if world > 1:
+        # the gather of step k runs on a side stream from a staged copy of the deltas, so it overlaps the
+        # kernels of step k+1 (which overwrite the library's buffers); the timed region waits for the last one
+        gstream = torch.cuda.Stream(device=local_rank)
+        st_new, st_pool = torch.empty_like(d_new), torch.empty_like(d_pool)
+        ev_staged, ev_gathered = torch.cuda.Event(), torch.cuda.Event()
+        ev_gathered.record(stream)
 
     def step():
         ctx.batch_restore_pool()
         ctx.batch_run()
         if world > 1:  # the single NCCL gather of the per-GPU surfel deltas (new + updated pool) onto rank 0
-            dist.gather(d_new, gather_new, dst=0)
-            dist.gather(d_pool, gather_pool, dst=0)
+            stream.wait_event(ev_gathered)      # previous gather has consumed the staging buffers
+            st_new.copy_(d_new, non_blocking=True)
+            st_pool.copy_(d_pool, non_blocking=True)
+            ev_staged.record(stream)
+            with torch.cuda.stream(gstream):
+                gstream.wait_event(ev_staged)
+                dist.gather(st_new, gather_new, dst=0)
+                dist.gather(st_pool, gather_pool, dst=0)
+                ev_gathered.record(gstream)
+
+    def drain():
+        if world > 1:
+            stream.wait_event(ev_gathered)
 
     def barrier_sync():
         if world > 1:
@@ -393,6 +411,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     ctx.profile_reset()
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     ms, nl = ctx.profile_read()
     names = capi.kernel_names()
     kernel_ms = {names[i]: float(ms[i]) / max(args.warmup, 3) for i in range(len(names)) if nl[i]}  # ms per step
@@ -411,6 +430,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()
     e1.record()
     barrier_sync()
     wall1 = time.time()

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -618,7 +619,12 @@ extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uin
     if (rc != DSM_OK) return rc;
     const int W = ctx->p.width, H = ctx->p.height, S = ctx->S;
     const size_t fpx = (size_t)H * W;
-    const int nchunks = n >= 16 ? 4 : (n >= 4 ? 2 : 1);
+    int nchunks = n >= 16 ? 4 : (n >= 4 ? 2 : 1);
+    if (const char *e = getenv("DSM_E2E_CHUNKS"))
+    { // tuning knob for experiments (1..8)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 8 && v <= n) nchunks = v;
+    }
     const int per = (n + nchunks - 1) / nchunks;
     // copies must not start before earlier work on the compute stream (previous users of the buffers) is done
     CK(cudaEventRecord(ctx->ev_start, ctx->stream));

@@ -199,10 +199,12 @@ struct SeedC
     double inv;
 };
 
-__device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pix_inv, int x, int y,
+// Branch-free: both costs and the has-depth predicate are always computed; the caller selects.
+// (When mean_depth <= 0 the hoisted 1/mean_depth is inf/NaN; the result is discarded by the select.)
+__device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pix_inv, double pix_inv_d, float fx, float fy,
                                           float &nodepth, float &withdepth)
 {
-    const float ax = sd.x - (float)x, ay = sd.y - (float)y;
+    const float ax = sd.x - fx, ay = sd.y - fy;
     const float dist = ax * ax + ay * ay;
     float n = dist * 0.0625f; // / (SP_SIZE/2)^2, exact power of two (:374)
     const float idf = sd.I - pix_i;
@@ -212,16 +214,14 @@ __device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pi
     const double a = (double)(idf * idf);
     const double q0 = a * 0.01;
     const double q = __fma_rn(__fma_rn(-q0, 100.0, a), 0.01, q0);
-    n = (float)((double)n + q);
+    const double nd = (double)n + q;
+    n = (float)nd;
     nodepth = n;
-    withdepth = n;
-    if (sd.md > 0 && pix_inv > 0)
-    {
-        const float idd = (float)(sd.inv - (double)pix_inv);        // (:380)
-        withdepth = (float)((double)n + (double)(idd * idd) * 400.0); // (:381)
-        return true;
-    }
-    return false;
+    const bool has = sd.md > 0 && pix_inv > 0; // (:378)
+    const float idd = (float)(sd.inv - pix_inv_d);                  // (:380)
+    const float wd = (float)((double)n + (double)(idd * idd) * 400.0); // (:381)
+    withdepth = has ? wd : n;
+    return has;
 }
 
 template <bool FIRST>
@@ -264,48 +264,43 @@ __global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDe
             const int cx = (c >> 1) ? xb : xa, cy = (c & 1) ? yb : ya;
             sv[c] = ((c >> 1) ? vxb : vxa) && ((c & 1) ? vyb : vya);
             sidx[c] = cy * d.spw + cx;
-            if (sv[c])
-            {
-                const float4 s4 = d.seed[so + sidx[c]];
-                sc[c].x = s4.x, sc[c].y = s4.y, sc[c].I = s4.z, sc[c].md = s4.w;
-                sc[c].inv = d.inv_md[so + sidx[c]];
-            }
+            const int li = sv[c] ? sidx[c] : 0; // invalid candidates read seed 0 and are masked out below
+            const float4 s4 = d.seed[so + li];
+            sc[c].x = s4.x, sc[c].y = s4.y, sc[c].I = s4.z, sc[c].md = s4.w;
+            sc[c].inv = d.inv_md[so + li];
         }
+        const float fy = (float)y;
 #pragma unroll
         for (int i = 0; i < 4; i++)
         {
             const int x = x4 + i;
-            if (x >= d.W) continue;
             const float my_i = gi[i];
             // (:404-405) my_inv = (float)(1.0 / (double)depth) for depth > 0.01.  53 >= 2*24+2 bits, so the
             // double rounding is innocuous and the IEEE float reciprocal gives the same value.
             float my_inv = 0.0f;
             if (zi[i] > F_0p01_LO) my_inv = (zi[i] < 1e30f) ? __fdiv_rn(1.0f, zi[i]) : (float)(1.0 / (double)zi[i]);
+            const double my_inv_d = (double)my_inv;
+            const float fx = (float)x;
             float min_d = 1e6f, min_nd = 1e6f;
             int idx_d = -1, idx_nd = -1;
             bool all_has_depth = true;
 #pragma unroll
             for (int c = 0; c < 4; c++)
-            {
-                // x%8 == 4 sees only its own column (rx0==4, i==0 -> only xa)
-                const bool xvalid = (c >> 1) ? !(rx0 == 4 && i == 0) : true;
-                if (sv[c] && xvalid)
-                {
-                    float cnd, cd;
-                    all_has_depth &= calc_cost(sc[c], my_i, my_inv, x, y, cnd, cd);
-                    if (cd < min_d)
-                    {
-                        min_d = cd;
-                        idx_d = sidx[c];
-                    }
-                    if (cnd < min_nd)
-                    {
-                        min_nd = cnd;
-                        idx_nd = sidx[c];
-                    }
-                }
+            { // branch-free: an invalid candidate gets cost +inf (never < the running minimum) and does not
+              // touch all_has_depth; x%8 == 4 sees only its own column (rx0==4, i==0 -> only xa)
+                const bool valid = sv[c] && ((c >> 1) ? !(rx0 == 4 && i == 0) : true);
+                float cnd, cd;
+                const bool has = calc_cost(sc[c], my_i, my_inv, my_inv_d, fx, fy, cnd, cd);
+                cd = valid ? cd : __int_as_float(0x7f800000);
+                cnd = valid ? cnd : __int_as_float(0x7f800000);
+                all_has_depth &= has || !valid;
+                const bool bd = cd < min_d, bn = cnd < min_nd;
+                min_d = bd ? cd : min_d;
+                idx_d = bd ? sidx[c] : idx_d;
+                min_nd = bn ? cnd : min_nd;
+                idx_nd = bn ? sidx[c] : idx_nd;
             }
-            win[i] = all_has_depth ? idx_d : idx_nd;
+            win[i] = (x < d.W) ? (all_has_depth ? idx_d : idx_nd) : -1;
         }
     }
 
