@@ -639,157 +639,6 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
 }
 
 // -------------------------------------------------------------------------------------------
-// K2 (fused)  k_update_seeds — update_seeds_kernel (:468-562) in ONE kernel, thread per seed.
-//
-// A block owns US_NR seed rows x 32 seed columns.  It first copies the pixel region those seeds can
-// own (264 x (8*US_NR+8) pixels: labels, depth, gray) into shared memory, cell-interleaved as
-// [y][x%8][x/8]: for a fixed window offset (r, c) the 32 lanes of a warp (32 neighbouring seeds of one
-// seed row) then read 32 CONSECUTIVE words -- conflict-free.  Each thread scans its seed's 16x16
-// window serially in raster order, which is exactly the reference's loop nest (:497-515): integer sums
-// and the ordered float sum_depth (:511) fall out directly, with no warp reductions, no compaction and
-// no intermediate lists; the member pixels with depth are remembered as a 256-bit mask so the
-// Huber-Newton passes (:534-554) revisit only those (still in raster order).
-// Compared with the warp-per-seed gather + per-seed newton pair this executes ~4x fewer instructions
-// (every lane does useful serial work instead of 8 predicated pixels + reductions per lane).
-// -------------------------------------------------------------------------------------------
-#define US_NR 4
-#define US_RH (8 * US_NR + 8)
-#define US_AST 33
-#define US_N (US_RH * 8 * US_AST)
-#define US_SMEM (US_N * 9)
-
-__global__ void __launch_bounds__(32 * US_NR) k_update_seeds(const __grid_constant__ DsmDev d)
-{
-    extern __shared__ __align__(16) uint8_t us_smem[];
-    int32_t *lab = reinterpret_cast<int32_t *>(us_smem);
-    float *dep = reinterpret_cast<float *>(us_smem + (size_t)US_N * 4);
-    uint8_t *gry = us_smem + (size_t)US_N * 8;
-    const int b = d.frame0 + blockIdx.z;
-    const int sx0 = blockIdx.x * 32, sy0 = blockIdx.y * US_NR;
-    const int X0 = 8 * sx0 - 4, Y0 = 8 * sy0 - 4;
-    const int W = d.W, H = d.H, Wp = d.Wp;
-    const size_t fo = (size_t)b * d.px_stride, so = (size_t)b * d.S;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) d.nlist[b] = 0; // the deferred-pixel list of this pass is consumed
-    // ---- phase 1: region -> shared memory (pixels outside the counted window range get label -1:
-    //      the reference's windows exclude the last image row and column, :488-489)
-    {
-        const int32_t *glab = d.labels + fo;
-        const float *gdep = d.depth + fo;
-        const uint8_t *ggry = d.gray + fo;
-        for (int g = threadIdx.x; g < 66 * US_RH; g += 32 * US_NR)
-        {
-            const int yp = g / 66, xp = (g - yp * 66) * 4;
-            const int X = X0 + xp, Y = Y0 + yp;
-            int4 l = make_int4(-1, -1, -1, -1);
-            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            uchar4 q = make_uchar4(0, 0, 0, 0);
-            if (Y >= 0 && Y < H - 1 && X >= 0 && X < Wp)
-            {
-                const unsigned po = (unsigned)(Y * Wp + X);
-                l = *reinterpret_cast<const int4 *>(glab + po);
-                z = *reinterpret_cast<const float4 *>(gdep + po);
-                q = *reinterpret_cast<const uchar4 *>(ggry + po);
-                if (X >= W - 1) l.x = -1;
-                if (X + 1 >= W - 1) l.y = -1;
-                if (X + 2 >= W - 1) l.z = -1;
-                if (X + 3 >= W - 1) l.w = -1;
-            }
-            const int base = (yp * 8 + (xp & 7)) * US_AST + (xp >> 3);
-            lab[base] = l.x, lab[base + US_AST] = l.y, lab[base + 2 * US_AST] = l.z, lab[base + 3 * US_AST] = l.w;
-            dep[base] = z.x, dep[base + US_AST] = z.y, dep[base + 2 * US_AST] = z.z, dep[base + 3 * US_AST] = z.w;
-            gry[base] = q.x, gry[base + US_AST] = q.y, gry[base + 2 * US_AST] = q.z, gry[base + 3 * US_AST] = q.w;
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: thread per seed
-    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sp_x = sx0 + lane, sp_y = sy0 + wq;
-    if (sp_x >= d.spw || sp_y >= d.sph) return;
-    const int s = sp_y * d.spw + sp_x;
-    if (d.tstable[so + s] == DSM_STABLE) return; // stable seeds are skipped (:478-479)
-    unsigned mask[8]; // bit (16*(r&1) + c) of word r>>1: member pixel with depth > 0.1
-    int cnt = 0, sumx = 0, sumy = 0, sumi = 0, nd = 0;
-    float sum_d = 0.0f;
-    const int xw = X0 + 8 * lane; // image x of window column 0
-#pragma unroll
-    for (int r = 0; r < 16; r++)
-    {
-        if ((r & 1) == 0) mask[r >> 1] = 0;
-        const int rowbase = ((8 * wq + r) * 8) * US_AST + lane;
-        int rc = 0;
-#pragma unroll
-        for (int c = 0; c < 16; c++)
-        {
-            const int idx = rowbase + (c & 7) * US_AST + (c >> 3);
-            if (lab[idx] == s)
-            {
-                rc++;
-                sumx += xw + c;
-                sumi += gry[idx];
-                const float dv = dep[idx];
-                if (dv > F_0p1_LO) // (double)depth > 0.1 (:508)
-                {
-                    sum_d += dv; // raster order (:511)
-                    nd++;
-                    mask[r >> 1] |= 1u << (16 * (r & 1) + c);
-                }
-            }
-        }
-        cnt += rc;
-        sumy += rc * (Y0 + 8 * wq + r);
-    }
-    if (cnt == 0)
-    { // unreachable for supported shapes (the centre pixel always belongs to its seed); recorded, never ignored
-        atomicAdd(&d.errflag[b], 1);
-        d.tstable[so + s] = -1;
-        return;
-    }
-    const float fn = (float)cnt; // sums are < 2^24 so the reference's float accumulation is exact
-    const float mi = (float)sumi / fn;
-    const float mx = (float)sumx / fn;
-    const float my = (float)sumy / fn;
-    const float4 pre = d.seed[so + s];
-    // ::fabs(double): float differences, summed in double, rounded once (:527)
-    const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
-    const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
-    float md = 0.0f;
-    if (nd > 0)
-    {
-        md = sum_d / (float)nd;
-        const int wbase = (8 * wq * 8) * US_AST + lane;
-        for (int it = 0; it < 5; it++)
-        { // damped Huber-Newton (:534-554) over the member pixels, raster order
-            float sa = 0.0f, sb = 0.0f;
-#pragma unroll
-            for (int wi = 0; wi < 8; wi++)
-            {
-                unsigned m = mask[wi];
-                while (m)
-                {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int r = 2 * wi + (j >> 4), c = j & 15;
-                    const float rres = md - dep[wbase + (r * 8 + (c & 7)) * US_AST + (c >> 3)];
-                    if (rres < F_0p4_HI && rres > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
-                    {
-                        sa += 2 * rres;
-                        sb += 2;
-                    }
-                    else
-                        sa = (float)((double)sa + (rres > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
-                }
-            }
-            const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
-            md = md + delta;
-            if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
-        }
-    }
-    d.seed[so + s] = make_float4(mx, my, mi, md);
-    d.inv_md[so + s] = 1.0 / (double)md;
-    d.tstable[so + s] = newstable ? DSM_STABLE : -1;
-}
-
-// -------------------------------------------------------------------------------------------
 // K3  backproject_normals — calculate_spaces_kernel (:644-662) + calculate_pixels_norms_kernel
 // (:664-712), fused: the reference's 24 B/px fp64 space_map is never materialised.
 //
@@ -1536,17 +1385,6 @@ void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s)
 {
     dim3 grid((d.spw + 7) / 8, d.sph, nb);
     k_gather_depths<<<grid, 256, 0, s>>>(d);
-}
-void dsm_launch_update_seeds(const DsmDev &d, int nb, cudaStream_t s)
-{
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaFuncSetAttribute(k_update_seeds, cudaFuncAttributeMaxDynamicSharedMemorySize, US_SMEM);
-        configured = true;
-    }
-    dim3 grid((d.spw + 31) / 32, (d.sph + US_NR - 1) / US_NR, nb);
-    k_update_seeds<<<grid, 32 * US_NR, US_SMEM, s>>>(d);
 }
 void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s)
 {
