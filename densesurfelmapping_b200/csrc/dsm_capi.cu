@@ -29,7 +29,6 @@ struct dsm_ctx
     int n_pool;   // local surfels in the current batch
     bool uploaded, ran;
     int stop_after; // debug: number of kernels to enqueue (<= 0: all)
-    bool fused_update; // K2 as one thread-per-seed kernel (default) or the gather + newton pair
     // raw allocations (non-const views of what DsmDev holds)
     uint8_t *gray;
     float *depth;
@@ -201,10 +200,6 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->n_pool = 0;
     ctx->uploaded = ctx->ran = false;
     ctx->stop_after = 0;
-    {
-        const char *e = getenv("DSM_FUSED_UPDATE");
-        ctx->fused_update = !(e && e[0] == '0');
-    }
     ctx->s_h2d = ctx->s_d2h = nullptr;
     for (int i = 0; i < 4; i++) ctx->s_comp[i] = nullptr;
     ctx->ev_start = nullptr;
@@ -536,16 +531,8 @@ static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame
             STEP(DSM_K_ASSIGN, dsm_launch_assign(d, nb, false, st));
             STEP(DSM_K_RELAX, dsm_launch_relax(d, nb, st));
         }
-        if (ctx->fused_update)
-        { // one fused kernel; the debug kernel budget still counts two so the staged tests line up
-            STEP(DSM_K_GATHER_DEPTHS, dsm_launch_update_seeds(d, nb, st));
-            budget--;
-        }
-        else
-        {
-            STEP(DSM_K_GATHER_DEPTHS, dsm_launch_gather_depths(d, nb, st));
-            STEP(DSM_K_NEWTON, dsm_launch_newton(d, nb, st));
-        }
+        STEP(DSM_K_GATHER_DEPTHS, dsm_launch_gather_depths(d, nb, st));
+        STEP(DSM_K_NEWTON, dsm_launch_newton(d, nb, st));
     }
     STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
     STEP(DSM_K_GATHER_POINTS, dsm_launch_gather_points(d, nb, st));

@@ -95,7 +95,6 @@ void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s);
 void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_update_seeds(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_gather_points(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s);

@@ -639,141 +639,6 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
 }
 
 // -------------------------------------------------------------------------------------------
-// K2 (single kernel)  k_update_seeds — update_seeds_kernel (:468-562), thread per seed, straight from
-// global memory.  Lane = seed column (32 neighbouring seeds of one seed row per warp), so for every
-// window row the warp reads one contiguous 1 KB stretch of the label / depth / gray rows (adjacent
-// lanes' 16-pixel windows overlap by half: L1 serves the reuse).  Each thread walks its 16x16 window
-// in raster order -- the reference's own loop nest (:497-515) -- so the integer sums and the ordered
-// float sum_depth (:511) need no warp reductions, no compaction and no intermediate lists; member
-// pixels with depth are remembered as a 256-bit mask and the Huber-Newton passes (:534-554) revisit
-// only those, in the same order.  No shared memory => full occupancy hides the serial chains.
-// -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_update_seeds(const __grid_constant__ DsmDev d)
-{
-    const int b = d.frame0 + blockIdx.z;
-    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int sp_x = blockIdx.x * 32 + lane, sp_y = blockIdx.y * 4 + wq;
-    const size_t so = (size_t)b * d.S;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) d.nlist[b] = 0; // the deferred-pixel list of this pass is consumed
-    if (sp_x >= d.spw || sp_y >= d.sph) return;
-    const int s = sp_y * d.spw + sp_x;
-    if (d.tstable[so + s] == DSM_STABLE) return; // stable seeds are skipped (:478-479)
-    const int W = d.W, H = d.H, Wp = d.Wp;
-    const size_t fo = (size_t)b * d.px_stride;
-    const int32_t *lab = d.labels + fo;
-    const float *dep = d.depth + fo;
-    const uint8_t *gry = d.gray + fo;
-    const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
-    const int xb = x0 > 0 ? x0 : 0, yb = y0 > 0 ? y0 : 0;
-    const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
-    const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
-    unsigned colmask = 0; // bit c: window column c lies in [xb, xe)
-#pragma unroll
-    for (int c = 0; c < 16; c++)
-        if (x0 + c >= xb && x0 + c < xe) colmask |= 1u << c;
-    unsigned mask[8]; // bit (16*(r&1)+c) of word r>>1: member pixel with depth > 0.1
-    int cnt = 0, sumx = 0, sumy = 0, sumi = 0, nd = 0;
-    float sum_d = 0.0f;
-#pragma unroll
-    for (int r = 0; r < 16; r++)
-    {
-        if ((r & 1) == 0) mask[r >> 1] = 0;
-        const int y = y0 + r;
-        if (y < yb || y >= ye) continue;
-        const unsigned ro = (unsigned)(y * Wp); // row offset; x0 may be -4 at the left border (masked by colmask)
-        unsigned m16 = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-        {
-            if (!((colmask >> (4 * q)) & 0xfu)) continue;
-            const int xq = x0 + 4 * q;
-            const int4 l4 = *reinterpret_cast<const int4 *>(lab + ro + (xq < 0 ? 0 : xq));
-            m16 |= ((l4.x == s ? 1u : 0u) | (l4.y == s ? 2u : 0u) | (l4.z == s ? 4u : 0u) | (l4.w == s ? 8u : 0u)) << (4 * q);
-        }
-        m16 &= colmask;
-        if (m16 == 0) continue;
-        const int rc = __popc(m16);
-        cnt += rc;
-        sumy += rc * y;
-        unsigned dm = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-        {
-            const unsigned mq = (m16 >> (4 * q)) & 0xfu;
-            if (!mq) continue;
-            const int xq = x0 + 4 * q;
-            const float4 z4 = *reinterpret_cast<const float4 *>(dep + ro + xq);
-            const uchar4 g4 = *reinterpret_cast<const uchar4 *>(gry + ro + xq);
-            const float zk[4] = {z4.x, z4.y, z4.z, z4.w};
-            const int gk[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if ((mq >> k) & 1u)
-                {
-                    sumx += xq + k;
-                    sumi += gk[k];
-                    if (zk[k] > F_0p1_LO) // (double)depth > 0.1 (:508)
-                    {
-                        sum_d += zk[k]; // raster order (:511)
-                        nd++;
-                        dm |= 1u << (4 * q + k);
-                    }
-                }
-        }
-        mask[r >> 1] |= dm << (16 * (r & 1));
-    }
-    if (cnt == 0)
-    { // unreachable for supported shapes (the centre pixel always belongs to its seed); recorded, never ignored
-        atomicAdd(&d.errflag[b], 1);
-        d.tstable[so + s] = -1;
-        return;
-    }
-    const float fn = (float)cnt; // sums are < 2^24 so the reference's float accumulation is exact
-    const float mi = (float)sumi / fn;
-    const float mx = (float)sumx / fn;
-    const float my = (float)sumy / fn;
-    const float4 pre = d.seed[so + s];
-    // ::fabs(double): float differences, summed in double, rounded once (:527)
-    const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
-    const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
-    float md = 0.0f;
-    if (nd > 0)
-    {
-        md = sum_d / (float)nd;
-        const float *wp = dep + (y0 * Wp + x0); // window origin (may point before the row start at the borders; only member pixels are read)
-        for (int it = 0; it < 5; it++)
-        { // damped Huber-Newton (:534-554) over the member pixels, raster order
-            float sa = 0.0f, sb = 0.0f;
-#pragma unroll
-            for (int wi = 0; wi < 8; wi++)
-            {
-                unsigned m = mask[wi];
-                const float *rp = wp + (2 * wi) * Wp;
-                while (m)
-                {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float rres = md - rp[(j >> 4) * Wp + (j & 15)];
-                    if (rres < F_0p4_HI && rres > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
-                    {
-                        sa += 2 * rres;
-                        sb += 2;
-                    }
-                    else
-                        sa = (float)((double)sa + (rres > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
-                }
-            }
-            const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
-            md = md + delta;
-            if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
-        }
-    }
-    d.seed[so + s] = make_float4(mx, my, mi, md);
-    d.inv_md[so + s] = 1.0 / (double)md;
-    d.tstable[so + s] = newstable ? DSM_STABLE : -1;
-}
-
-// -------------------------------------------------------------------------------------------
 // K3  backproject_normals — calculate_spaces_kernel (:644-662) + calculate_pixels_norms_kernel
 // (:664-712), fused: the reference's 24 B/px fp64 space_map is never materialised.
 //
@@ -1520,11 +1385,6 @@ void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s)
 {
     dim3 grid((d.spw + 7) / 8, d.sph, nb);
     k_gather_depths<<<grid, 256, 0, s>>>(d);
-}
-void dsm_launch_update_seeds(const DsmDev &d, int nb, cudaStream_t s)
-{
-    dim3 grid((d.spw + 31) / 32, (d.sph + 3) / 4, nb);
-    k_update_seeds<<<grid, 128, 0, s>>>(d);
 }
 void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s)
 {
