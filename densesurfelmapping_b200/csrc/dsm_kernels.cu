@@ -881,34 +881,7 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
     }
 }
 
-// Rare path of k_gauss_newton: some residual is outside the Huber range, so the normal equations need the
-// corrections H_R = H_all - sum_out 2 q q^T and J += sum_out +-0.4 q (:157-170).  Kept out of line so its
-// 14 fp64 accumulators do not cost registers in the common all-in-range loops.
-__device__ __noinline__ void gn_outliers(const float *qx, const float *qy, const float *qz, size_t st, int n,
-                                         float nx, float ny, float nz, float nb, double *ho, double *jo)
-{
-    for (int k = 0; k < n; k++)
-    {
-        const float ax = qx[k * st], ay = qy[k * st], az = qz[k * st];
-        const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
-        if (r < F_0p4_HI && r > -F_0p4_HI) continue;      // (:134) in range: nothing to correct (NaN falls through)
-        ho[0] += (double)(2 * ax * ax), ho[1] += (double)(2 * ax * ay), ho[2] += (double)(2 * ax * az), ho[3] += (double)(2 * ax);
-        ho[4] += (double)(2 * ay * ay), ho[5] += (double)(2 * ay * az), ho[6] += (double)(2 * ay);
-        ho[7] += (double)(2 * az * az), ho[8] += (double)(2 * az), ho[9] += 2;
-        if (r >= F_0p4_HI)
-        { // (double)r >= 0.4 (:157-163)
-            jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
-            jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
-        }
-        else if (r <= -F_0p4_HI)
-        { // (double)r <= -0.4 (:164-170)
-            jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
-            jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128, 6) k_gauss_newton(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ DsmDev d)
 {
     const int b = d.frame0 + blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -940,61 +913,58 @@ __global__ void __launch_bounds__(128, 6) k_gauss_newton(const __grid_constant__
         bool need_pass = true;
         for (int gn = 0; gn < 5; gn++)
         {
-            double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // same as hall, over the points outside the Huber range
+            double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // same, over the points outside the Huber range
             double jo[4] = {0, 0, 0, 0};
             if (need_pass)
             {
                 float rm = 0.f;
-                bool rnan = false, anyout = false;
-                if (gn == 0)
-                { // first pass: H over all points, residual range, point radius
-                    auto point = [&](float ax, float ay, float az)
+                bool rnan = false;
+                auto point = [&](float ax, float ay, float az)
+                {
+                    const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
+                    const bool inr = r < F_0p4_HI && r > -F_0p4_HI;  // (:134)
+                    rm = fmaxf(rm, fabsf(r));
+                    rnan |= !(r == r);
+                    if (gn == 0 || !inr)
                     {
-                        const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
-                        rm = fmaxf(rm, fabsf(r));
-                        rnan |= !(r == r);
-                        anyout |= !(r < F_0p4_HI && r > -F_0p4_HI); // (:134)
-                        hall[0] += (double)(2 * ax * ax), hall[1] += (double)(2 * ax * ay), hall[2] += (double)(2 * ax * az);
-                        hall[3] += (double)(2 * ax), hall[4] += (double)(2 * ay * ay), hall[5] += (double)(2 * ay * az);
-                        hall[6] += (double)(2 * ay), hall[7] += (double)(2 * az * az), hall[8] += (double)(2 * az), hall[9] += 2;
-                        qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
-                    };
-                    int k = 0;
-                    for (; k + 4 <= n; k += 4)
-                    { // four points in flight: 12 coalesced loads issued before the first is consumed
-                        const float a0 = qx[k * st], a1 = qx[(k + 1) * st], a2 = qx[(k + 2) * st], a3 = qx[(k + 3) * st];
-                        const float b0 = qy[k * st], b1 = qy[(k + 1) * st], b2 = qy[(k + 2) * st], b3 = qy[(k + 3) * st];
-                        const float c0 = qz[k * st], c1 = qz[(k + 1) * st], c2 = qz[(k + 2) * st], c3 = qz[(k + 3) * st];
-                        point(a0, b0, c0);
-                        point(a1, b1, c1);
-                        point(a2, b2, c2);
-                        point(a3, b3, c3);
+                        const double t0 = (double)(2 * ax * ax), t1 = (double)(2 * ax * ay), t2 = (double)(2 * ax * az), t3 = (double)(2 * ax);
+                        const double t4 = (double)(2 * ay * ay), t5 = (double)(2 * ay * az), t6 = (double)(2 * ay);
+                        const double t7 = (double)(2 * az * az), t8 = (double)(2 * az);
+                        if (gn == 0)
+                        {
+                            hall[0] += t0, hall[1] += t1, hall[2] += t2, hall[3] += t3, hall[4] += t4;
+                            hall[5] += t5, hall[6] += t6, hall[7] += t7, hall[8] += t8, hall[9] += 2;
+                            qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
+                        }
+                        if (!inr)
+                        {
+                            ho[0] += t0, ho[1] += t1, ho[2] += t2, ho[3] += t3, ho[4] += t4;
+                            ho[5] += t5, ho[6] += t6, ho[7] += t7, ho[8] += t8, ho[9] += 2;
+                            if (r >= F_0p4_HI)
+                            { // (double)r >= 0.4 (:157-163)
+                                jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
+                                jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                            }
+                            else if (r <= -F_0p4_HI)
+                            { // (double)r <= -0.4 (:164-170)
+                                jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
+                                jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
+                            }
+                        }
                     }
-                    for (; k < n; k++) point(qx[k * st], qy[k * st], qz[k * st]);
+                };
+                int k = 0;
+                for (; k + 4 <= n; k += 4)
+                { // four points in flight: 12 coalesced loads issued before the first is consumed
+                    const float a0 = qx[k * st], a1 = qx[(k + 1) * st], a2 = qx[(k + 2) * st], a3 = qx[(k + 3) * st];
+                    const float b0 = qy[k * st], b1 = qy[(k + 1) * st], b2 = qy[(k + 2) * st], b3 = qy[(k + 3) * st];
+                    const float c0 = qz[k * st], c1 = qz[(k + 1) * st], c2 = qz[(k + 2) * st], c3 = qz[(k + 3) * st];
+                    point(a0, b0, c0);
+                    point(a1, b1, c1);
+                    point(a2, b2, c2);
+                    point(a3, b3, c3);
                 }
-                else
-                { // later passes only need to know whether every residual is still inside the range
-                    auto point = [&](float ax, float ay, float az)
-                    {
-                        const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
-                        rm = fmaxf(rm, fabsf(r));
-                        rnan |= !(r == r);
-                        anyout |= !(r < F_0p4_HI && r > -F_0p4_HI); // (:134)
-                    };
-                    int k = 0;
-                    for (; k + 4 <= n; k += 4)
-                    {
-                        const float a0 = qx[k * st], a1 = qx[(k + 1) * st], a2 = qx[(k + 2) * st], a3 = qx[(k + 3) * st];
-                        const float b0 = qy[k * st], b1 = qy[(k + 1) * st], b2 = qy[(k + 2) * st], b3 = qy[(k + 3) * st];
-                        const float c0 = qz[k * st], c1 = qz[(k + 1) * st], c2 = qz[(k + 2) * st], c3 = qz[(k + 3) * st];
-                        point(a0, b0, c0);
-                        point(a1, b1, c1);
-                        point(a2, b2, c2);
-                        point(a3, b3, c3);
-                    }
-                    for (; k < n; k++) point(qx[k * st], qy[k * st], qz[k * st]);
-                }
-                if (anyout) gn_outliers(qx, qy, qz, st, n, nx, ny, nz, nb, ho, jo); // rare: second sweep for the corrections
+                for (; k < n; k++) point(qx[k * st], qy[k * st], qz[k * st]);
                 rmax = rnan ? __int_as_float(0x7f800000) : rm; // a NaN residual forces every later pass
             }
             double hh[10], jj[4];
