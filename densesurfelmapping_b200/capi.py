@@ -24,7 +24,7 @@ EXPORTS = [
     "dsm_version", "dsm_strerror", "dsm_last_error", "dsm_create", "dsm_destroy", "dsm_num_seeds",
     "dsm_fuse_frame", "dsm_batch_upload", "dsm_batch_run", "dsm_batch_download", "dsm_sync",
     "dsm_fuse_batch", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
-    "dsm_pool_transform", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
+    "dsm_pool_transform", "dsm_pool_retire", "dsm_pool_append", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
 ]
 
@@ -76,6 +76,8 @@ def load_library():
     L.dsm_pool_upload.argtypes = [vp, vp, ci]
     L.dsm_fuse_frame_resident.argtypes = [vp, ci, vp, cs, vp, cs, vp, ctypes.POINTER(ci)]
     L.dsm_pool_transform.argtypes = [vp, vp]
+    L.dsm_pool_retire.argtypes = [vp, ci, vp, ci, ctypes.POINTER(ci)]
+    L.dsm_pool_append.argtypes = [vp, vp, ci]
     L.dsm_pool_size.argtypes = [vp, ctypes.POINTER(ci)]
     L.dsm_pool_download.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
     L.dsm_get_labels.argtypes = [vp, ci, vp]
@@ -194,6 +196,17 @@ class Context:
     def pool_transform(self, W_colmajor):
         w = np.ascontiguousarray(W_colmajor, dtype=np.float32).reshape(16)
         self._ck(self.lib.dsm_pool_transform(self.h, _ptr(w)))
+
+    def pool_retire(self, keyframe_index, cap=None):
+        cap = self.pool_size() if cap is None else cap
+        out = np.zeros(max(cap, 1), dtype=SURFEL_DTYPE)
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_pool_retire(self.h, int(keyframe_index), _ptr(out), cap, ctypes.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    def pool_append(self, surfels):
+        surfels = np.ascontiguousarray(surfels, dtype=SURFEL_DTYPE)
+        self._ck(self.lib.dsm_pool_append(self.h, _ptr(surfels) if len(surfels) else None, len(surfels)))
 
     def pool_size(self):
         n = ctypes.c_int(0)

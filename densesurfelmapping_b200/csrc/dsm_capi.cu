@@ -771,6 +771,45 @@ extern "C" int dsm_pool_download(dsm_ctx *ctx, dsm_surfel_t *out, int cap, int *
     return DSM_OK;
 }
 
+extern "C" int dsm_pool_retire(dsm_ctx *ctx, int kf, dsm_surfel_t *out, int cap, int *n_out)
+{
+    if (!ctx || !n_out || cap < 0 || (cap > 0 && !out)) return DSM_E_INVALID;
+    if (!ctx->res_active) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    // the alternate pool buffer is free between frames: use it as the ordered output
+    dsm_launch_pool_retire(resident_view(ctx, 0), 0, ctx->res_upper, kf, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
+    int32_t h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->newofs, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    *n_out = h[0];
+    const int c = h[0] < cap ? h[0] : cap;
+    if (c > 0)
+    {
+        CK(cudaMemcpyAsync(out, ctx->pool_snap, (size_t)c * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return DSM_OK;
+}
+
+extern "C" int dsm_pool_append(dsm_ctx *ctx, const dsm_surfel_t *surfels, int n)
+{
+    if (!ctx || n < 0 || (n > 0 && !surfels)) return DSM_E_INVALID;
+    if (!ctx->res_active) return DSM_E_STATE;
+    int cur = 0;
+    int rc = dsm_pool_size(ctx, &cur);
+    if (rc != DSM_OK) return rc;
+    if (cur + n > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
+    if (n == 0) return DSM_OK;
+    CK(cudaMemcpyAsync(ctx->d.pool + cur, surfels, (size_t)n * sizeof(dsm_surfel_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_ofs[0] = 0;
+    ctx->h_ofs[1] = cur + n;
+    CK(cudaMemcpyAsync(ctx->res_ofs, ctx->h_ofs, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->res_upper = cur + n;
+    return DSM_OK;
+}
+
 extern "C" int dsm_pool_transform(dsm_ctx *ctx, const float Wm[16])
 {
     if (!ctx || !Wm) return DSM_E_INVALID;

@@ -1229,11 +1229,18 @@ __global__ void __launch_bounds__(1024) k_init_surfels(const __grid_constant__ D
 //   for every surfel of the pool after a loop closure.  Pure streaming over the 44-byte records,
 //   staged through shared memory like k_fuse.
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pool_count(const __grid_constant__ DsmDev d, int b, int *blkcnt)
+// selection predicate of the pool kernels: mode 0 = live surfels (update_times != 0, fuse_map post-step);
+// mode 1 = live surfels last updated by keyframe `key` (move_add_surfels, surfel_map.cpp:1479-1497)
+__device__ __forceinline__ bool pool_pred(const dsm_surfel_t &e, int mode, int key)
+{
+    return mode == 0 ? (e.update_times != 0) : (e.update_times > 0 && e.last_update == key);
+}
+
+__global__ void __launch_bounds__(256) k_pool_count(const __grid_constant__ DsmDev d, int b, int *blkcnt, int mode, int key)
 {
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
     const int i = begin + blockIdx.x * 256 + threadIdx.x;
-    const bool live = i < end && d.pool[i].update_times != 0;
+    const bool live = i < end && pool_pred(d.pool[i], mode, key);
     const int c = __syncthreads_count(live);
     if (threadIdx.x == 0) blkcnt[blockIdx.x] = (begin + blockIdx.x * 256 < end) ? c : 0;
 }
@@ -1275,7 +1282,7 @@ __global__ void __launch_bounds__(1024) k_pool_scan(const __grid_constant__ DsmD
     }
 }
 
-__global__ void __launch_bounds__(256) k_pool_scatter(const __grid_constant__ DsmDev d, int b, const int *blkofs, dsm_surfel_t *dst)
+__global__ void __launch_bounds__(256) k_pool_scatter(const __grid_constant__ DsmDev d, int b, const int *blkofs, dsm_surfel_t *dst, int mode, int key)
 {
     __shared__ int s_warp[8];
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
@@ -1287,7 +1294,8 @@ __global__ void __launch_bounds__(256) k_pool_scatter(const __grid_constant__ Ds
     if (i < end)
     {
         e = d.pool[i];
-        live = e.update_times != 0;
+        live = pool_pred(e, mode, key);
+        if (live && mode == 1) d.pool[i].update_times = 0; // "delete the surfel from the local point" (surfel_map.cpp:1496)
     }
     const unsigned bal = __ballot_sync(FULL, live);
     if (lane == 0) s_warp[warp] = __popc(bal);
@@ -1422,10 +1430,19 @@ void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, in
 void dsm_launch_pool_compact(const DsmDev &d, int frame, int upper, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, cudaStream_t s)
 {
     const int nblk = (upper + 255) / 256;
-    if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt);
+    if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt, 0, 0);
     k_pool_scan<<<1, 1024, 0, s>>>(d, frame, blkcnt, blkofs, newofs);
-    if (nblk > 0) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst);
+    if (nblk > 0) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst, 0, 0);
     k_pool_append<<<(d.S + 255) / 256, 256, 0, s>>>(d, frame, newofs, dst);
+}
+// move_add_surfels, removal half (surfel_map.cpp:1479-1497): the live surfels whose last_update == key are
+// copied in pool order to dst (count in newofs[0]) and flagged dead in the pool
+void dsm_launch_pool_retire(const DsmDev &d, int frame, int upper, int key, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, cudaStream_t s)
+{
+    const int nblk = (upper + 255) / 256;
+    if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt, 1, key);
+    k_pool_scan<<<1, 1024, 0, s>>>(d, frame, blkcnt, blkofs, newofs);
+    if (nblk > 0) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst, 1, key);
 }
 void dsm_launch_pool_transform(const DsmDev &d, int frame, int upper, const float *Wm_dev, cudaStream_t s)
 {

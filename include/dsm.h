@@ -154,12 +154,20 @@ int dsm_batch_restore_pool(dsm_ctx *ctx);
  *   dsm_pool_transform         warp_active_surfels_cpu_kernel (surfel_map.cpp:750-789):
  *                              p <- W p, n <- R_W n for every pool surfel after a loop closure
  *                              (W = T_loop * T_cam^-1 computed by the caller in fp64, cast to f32).
+ *   dsm_pool_retire            the removal half of SurfelMap::move_add_surfels (surfel_map.cpp:1479-1497):
+ *                              the live surfels whose last_update == keyframe_index are copied out in
+ *                              pool order (they become that pose's attached_surfels) and flagged dead
+ *                              (update_times = 0; the next fuse post-step drops them).  Synchronises.
+ *   dsm_pool_append            the insertion half (surfel_map.cpp:1583-1587): surfels of poses that
+ *                              re-enter the drift-free set are appended to the pool.  Synchronises.
  *   dsm_pool_size / dsm_pool_download   read back (synchronise). */
 int dsm_pool_upload(dsm_ctx *ctx, const dsm_surfel_t *local, int n_local);
 int dsm_fuse_frame_resident(dsm_ctx *ctx, int reference_frame_index,
                             const uint8_t *gray, size_t gray_pitch, const float *depth, size_t depth_pitch,
                             const float pose_colmajor[16], int *n_new);
 int dsm_pool_transform(dsm_ctx *ctx, const float W_colmajor[16]);
+int dsm_pool_retire(dsm_ctx *ctx, int keyframe_index, dsm_surfel_t *out, int cap, int *n_out);
+int dsm_pool_append(dsm_ctx *ctx, const dsm_surfel_t *surfels, int n);
 int dsm_pool_size(dsm_ctx *ctx, int *n_local);
 int dsm_pool_download(dsm_ctx *ctx, dsm_surfel_t *out, int cap, int *n_local);
 

@@ -784,6 +784,21 @@ int dsmor_fuse_map_poststep(void *local_v, int n_local, const void *fresh_v, int
     return size;
 }
 
+/* move_add_surfels, removal half (surfel_map.cpp:1479-1497): live surfels last updated by keyframe
+ * `kf` are copied to `out` in pool order and flagged dead.  Returns how many. */
+int dsmor_retire(void *local_v, int n_local, int kf, void *out_v)
+{
+    surfel_t *local = (surfel_t *)local_v, *out = (surfel_t *)out_v;
+    int n = 0;
+    for (int i = 0; i < n_local; i++)
+        if (local[i].update_times > 0 && local[i].last_update == kf)
+        {
+            out[n++] = local[i];
+            local[i].update_times = 0;
+        }
+    return n;
+}
+
 /* warp_active_surfels_cpu_kernel (surfel_map.cpp:750-789): p <- W p (homogeneous), n <- R_W n */
 void dsmor_warp_active(void *surfels_v, int n, const float *W)
 {

@@ -149,6 +149,17 @@ def fuse_map_poststep(local, new):
     return buf[:n].copy()
 
 
+def retire(local, kf):
+    """move_add_surfels removal half (surfel_map.cpp:1479-1497) via the restatement: returns (local_after, retired)."""
+    lib = _lib("libdsm_oracle.so")
+    lib.dsmor_retire.restype = ctypes.c_int
+    lib.dsmor_retire.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    loc = np.array(local, dtype=SURFEL_DTYPE, copy=True)
+    out = np.zeros(len(loc) + 1, dtype=SURFEL_DTYPE)
+    n = lib.dsmor_retire(loc.ctypes.data if len(loc) else None, len(loc), int(kf), out.ctypes.data)
+    return loc, out[:n].copy()
+
+
 def warp_active(surfels, W_colmajor):
     """warp_active_surfels_cpu_kernel (surfel_map.cpp:750-789) via the restatement."""
     lib = _lib("libdsm_oracle.so")

@@ -99,3 +99,27 @@ def test_pool_transform_loop_closure():
     got = ctx.pool_download()
     check_surfels(got, pyoracle.warp_active(pool, w), "warped pool")
     ctx.close()
+
+
+def test_pool_retire_and_append_move_add_surfels():
+    """move_add_surfels on the resident pool (surfel_map.cpp:1479-1497, :1583-1587): exact, ordered."""
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    orc = oracle_for(cam)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    for t in range(3):  # a pool whose surfels carry last_update in {0, 1, 2}
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(cam, 500 + t, pose)
+        lo, no = orc.fuse(t, gray, depth, pose, pool)
+        pool = pyoracle.fuse_map_poststep(lo, no)
+    assert len(set(pool["last_update"])) >= 2
+    ctx = capi.Context(cam, max_batch=2, max_local_surfels=len(pool) + 5000)
+    ctx.pool_upload(pool)
+    want_local, want_out = pyoracle.retire(pool, 1)
+    got_out = ctx.pool_retire(1)
+    assert len(want_out) > 0 and got_out.tobytes() == want_out.tobytes()
+    assert ctx.pool_download().tobytes() == want_local.tobytes()
+    ctx.pool_append(got_out[:100])
+    after = ctx.pool_download()
+    assert len(after) == len(pool) + 100 and after[len(pool):].tobytes() == got_out[:100].tobytes()
+    ctx.close()
