@@ -168,3 +168,47 @@ def test_pitched_input_and_errors(capi):
     with pytest.raises(capi.DsmError) as ei:
         capi.Context(bad)
     assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("case", ["no_depth", "constant", "binary_noise_holes", "checker_steps", "tiny_depths"])
+def test_adversarial_small_frames(capi, case):
+    """Edge inputs on an odd shape (W%8 == 4, H%8 == 2): no depth at all (only the no-depth cost path),
+    a constant image (every seed goes stable after the first update, so EVERY pixel of passes 2-3 goes
+    through the deferred list / k_relax), salt-and-pepper gray with 50 % holes (maximal label churn),
+    a checkerboard with depth steps (plane fits rejected / NaN normals), and depths around the three
+    validity thresholds 0.01 / 0.05 / 0.1."""
+    cam = synth.Camera(324, 242, 260.0, 260.0, 161.5, 120.5, 0.5, 30.0)
+    H, W = cam.height, cam.width
+    rng = np.random.RandomState(99)
+    yy, xx = np.mgrid[0:H, 0:W]
+    if case == "no_depth":
+        gray = rng.randint(0, 256, (H, W)).astype(np.uint8)
+        depth = np.zeros((H, W), np.float32)
+    elif case == "constant":
+        gray = np.full((H, W), 77, np.uint8)
+        depth = np.full((H, W), 3.0, np.float32)
+    elif case == "binary_noise_holes":
+        gray = (rng.randint(0, 2, (H, W)) * 255).astype(np.uint8)
+        depth = rng.uniform(0.5, 20.0, (H, W)).astype(np.float32)
+        depth[rng.rand(H, W) < 0.5] = 0
+    elif case == "checker_steps":
+        gray = (((xx // 8 + yy // 8) % 2) * 200 + 20).astype(np.uint8)
+        depth = (2.0 + 3.0 * ((xx // 16 + yy // 16) % 2)).astype(np.float32)
+    else:
+        gray = (xx % 256).astype(np.uint8)
+        depth = rng.choice(np.array([0.0, 0.009, 0.011, 0.049, 0.051, 0.099, 0.101, 0.5, 2.0], np.float32), size=(H, W))
+    orc = oracle_for(cam)
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=20000)
+    pose = synth.pose_stream(1)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    for rep in range(2):  # second pass fuses against the surfels of the first
+        lo, no = orc.fuse(rep, gray, depth, pose, pool)
+        lg, ng = ctx.fuse_frame(rep, gray, depth, pose, pool)
+        nbad = int((orc.labels() != ctx.labels()).sum())
+        assert nbad == 0, f"{case} rep {rep}: {nbad} label mismatches"
+        check_seeds(ctx.seeds(), orc.seeds())
+        assert ctx.invariant_violations() == 0
+        check_surfels(lg, lo, f"{case} local")
+        check_surfels(ng, no, f"{case} new")
+        pool = compact_like_caller(lo, no)
+    ctx.close()
