@@ -112,7 +112,9 @@ int dsm_num_seeds(const dsm_ctx *ctx); /* S = (W/8)*(H/8) */
  * update_times == 0, the caller compacts: surfel_map.cpp:1077-1109), `new_out` receives the
  * newly initialised surfels in seed-index order (the reference clears and push_backs,
  * fusion_functions.cpp:320,359); at most new_cap are written, *n_new is the full count.
- * Host pointers; uploads, runs all kernels, downloads, synchronises. */
+ * Host pointers; uploads, runs all kernels, downloads, synchronises.
+ * Input domain: depth values are metres, <= 0.01 means "no measurement"; valid depths must be >= 0.02 m
+ * (below that the reference itself indexes out of bounds). */
 int dsm_fuse_frame(dsm_ctx *ctx, int reference_frame_index,
                    const uint8_t *gray, size_t gray_pitch,
                    const float *depth, size_t depth_pitch,
