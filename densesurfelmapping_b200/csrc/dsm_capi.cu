@@ -16,6 +16,14 @@ struct ProfRec
     cudaEvent_t e0, e1;
 };
 
+// A captured kernel schedule, replayable while every launch parameter is unchanged.
+struct GraphEntry
+{
+    int f0, nf, maxper, compact;
+    const void *pool, *poolofs, *alt;
+    cudaGraphExec_t exec;
+};
+
 struct dsm_ctx
 {
     dsm_params p;
@@ -29,6 +37,8 @@ struct dsm_ctx
     int n_pool;   // local surfels in the current batch
     bool uploaded, ran;
     int stop_after; // debug: number of kernels to enqueue (<= 0: all)
+    std::vector<GraphEntry> graphs; // CUDA-graph cache of the kernel schedule (launch-bound single-frame / small-chunk runs)
+    bool use_graphs;
     // raw allocations (non-const views of what DsmDev holds)
     uint8_t *gray;
     float *depth;
@@ -119,6 +129,7 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
         cudaEventDestroy(r.e1);
     }
     for (auto &e : ctx->ev_free) cudaEventDestroy(e);
+    for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     DsmDev &d = ctx->d;
     cudaFree(ctx->gray);
     cudaFree(ctx->depth);
@@ -200,6 +211,10 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->n_pool = 0;
     ctx->uploaded = ctx->ran = false;
     ctx->stop_after = 0;
+    {
+        const char *e = getenv("DSM_GRAPHS");
+        ctx->use_graphs = !(e && e[0] == '0');
+    }
     ctx->s_h2d = ctx->s_d2h = nullptr;
     for (int i = 0; i < 4; i++) ctx->s_comp[i] = nullptr;
     ctx->ev_start = nullptr;
@@ -506,7 +521,7 @@ extern "C" int dsm_batch_restore_pool(dsm_ctx *ctx)
 
 // The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79),
 // enqueued for the frame slots [f0, f0 + nf).
-static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame, cudaStream_t st)
+static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame, cudaStream_t st)
 {
     DsmDev d = ctx->d;
     d.frame0 = f0;
@@ -544,6 +559,66 @@ static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame
     STEP(DSM_K_INIT_SURFELS, dsm_launch_init_surfels(d, nb, st));
 #undef STEP
     CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+// Enqueue the schedule, optionally followed by the resident-pool post-step (compaction into `alt`).
+// The 17-21 launches are captured once per distinct parameter set into a CUDA graph and replayed: the
+// per-launch CPU cost and inter-kernel gaps matter for single frames and small chunks.  Profiling
+// (event pairs around kernels) and the debug kernel budget use plain launches.
+static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream_t st, bool compact = false)
+{
+    auto plain = [&]() -> int
+    {
+        int rc = launch_schedule(ctx, f0, nf, maxper, st);
+        if (rc != DSM_OK) return rc;
+        if (compact)
+        {
+            DsmDev d = ctx->d;
+            d.frame0 = f0;
+            dsm_launch_pool_compact(d, f0, maxper, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, st);
+        }
+        return DSM_OK;
+    };
+    if (!ctx->use_graphs || ctx->prof_mask != 0 || ctx->stop_after > 0) return plain();
+    for (auto &g : ctx->graphs)
+        if (g.f0 == f0 && g.nf == nf && g.maxper == maxper && g.compact == (int)compact && g.pool == ctx->d.pool &&
+            g.poolofs == ctx->d.poolofs && g.alt == ctx->pool_snap)
+        {
+            CK(cudaGraphLaunch(g.exec, st));
+            return DSM_OK;
+        }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return plain();
+    }
+    int rc = plain();
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != DSM_OK || ce != cudaSuccess || !graph)
+    {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        ctx->use_graphs = false; // capture is not possible in this environment: fall back to plain launches
+        return rc != DSM_OK ? rc : plain();
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || !exec)
+    {
+        cudaGetLastError();
+        ctx->use_graphs = false;
+        return plain();
+    }
+    if (ctx->graphs.size() >= 64)
+    { // bounded cache
+        cudaGraphExecDestroy(ctx->graphs.front().exec);
+        ctx->graphs.erase(ctx->graphs.begin());
+    }
+    ctx->graphs.push_back(GraphEntry{f0, nf, maxper, (int)compact, ctx->d.pool, ctx->d.poolofs, ctx->pool_snap, exec});
+    CK(cudaGraphLaunch(exec, st));
     return DSM_OK;
 }
 
@@ -875,13 +950,16 @@ extern "C" int dsm_fuse_frame_resident(dsm_ctx *ctx, int ref_idx, const uint8_t 
         // enqueue_schedule takes its view from ctx->d: temporarily present the resident pool table
         const int32_t *saved = ctx->d.poolofs;
         ctx->d.poolofs = dv.poolofs;
-        int rc = enqueue_schedule(ctx, slot, 1, ctx->res_upper, ctx->stream);
+        // + post-step of SurfelMap::fuse_map on the device: compact into the alternate buffer (then swap)
+        // grid sizes use the bound rounded up to 64 Ki surfels so that the captured graph stays valid while
+        // the pool grows (surplus blocks exit at once: the kernels read the true range from the device)
+        int upq = (ctx->res_upper + 65535) / 65536 * 65536;
+        if (upq > ctx->p.max_local_surfels) upq = ctx->p.max_local_surfels;
+        int rc = enqueue_schedule(ctx, slot, 1, upq, ctx->stream, true);
         ctx->d.poolofs = saved;
         if (rc != DSM_OK) return rc;
     }
     ctx->ran = true;
-    // post-step of SurfelMap::fuse_map on the device: compact into the alternate buffer, then swap
-    dsm_launch_pool_compact(dv, slot, ctx->res_upper, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
     CK(cudaMemcpyAsync(ctx->res_ofs + 1, ctx->newofs + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
     {
