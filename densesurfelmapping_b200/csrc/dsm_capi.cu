@@ -700,16 +700,30 @@ extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uin
         const int v = atoi(e);
         if (v >= 1 && v <= 8 && v <= n) nchunks = v;
     }
-    const int per = (n + nchunks - 1) / nchunks;
+    // chunk sizes: a SMALL first chunk (the kernels cannot start before it has arrived), the rest even
+    int csize[8];
+    {
+        int first = nchunks >= 4 ? (n / (2 * nchunks) > 0 ? n / (2 * nchunks) : 1) : (n + nchunks - 1) / nchunks;
+        if (nchunks == 1) first = n;
+        csize[0] = first;
+        int rest = n - first, left = nchunks - 1;
+        for (int c = 1; c < nchunks; c++)
+        {
+            csize[c] = left > 0 ? (rest + left - 1) / left : 0;
+            rest -= csize[c];
+            left--;
+        }
+    }
     // copies must not start before earlier work on the compute stream (previous users of the buffers) is done
     CK(cudaEventRecord(ctx->ev_start, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
     CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
     for (int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(ctx->s_comp[i], ctx->ev_start, 0));
     int nc = 0;
-    for (int f0 = 0; f0 < n; f0 += per, nc++)
+    for (int f0 = 0; f0 < n; f0 += csize[nc], nc++)
     {
-        const int nf = (n - f0 < per) ? n - f0 : per;
+        const int nf = csize[nc];
+        if (nf <= 0) break;
         const int p0 = ofs[f0], p1 = ofs[f0 + nf];
         int maxper = 0;
         for (int b = f0; b < f0 + nf; b++) maxper = (ofs[b + 1] - ofs[b] > maxper) ? ofs[b + 1] - ofs[b] : maxper;

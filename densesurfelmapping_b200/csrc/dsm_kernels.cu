@@ -638,6 +638,90 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
     d.tstable[so + s] = newstable ? DSM_STABLE : -1;
 }
 
+// k_newton for SMALL batches (a single-frame stream): with only ~7 k seeds in flight the thread-per-seed
+// chains are pure latency (31 us per launch at batch 1).  Here 8 lanes share a seed: each loads one list
+// entry per step (coalescing is irrelevant at this size, latency is), the residuals are computed in
+// parallel and only the ORDERED accumulation runs as a chain over width-8 shuffles -- same additions in
+// the same order as k_newton, so the results are bit-identical.
+__global__ void __launch_bounds__(128) k_newton_small(const __grid_constant__ DsmDev d)
+{
+    const int b = d.frame0 + blockIdx.y;
+    const int lane = threadIdx.x & 31, gl = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.nlist[b] = 0; // the deferred-pixel list of this pass is consumed
+    if (s >= d.S) return; // whole 8-lane groups leave together
+    const size_t so = (size_t)b * d.S;
+    if (d.tstable[so + s] == DSM_STABLE) return; // untouched by update_seeds
+    const int4 su = d.usum[so + s];
+    const int n = su.x;
+    if (n == 0)
+    { // unreachable for supported shapes; recorded, never silently ignored
+        if (gl == 0)
+        {
+            atomicAdd(&d.errflag[b], 1);
+            d.tstable[so + s] = -1;
+        }
+        return;
+    }
+    const float fn = (float)n;
+    const float mi = (float)su.w / fn, mx = (float)su.y / fn, my = (float)su.z / fn;
+    const float4 pre = d.seed[so + s];
+    const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my))); // (:527)
+    const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
+    const int nd = d.und[so + s];
+    float md = 0.0f;
+    if (nd > 0)
+    {
+        const float *dl = d.dlist + (size_t)b * DL_CAP * d.Sp + s;
+        const size_t st = (size_t)d.Sp;
+        float sum_d = 0.0f;
+        for (int k0 = 0; k0 < nd; k0 += 8)
+        {
+            const float v = (k0 + gl < nd) ? dl[(size_t)(k0 + gl) * st] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+            {
+                const float t = __shfl_sync(gmask, v, j, 8);
+                if (k0 + j < nd) sum_d += t; // raster order (:511)
+            }
+        }
+        md = sum_d / (float)nd;
+        for (int it = 0; it < 5; it++)
+        { // damped Huber-Newton (:534-554)
+            float sa = 0.0f, sb = 0.0f;
+            for (int k0 = 0; k0 < nd; k0 += 8)
+            {
+                const float r = md - ((k0 + gl < nd) ? dl[(size_t)(k0 + gl) * st] : 0.0f);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    const float rj = __shfl_sync(gmask, r, j, 8);
+                    if (k0 + j < nd)
+                    {
+                        if (rj < F_0p4_HI && rj > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
+                        {
+                            sa += 2 * rj;
+                            sb += 2;
+                        }
+                        else
+                            sa = (float)((double)sa + (rj > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
+                    }
+                }
+            }
+            const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
+            md = md + delta;
+            if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552); uniform within the group
+        }
+    }
+    if (gl == 0)
+    {
+        d.seed[so + s] = make_float4(mx, my, mi, md);
+        d.inv_md[so + s] = 1.0 / (double)md;
+        d.tstable[so + s] = newstable ? DSM_STABLE : -1;
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // K3  backproject_normals — calculate_spaces_kernel (:644-662) + calculate_pixels_norms_kernel
 // (:664-712), fused: the reference's 24 B/px fp64 space_map is never materialised.
@@ -1022,6 +1106,163 @@ __global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ Ds
     pl[2] = r2;
 }
 
+// k_gauss_newton for SMALL batches (single-frame stream): 8 lanes per seed.  Every lane takes every 8th
+// point, the fp64 sums are combined with three width-8 shuffle steps, all lanes of the group then hold
+// the same normal equations and solve them redundantly.  Same algebra, pass skipping and thresholds as
+// k_gauss_newton; only the summation order of the fp64 accumulators differs (~1e-16 relative).
+__device__ __forceinline__ double group8_sum(double v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, 8);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_gauss_newton_small(const __grid_constant__ DsmDev d)
+{
+    const int b = d.frame0 + blockIdx.y;
+    const int lane = threadIdx.x & 31, gl = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (s >= d.S) return; // whole 8-lane groups leave together
+    const size_t so = (size_t)b * d.S;
+    const float4 sd = d.seed[so + s];
+    const float4 P0 = d.pfsum[(so + s) * 2], P1 = d.pfsum[(so + s) * 2 + 1];
+    const int n = __float_as_int(P1.w);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r1 = make_float4(0.f, 0.f, 0.f, sd.w);
+    float4 r2 = make_float4(0.f, sd.z, sd.x, sd.y);
+    if (n > 0)
+    {
+        const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
+        float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
+        const float mxs = P1.x, mys = P1.y, mzs = P1.z;
+        const size_t plane = (size_t)d.B * PF_CAP * d.Sp, st = (size_t)d.Sp;
+        const float *qx = d.qlist + (size_t)b * PF_CAP * d.Sp + s;
+        const float *qy = qx + plane, *qz = qy + plane;
+        double hall[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float rmax = 0.f, qmax2 = 0.f;
+        bool need_pass = true;
+        for (int gn = 0; gn < 5; gn++)
+        {
+            double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double jo[4] = {0, 0, 0, 0};
+            if (need_pass)
+            {
+                float rm = 0.f;
+                int flags = 0; // bit0: some residual NaN, bit1: some residual outside the Huber range
+                for (int k = gl; k < n; k += 8)
+                {
+                    const float ax = qx[k * st], ay = qy[k * st], az = qz[k * st];
+                    const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
+                    const bool inr = r < F_0p4_HI && r > -F_0p4_HI;  // (:134)
+                    rm = fmaxf(rm, fabsf(r));
+                    flags |= (r == r ? 0 : 1) | (inr ? 0 : 2);
+                    if (gn == 0 || !inr)
+                    {
+                        const double t0 = (double)(2 * ax * ax), t1 = (double)(2 * ax * ay), t2 = (double)(2 * ax * az), t3 = (double)(2 * ax);
+                        const double t4 = (double)(2 * ay * ay), t5 = (double)(2 * ay * az), t6 = (double)(2 * ay);
+                        const double t7 = (double)(2 * az * az), t8 = (double)(2 * az);
+                        if (gn == 0)
+                        {
+                            hall[0] += t0, hall[1] += t1, hall[2] += t2, hall[3] += t3, hall[4] += t4;
+                            hall[5] += t5, hall[6] += t6, hall[7] += t7, hall[8] += t8, hall[9] += 2;
+                            qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
+                        }
+                        if (!inr)
+                        {
+                            ho[0] += t0, ho[1] += t1, ho[2] += t2, ho[3] += t3, ho[4] += t4;
+                            ho[5] += t5, ho[6] += t6, ho[7] += t7, ho[8] += t8, ho[9] += 2;
+                            if (r >= F_0p4_HI)
+                            {
+                                jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
+                                jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                            }
+                            else if (r <= -F_0p4_HI)
+                            {
+                                jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
+                                jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1)
+                {
+                    rm = fmaxf(rm, __shfl_xor_sync(gmask, rm, o, 8));
+                    flags |= __shfl_xor_sync(gmask, flags, o, 8);
+                }
+                if (gn == 0)
+                {
+#pragma unroll
+                    for (int i = 0; i < 10; i++) hall[i] = group8_sum(hall[i], gmask);
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) qmax2 = fmaxf(qmax2, __shfl_xor_sync(gmask, qmax2, o, 8));
+                }
+                if (flags & 2)
+                { // uniform within the group after the reduction
+#pragma unroll
+                    for (int i = 0; i < 10; i++) ho[i] = group8_sum(ho[i], gmask);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) jo[i] = group8_sum(jo[i], gmask);
+                }
+                rmax = (flags & 1) ? __int_as_float(0x7f800000) : rm;
+            }
+            double hh[10], jj[4];
+#pragma unroll
+            for (int i = 0; i < 10; i++) hh[i] = hall[i] - ho[i];
+            const double tx = (double)nx, ty = (double)ny, tz = (double)nz, tb = (double)nb;
+            jj[0] = ((hh[0] * tx + hh[1] * ty) + hh[2] * tz) + hh[3] * tb + jo[0];
+            jj[1] = ((hh[1] * tx + hh[4] * ty) + hh[5] * tz) + hh[6] * tb + jo[1];
+            jj[2] = ((hh[2] * tx + hh[5] * ty) + hh[7] * tz) + hh[8] * tb + jo[2];
+            jj[3] = ((hh[3] * tx + hh[6] * ty) + hh[8] * tz) + hh[9] * tb + jo[3];
+            hh[0] += 5, hh[4] += 5, hh[7] += 5, hh[9] += 5; // LM damping (:172-175)
+            double u[4];
+            solve4_spd(hh, jj, u);
+            const float ox = nx, oy = ny, oz = nz, ob = nb;
+            nx = (float)((double)nx - u[0]);
+            ny = (float)((double)ny - u[1]);
+            nz = (float)((double)nz - u[2]);
+            nb = (float)((double)nb - u[3]);
+            const float dx = nx - ox, dy = ny - oy, dz = nz - oz;
+            const float bound = rmax + sqrtf(qmax2) * sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + fabsf(nb - ob) + 1e-3f;
+            need_pass = !(bound < 0.39f);
+            rmax = bound;
+        }
+        nb = nb - (nx * mxs + ny * mys + nz * mzs);
+        const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
+        nx /= nl;
+        ny /= nl;
+        nz /= nl;
+        nb /= nl;
+        const float axf = (sd.x - d.cx) / d.fx * sd.w;
+        const float ayf = (sd.y - d.cy) / d.fy * sd.w;
+        double ax = (double)axf, ay = (double)ayf, az = (double)sd.w;
+        const float kk = (float)(-1 * (ax * (double)nx + ay * (double)ny + az * (double)nz) - (double)nb);
+        ax += (double)(kk * nx);
+        ay += (double)(kk * ny);
+        az += (double)(kk * nz);
+        const float mean_depth = (float)az;
+        float view_cos = (float)(-1.0 * ((double)nx * ax + (double)ny * ay + (double)nz * az) / sqrt(ax * ax + ay * ay + az * az));
+        if (view_cos < 0)
+        {
+            view_cos = -view_cos;
+            nx = -nx;
+            ny = -ny;
+            nz = -nz;
+        }
+        r0 = make_float4(nx, ny, nz, view_cos);
+        r1 = make_float4((float)ax, (float)ay, (float)az, mean_depth);
+        r2.x = sqrtf(P0.w);
+    }
+    if (gl == 0)
+    {
+        float4 *pl = d.plane + (so + s) * 3;
+        pl[0] = r0;
+        pl[1] = r1;
+        pl[2] = r2;
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // K5  surfel_fuse — fuse_surfels_kernel (:190-313).  Pure map over the frame's pool slice.
 // The AoS pool (44 B/element, ABI layout) is staged through shared memory with fully coalesced
@@ -1396,6 +1637,12 @@ void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s)
 }
 void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s)
 {
+    if ((long)nb * d.S <= 20000)
+    { // single-frame streams: 8 lanes per seed, latency- instead of throughput-oriented
+        dim3 grid((d.S * 8 + 127) / 128, nb);
+        k_newton_small<<<grid, 128, 0, s>>>(d);
+        return;
+    }
     dim3 grid((d.S + 127) / 128, nb);
     k_newton<<<grid, 128, 0, s>>>(d);
 }
@@ -1412,6 +1659,12 @@ void dsm_launch_gather_points(const DsmDev &d, int nb, cudaStream_t s)
 }
 void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s)
 {
+    if ((long)nb * d.S <= 20000)
+    { // single-frame streams: 8 lanes per seed
+        dim3 grid((d.S * 8 + 127) / 128, nb);
+        k_gauss_newton_small<<<grid, 128, 0, s>>>(d);
+        return;
+    }
     dim3 grid((d.S + 127) / 128, nb);
     k_gauss_newton<<<grid, 128, 0, s>>>(d);
 }
