@@ -700,16 +700,12 @@ extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uin
         const int v = atoi(e);
         if (v >= 1 && v <= 8 && v <= n) nchunks = v;
     }
-    // chunk sizes: a SMALL first chunk (the kernels cannot start before it has arrived), the rest even
-    int csize[8];
+    int csize[8]; // even chunks (a smaller first chunk was tried: no gain, the kernels of small chunks are less efficient)
     {
-        int first = nchunks >= 4 ? (n / (2 * nchunks) > 0 ? n / (2 * nchunks) : 1) : (n + nchunks - 1) / nchunks;
-        if (nchunks == 1) first = n;
-        csize[0] = first;
-        int rest = n - first, left = nchunks - 1;
-        for (int c = 1; c < nchunks; c++)
+        int rest = n, left = nchunks;
+        for (int c = 0; c < nchunks; c++)
         {
-            csize[c] = left > 0 ? (rest + left - 1) / left : 0;
+            csize[c] = (rest + left - 1) / left;
             rest -= csize[c];
             left--;
         }

@@ -675,29 +675,38 @@ __global__ void __launch_bounds__(128) k_newton_small(const __grid_constant__ Ds
     {
         const float *dl = d.dlist + (size_t)b * DL_CAP * d.Sp + s;
         const size_t st = (size_t)d.Sp;
+        // the whole list is fetched up front (one round trip, up to 29 loads in flight per lane) and kept
+        // in registers: lane gl owns entries gl, gl+8, gl+16, ...
+        constexpr int NC = (DL_CAP + 7) / 8;
+        float vc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) vc[c] = (8 * c + gl < nd) ? dl[(size_t)(8 * c + gl) * st] : 0.0f;
         float sum_d = 0.0f;
-        for (int k0 = 0; k0 < nd; k0 += 8)
+#pragma unroll
+        for (int c = 0; c < NC; c++)
         {
-            const float v = (k0 + gl < nd) ? dl[(size_t)(k0 + gl) * st] : 0.0f;
+            if (8 * c >= nd) break;
 #pragma unroll
             for (int j = 0; j < 8; j++)
             {
-                const float t = __shfl_sync(gmask, v, j, 8);
-                if (k0 + j < nd) sum_d += t; // raster order (:511)
+                const float t = __shfl_sync(gmask, vc[c], j, 8);
+                if (8 * c + j < nd) sum_d += t; // raster order (:511)
             }
         }
         md = sum_d / (float)nd;
         for (int it = 0; it < 5; it++)
         { // damped Huber-Newton (:534-554)
             float sa = 0.0f, sb = 0.0f;
-            for (int k0 = 0; k0 < nd; k0 += 8)
+#pragma unroll
+            for (int c = 0; c < NC; c++)
             {
-                const float r = md - ((k0 + gl < nd) ? dl[(size_t)(k0 + gl) * st] : 0.0f);
+                if (8 * c >= nd) break;
+                const float r = md - vc[c];
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                 {
                     const float rj = __shfl_sync(gmask, r, j, 8);
-                    if (k0 + j < nd)
+                    if (8 * c + j < nd)
                     {
                         if (rj < F_0p4_HI && rj > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
                         {
