@@ -638,99 +638,6 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
     d.tstable[so + s] = newstable ? DSM_STABLE : -1;
 }
 
-// k_newton for SMALL batches (a single-frame stream): with only ~7 k seeds in flight the thread-per-seed
-// chains are pure latency (31 us per launch at batch 1).  Here 8 lanes share a seed: each loads one list
-// entry per step (coalescing is irrelevant at this size, latency is), the residuals are computed in
-// parallel and only the ORDERED accumulation runs as a chain over width-8 shuffles -- same additions in
-// the same order as k_newton, so the results are bit-identical.
-__global__ void __launch_bounds__(128) k_newton_small(const __grid_constant__ DsmDev d)
-{
-    const int b = d.frame0 + blockIdx.y;
-    const int lane = threadIdx.x & 31, gl = lane & 7;
-    const unsigned gmask = 0xffu << (lane & 24);
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.nlist[b] = 0; // the deferred-pixel list of this pass is consumed
-    if (s >= d.S) return; // whole 8-lane groups leave together
-    const size_t so = (size_t)b * d.S;
-    if (d.tstable[so + s] == DSM_STABLE) return; // untouched by update_seeds
-    const int4 su = d.usum[so + s];
-    const int n = su.x;
-    if (n == 0)
-    { // unreachable for supported shapes; recorded, never silently ignored
-        if (gl == 0)
-        {
-            atomicAdd(&d.errflag[b], 1);
-            d.tstable[so + s] = -1;
-        }
-        return;
-    }
-    const float fn = (float)n;
-    const float mi = (float)su.w / fn, mx = (float)su.y / fn, my = (float)su.z / fn;
-    const float4 pre = d.seed[so + s];
-    const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my))); // (:527)
-    const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
-    const int nd = d.und[so + s];
-    float md = 0.0f;
-    if (nd > 0)
-    {
-        const float *dl = d.dlist + (size_t)b * DL_CAP * d.Sp + s;
-        const size_t st = (size_t)d.Sp;
-        // the whole list is fetched up front (one round trip, up to 29 loads in flight per lane) and kept
-        // in registers: lane gl owns entries gl, gl+8, gl+16, ...
-        constexpr int NC = (DL_CAP + 7) / 8;
-        float vc[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) vc[c] = (8 * c + gl < nd) ? dl[(size_t)(8 * c + gl) * st] : 0.0f;
-        float sum_d = 0.0f;
-#pragma unroll
-        for (int c = 0; c < NC; c++)
-        {
-            if (8 * c >= nd) break;
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-            {
-                const float t = __shfl_sync(gmask, vc[c], j, 8);
-                if (8 * c + j < nd) sum_d += t; // raster order (:511)
-            }
-        }
-        md = sum_d / (float)nd;
-        for (int it = 0; it < 5; it++)
-        { // damped Huber-Newton (:534-554)
-            float sa = 0.0f, sb = 0.0f;
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-            {
-                if (8 * c >= nd) break;
-                const float r = md - vc[c];
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                {
-                    const float rj = __shfl_sync(gmask, r, j, 8);
-                    if (8 * c + j < nd)
-                    {
-                        if (rj < F_0p4_HI && rj > -F_0p4_HI) // (double)r < 0.4 && (double)r > -0.4
-                        {
-                            sa += 2 * rj;
-                            sb += 2;
-                        }
-                        else
-                            sa = (float)((double)sa + (rj > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
-                    }
-                }
-            }
-            const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
-            md = md + delta;
-            if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552); uniform within the group
-        }
-    }
-    if (gl == 0)
-    {
-        d.seed[so + s] = make_float4(mx, my, mi, md);
-        d.inv_md[so + s] = 1.0 / (double)md;
-        d.tstable[so + s] = newstable ? DSM_STABLE : -1;
-    }
-}
-
 // -------------------------------------------------------------------------------------------
 // K3  backproject_normals — calculate_spaces_kernel (:644-662) + calculate_pixels_norms_kernel
 // (:664-712), fused: the reference's 24 B/px fp64 space_map is never materialised.
@@ -1646,12 +1553,6 @@ void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s)
 }
 void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s)
 {
-    if ((long)nb * d.S <= 20000)
-    { // single-frame streams: 8 lanes per seed, latency- instead of throughput-oriented
-        dim3 grid((d.S * 8 + 127) / 128, nb);
-        k_newton_small<<<grid, 128, 0, s>>>(d);
-        return;
-    }
     dim3 grid((d.S + 127) / 128, nb);
     k_newton<<<grid, 128, 0, s>>>(d);
 }
