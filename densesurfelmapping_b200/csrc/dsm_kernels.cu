@@ -564,43 +564,36 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
         const float *dl = d.dlist + (size_t)b * DL_CAP * d.Sp + s;
         const size_t st = (size_t)d.Sp;
         // The adds are a serial dependence chain (that IS the reference's rounding order), but the
-        // loads are independent: list entries are fetched 8 at a time and double-buffered, so the next
-        // batch's 8 requests are in flight while the current batch goes through the chain.
-        const int nfull = nd >> 3;
-#define NW_LOAD(dst, ptr)               \
-    _Pragma("unroll") for (int j = 0; j < 8; j++) dst[j] = (ptr)[j * st];
+        // loads are independent: fetch 8 list entries at a time so 8 requests are in flight per lane.
+        // The list stays in registers for the first 32 entries (most seeds' whole first pass).
         float sum_d = 0.0f;
         {
             const float *pp = dl;
-            float va[8], vb[8];
-            int bi = 0;
-            if (nfull) { NW_LOAD(va, pp) }
-            while (bi < nfull)
+            int k = 0;
+            for (; k + 8 <= nd; k += 8, pp += 8 * st)
             {
-                if (bi + 1 < nfull) { NW_LOAD(vb, pp + 8 * st) }
+                float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) sum_d += va[j]; // raster order (:511)
-                bi++, pp += 8 * st;
-                if (bi >= nfull) break;
-                if (bi + 1 < nfull) { NW_LOAD(va, pp + 8 * st) }
+                for (int j = 0; j < 8; j++) v[j] = pp[j * st];
 #pragma unroll
-                for (int j = 0; j < 8; j++) sum_d += vb[j];
-                bi++, pp += 8 * st;
+                for (int j = 0; j < 8; j++) sum_d += v[j]; // raster order (:511)
             }
-            for (int k = nfull * 8; k < nd; k++, pp += st) sum_d += *pp;
+            for (; k < nd; k++, pp += st) sum_d += *pp;
         }
         md = sum_d / (float)nd;
         for (int it = 0; it < 5; it++)
         { // damped Huber-Newton (:534-554)
             float sa = 0.0f, sb = 0.0f;
-            auto chain8 = [&](const float *v)
+            const float *pp = dl;
+            int k = 0;
+            for (; k + 8 <= nd; k += 8, pp += 8 * st)
             {
                 float r[8];
                 bool allin = true;
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                 {
-                    r[j] = md - v[j];
+                    r[j] = md - pp[j * st];
                     allin &= r[j] < F_0p4_HI && r[j] > -F_0p4_HI; // (double)r < 0.4 && (double)r > -0.4
                 }
                 if (allin)
@@ -623,22 +616,8 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
                             sa = (float)((double)sa + (r[j] > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
                     }
                 }
-            };
-            const float *pp = dl;
-            float va[8], vb[8];
-            int bi = 0;
-            if (nfull) { NW_LOAD(va, pp) }
-            while (bi < nfull)
-            {
-                if (bi + 1 < nfull) { NW_LOAD(vb, pp + 8 * st) }
-                chain8(va);
-                bi++, pp += 8 * st;
-                if (bi >= nfull) break;
-                if (bi + 1 < nfull) { NW_LOAD(va, pp + 8 * st) }
-                chain8(vb);
-                bi++, pp += 8 * st;
             }
-            for (int k = nfull * 8; k < nd; k++, pp += st)
+            for (; k < nd; k++, pp += st)
             {
                 const float r = md - *pp;
                 if (r < F_0p4_HI && r > -F_0p4_HI)
@@ -653,7 +632,6 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
             md = md + delta;
             if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
         }
-#undef NW_LOAD
     }
     d.seed[so + s] = make_float4(mx, my, mi, md);
     d.inv_md[so + s] = 1.0 / (double)md;
