@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(256, 5) k_gather_points(const __grid_constant_
         const float4 k4 = *reinterpret_cast<const float4 *>(d.kx + (colin ? xq : 0));
         const float kxv[4] = {k4.x, k4.y, k4.z, k4.w};
         int4 l4[2];
-        float4 z4[2], na[2], nbv[2], ncv[2];
+        float4 z4[2];
         float kyv[2];
         int yy[2];
         unsigned pof[2];
@@ -781,11 +781,6 @@ __global__ void __launch_bounds__(256, 5) k_gather_points(const __grid_constant_
             pof[ps] = po;
             l4[ps] = *reinterpret_cast<const int4 *>(lab + po); // out-of-window lanes read element 0 and are masked below
             z4[ps] = *reinterpret_cast<const float4 *>(dep + po);
-            // the pixel normals are fetched with the labels (not after the member test): one memory round
-            // trip per window instead of two
-            na[ps] = *reinterpret_cast<const float4 *>(nrx + po);
-            nbv[ps] = *reinterpret_cast<const float4 *>(nry + po);
-            ncv[ps] = *reinterpret_cast<const float4 *>(nrz + po);
             kyv[ps] = d.ky[in ? y : 0];
             if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
         }
@@ -820,7 +815,9 @@ __global__ void __launch_bounds__(256, 5) k_gather_points(const __grid_constant_
             }
             if (mi)
             { // pixel normals of this 4-pixel group: three 16-byte loads instead of up to 12 scalar ones
-                const float4 a = na[ps], bb = nbv[ps], c = ncv[ps];
+                const float4 a = *reinterpret_cast<const float4 *>(nrx + pof[ps]);
+                const float4 bb = *reinterpret_cast<const float4 *>(nry + pof[ps]);
+                const float4 c = *reinterpret_cast<const float4 *>(nrz + pof[ps]);
                 const float ax[4] = {a.x, a.y, a.z, a.w}, ay[4] = {bb.x, bb.y, bb.z, bb.w}, az[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
