@@ -741,7 +741,7 @@ __device__ __forceinline__ void solve4_spd(const double *h, const double *j, dou
 
 #define PF_CAP 228 // >= 15*15 possible members of a superpixel
 
-__global__ void __launch_bounds__(256, 5) k_gather_points(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ DsmDev d)
 {
     // tile[plane][k][seed-in-block]: compacted in shared memory, copied out as full 32-byte sectors
     __shared__ float tile[3 * PF_CAP * 8];
