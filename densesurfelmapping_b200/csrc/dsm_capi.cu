@@ -95,7 +95,7 @@ extern "C" const char *dsm_strerror(int code)
     {
     case DSM_OK: return "ok";
     case DSM_E_INVALID: return "invalid argument";
-    case DSM_E_SHAPE: return "unsupported image shape (W%8 or H%8 > 4, or smaller than 24x24 / fewer than 10 seeds)";
+    case DSM_E_SHAPE: return "unsupported image shape (W%8 or H%8 > 4, or smaller than 24x24)";
     case DSM_E_NODEVICE: return "no usable CUDA device (sm_100 required)";
     case DSM_E_CUDA: return "CUDA error";
     case DSM_E_NOMEM: return "out of memory";
@@ -190,7 +190,6 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     const int W = params->width, H = params->height;
     if (params->max_batch < 1 || params->max_local_surfels < 0) return DSM_E_INVALID;
     if (W < 3 * DSM_SP || H < 3 * DSM_SP || W % DSM_SP > 4 || H % DSM_SP > 4) return DSM_E_SHAPE;
-    if ((W / DSM_SP) * (H / DSM_SP) < DSM_THREAD_NUM) return DSM_E_SHAPE;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DSM_E_NODEVICE;
     cudaDeviceProp prop;

@@ -29,7 +29,6 @@
 #include "../../include/dsm.h"
 
 #define DSM_SP 8
-#define DSM_THREAD_NUM 10 // the reference's static 10-way partition (fusion_functions.h:9), needed for H3
 #define DSM_STABLE 0x7fffffff
 
 struct DsmDev

@@ -44,21 +44,7 @@ __device__ __forceinline__ void sts_f32(unsigned addr, float v)
 { // st.shared with a precomputed 32-bit shared-window address (keeps the address math out of the hot loops)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
 }
-__device__ __forceinline__ int chunk_of(int s, int S)
-{ // which of the reference's 10 static chunks seed s falls in (:471-475)
-    int step = S / DSM_THREAD_NUM;
-    if (step == 0) return DSM_THREAD_NUM - 1;
-    int c = s / step;
-    return c > DSM_THREAD_NUM - 1 ? DSM_THREAD_NUM - 1 : c;
-}
-
 __device__ __forceinline__ float warp_sum_f(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_sum_d(double v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
