@@ -23,7 +23,7 @@ NUM_KERNELS = 12
 EXPORTS = [
     "dsm_version", "dsm_strerror", "dsm_last_error", "dsm_create", "dsm_destroy", "dsm_num_seeds",
     "dsm_fuse_frame", "dsm_batch_upload", "dsm_batch_run", "dsm_batch_download", "dsm_sync",
-    "dsm_fuse_batch", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
+    "dsm_fuse_batch", "dsm_fuse_batch_async", "dsm_batch_wait", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
     "dsm_pool_transform", "dsm_pool_retire", "dsm_pool_append", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
 ]
@@ -72,6 +72,8 @@ def load_library():
     L.dsm_batch_download.argtypes = [vp, vp, vp, vp]
     L.dsm_sync.argtypes = [vp]
     L.dsm_fuse_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dsm_fuse_batch_async.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dsm_batch_wait.argtypes = [vp]
     L.dsm_batch_restore_pool.argtypes = [vp]
     L.dsm_pool_upload.argtypes = [vp, vp, ci]
     L.dsm_fuse_frame_resident.argtypes = [vp, ci, vp, cs, vp, cs, vp, ctypes.POINTER(ci)]

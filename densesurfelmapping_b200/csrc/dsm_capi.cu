@@ -36,6 +36,7 @@ struct dsm_ctx
     int nb;       // frames in the current batch
     int n_pool;   // local surfels in the current batch
     bool uploaded, ran;
+    bool in_flight; // a dsm_fuse_batch_async batch has been enqueued and not yet waited for
     int stop_after; // debug: number of kernels to enqueue (<= 0: all)
     std::vector<GraphEntry> graphs; // CUDA-graph cache of the kernel schedule (launch-bound single-frame / small-chunk runs)
     bool use_graphs;
@@ -209,6 +210,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->nb = 0;
     ctx->n_pool = 0;
     ctx->uploaded = ctx->ran = false;
+    ctx->in_flight = false;
     ctx->stop_after = 0;
     {
         const char *e = getenv("DSM_GRAPHS");
@@ -676,18 +678,36 @@ extern "C" int dsm_sync(dsm_ctx *ctx)
     return DSM_OK;
 }
 
-// End-to-end batch call with host buffers.  The batch is cut into chunks of frames; chunk c's H2D
+// End-to-end batch call with host buffers (dsm_fuse_batch = dsm_fuse_batch_async + dsm_batch_wait).  The batch is cut into chunks of frames; chunk c's H2D
 // (copy stream), kernels (compute stream) and D2H (second copy stream) overlap with the neighbouring
 // chunks, so the call costs about max(PCIe time, kernel time) instead of their sum.  Host buffers
 // should be pinned for the copies to be truly asynchronous (pageable memory works, staged by the driver).
-extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uint8_t *gray, const float *depth,
-                              const float *poses, dsm_surfel_t *local, const int32_t *ofs,
-                              dsm_surfel_t *new_out, int32_t *n_new)
+extern "C" int dsm_batch_wait(dsm_ctx *ctx)
+{
+    if (!ctx) return DSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->s_h2d));
+    for (int i = 0; i < 4; i++) CK(cudaStreamSynchronize(ctx->s_comp[i]));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    CK(cudaGetLastError());
+    ctx->in_flight = false;
+    return DSM_OK;
+}
+
+extern "C" int dsm_fuse_batch_async(dsm_ctx *ctx, int n, const int32_t *ref, const uint8_t *gray, const float *depth,
+                                    const float *poses, dsm_surfel_t *local, const int32_t *ofs,
+                                    dsm_surfel_t *new_out, int32_t *n_new)
 {
     if (!ctx || !ref || !gray || !depth || !poses || !ofs) return DSM_E_INVALID;
     if (n < 1 || n > ctx->p.max_batch) return DSM_E_INVALID;
     if (ofs[n] > 0 && !local) return DSM_E_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->in_flight)
+    { // one batch per context at a time: finish the previous one first
+        int rcw = dsm_batch_wait(ctx);
+        if (rcw != DSM_OK) return rcw;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     int rc = upload_tables(ctx, n, ref, poses, ofs, 0); // small tables, on the compute stream
     if (rc != DSM_OK) return rc;
@@ -753,12 +773,18 @@ extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uin
     ctx->nb = n;
     ctx->uploaded = true;
     ctx->ran = true;
-    CK(cudaStreamSynchronize(ctx->s_h2d));
-    for (int i = 0; i < 4; i++) CK(cudaStreamSynchronize(ctx->s_comp[i]));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaStreamSynchronize(ctx->s_d2h));
+    ctx->in_flight = true;
     CK(cudaGetLastError());
     return DSM_OK;
+}
+
+extern "C" int dsm_fuse_batch(dsm_ctx *ctx, int n, const int32_t *ref, const uint8_t *gray, const float *depth,
+                              const float *poses, dsm_surfel_t *local, const int32_t *ofs,
+                              dsm_surfel_t *new_out, int32_t *n_new)
+{
+    int rc = dsm_fuse_batch_async(ctx, n, ref, gray, depth, poses, local, ofs, new_out, n_new);
+    if (rc != DSM_OK) return rc;
+    return dsm_batch_wait(ctx);
 }
 
 extern "C" int dsm_fuse_frame(dsm_ctx *ctx, int ref_idx, const uint8_t *gray, size_t gray_pitch,

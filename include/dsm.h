@@ -138,6 +138,15 @@ int dsm_fuse_batch(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_in
                    const uint8_t *gray, const float *depth, const float *poses_colmajor,
                    dsm_surfel_t *local, const int32_t *local_offsets,
                    dsm_surfel_t *new_out, int32_t *n_new);
+/* The same call split in two so that a caller can double-buffer: dsm_fuse_batch_async() enqueues the copies
+ * and kernels and returns; every host buffer must stay valid and untouched until dsm_batch_wait() returns.
+ * One batch per context may be in flight; with two contexts the H2D copies of batch k+1 overlap the kernels
+ * of batch k completely (what bench.py's e2e leg does). */
+int dsm_fuse_batch_async(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_index,
+                         const uint8_t *gray, const float *depth, const float *poses_colmajor,
+                         dsm_surfel_t *local, const int32_t *local_offsets,
+                         dsm_surfel_t *new_out, int32_t *n_new);
+int dsm_batch_wait(dsm_ctx *ctx);
 /* Re-upload only the local pool (the kernels update it in place, so a benchmark that replays
  * the same batch must restore it between steps). Device-to-device from an internal snapshot
  * taken at the last dsm_batch_upload. */

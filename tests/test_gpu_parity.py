@@ -214,3 +214,35 @@ def test_adversarial_small_frames(capi, case):
         check_surfels(ng, no, f"{case} new")
         pool = compact_like_caller(lo, no)
     ctx.close()
+
+
+def test_async_batch_double_buffering(capi):
+    """dsm_fuse_batch_async + dsm_batch_wait on two alternating contexts gives the same bytes as the
+    synchronous dsm_fuse_batch."""
+    cam = synth.VGA
+    B = 3
+    frames = [synth.make_frame(cam, 700 + b, synth.pose_stream(b)) for b in range(B)]
+    gray = np.stack([f[0] for f in frames])
+    depth = np.stack([f[1] for f in frames])
+    poses = np.stack([synth.pose_stream(b) for b in range(B)])
+    refs = np.zeros(B, np.int32)
+    ofs = np.zeros(B + 1, np.int32)
+    ctxs = [capi.Context(cam, max_batch=B, max_local_surfels=64) for _ in range(2)]
+    S = ctxs[0].S
+    want_local, want_new = ctxs[0].fuse_batch(refs, gray, depth, poses, np.zeros(0, SURFEL_DTYPE), ofs)
+    outs = []
+    for k in range(4):
+        c = ctxs[k & 1]
+        new = np.zeros((B, S), SURFEL_DTYPE)
+        cnt = np.zeros(B, np.int32)
+        assert c.lib.dsm_batch_wait(c.h) == 0
+        rc = c.lib.dsm_fuse_batch_async(c.h, B, refs.ctypes.data, gray.ctypes.data, depth.ctypes.data, poses.ctypes.data,
+                                        None, ofs.ctypes.data, new.ctypes.data, cnt.ctypes.data)
+        assert rc == 0
+        outs.append((c, new, cnt))
+    for c, new, cnt in outs:
+        assert c.lib.dsm_batch_wait(c.h) == 0
+        for b in range(B):
+            assert cnt[b] == len(want_new[b]) and new[b, :cnt[b]].tobytes() == want_new[b].tobytes()
+    for c in ctxs:
+        c.close()
