@@ -569,6 +569,10 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
 // (event pairs around kernels) and the debug kernel budget use plain launches.
 static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream_t st, bool compact = false)
 {
+    // grids over the pool are sized from `maxper` rounded up to 4 Ki surfels (the kernels take the true
+    // ranges from poolofs on the device, surplus blocks exit at once), so that callers whose pool size
+    // changes a little from call to call keep hitting the same captured graph
+    if (maxper > 0) maxper = (maxper + 4095) & ~4095;
     auto plain = [&]() -> int
     {
         int rc = launch_schedule(ctx, f0, nf, maxper, st);
