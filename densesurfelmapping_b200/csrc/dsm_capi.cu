@@ -284,8 +284,8 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(ctx->ky, (size_t)H + 16);
     ALLOC(ctx->gray_packed, (size_t)B * H * W + 64);
     ALLOC(ctx->depth_packed, (size_t)B * H * W + 64);
-    ALLOC(ctx->blkcnt, npool / 256 + 2);
-    ALLOC(ctx->blkofs, npool / 256 + 2);
+    ALLOC(ctx->blkcnt, npool / 256 + 64);
+    ALLOC(ctx->blkofs, npool / 256 + 64);
     ALLOC(ctx->newofs, 2);
     ALLOC(ctx->wmat, 16);
     ALLOC(ctx->res_ofs, 2);
