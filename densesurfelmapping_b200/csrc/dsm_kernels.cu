@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDe
             const float my_i = gi[i];
             // (:404-405) my_inv = (float)(1.0 / (double)depth) for depth > 0.01.  53 >= 2*24+2 bits, so the
             // double rounding is innocuous and the IEEE float reciprocal gives the same value.
-            float my_inv = 0.0f;
-            if (zi[i] > F_0p01_LO) my_inv = (zi[i] < 1e30f) ? __fdiv_rn(1.0f, zi[i]) : (float)(1.0 / (double)zi[i]);
+            // (__frcp_rn is the correctly rounded reciprocal, subnormal results included; -ftz=false)
+            const float my_inv = (zi[i] > F_0p01_LO) ? __frcp_rn(zi[i]) : 0.0f;
             const double my_inv_d = (double)my_inv;
             const float fx = (float)x;
             float min_d = 1e6f, min_nd = 1e6f;
@@ -425,7 +425,10 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     const int W = d.W, H = d.H, Wp = d.Wp;
     const size_t so = (size_t)b * d.S;
     const bool live = sp_x < d.spw && d.tstable[so + (sp_x < d.spw ? s : 0)] != DSM_STABLE; // stable seeds are skipped (:478-479)
-    if (live) // warp-uniform
+    // Non-live warps (stable seed, or the few slots past the last seed column) run the same straight-line
+    // code on an empty window instead of branching around it: the shuffles / REDUX below then sit in
+    // convergent code and compile to single instructions.
+    int ndt = 0;
     {
         const size_t fo = (size_t)b * d.px_stride;
         const int32_t *lab = d.labels + fo; // per-frame bases once; 32-bit element offsets below
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
         const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
         const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
         const int xq = x0 + 4 * (lane & 3);
-        const bool colin = xq >= 0 && xq < Wp;
+        const bool colin = live && xq >= 0 && xq < Wp;
         int4 l4[2];
         float4 z4[2];
         uchar4 g4[2];
@@ -454,8 +457,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
             if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
         }
         unsigned mdm = 0; // bit 4*ps+k: member with depth > 0.1
-        int cnt2 = 0;     // member count, pass 0 in the low half-word, pass 1 in the high one
-        int sumx = 0, sumy = 0, sumi = 0;
+        int cnt2 = 0, sumx = 0, sumy = 0, sumi = 0;
 #pragma unroll
         for (int ps = 0; ps < 2; ps++)
         {
@@ -476,15 +478,16 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
             cnt2 += c;
             sumy += c * yy[ps];
         }
-        const int cnt = __reduce_add_sync(FULL, cnt2);
+        // count (<= 225) and intensity sum (<= 57375) share one REDUX
+        const int ci = __reduce_add_sync(FULL, cnt2 | (sumi << 8));
         const int tsx = __reduce_add_sync(FULL, sumx);
         const int tsy = __reduce_add_sync(FULL, sumy);
-        const int tsi = __reduce_add_sync(FULL, sumi);
         // one scan for both passes: pass-0 count in the low half-word, pass-1 count in the high one
         const int c2 = __popc(mdm & 0xfu) | (__popc(mdm >> 4) << 16);
         int tot2;
         const int ex2 = warp_excl_scan(c2, lane, tot2);
-        const int n0 = tot2 & 0xffff, ndt = n0 + (tot2 >> 16);
+        const int n0 = tot2 & 0xffff;
+        ndt = n0 + (tot2 >> 16);
         const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
         unsigned a0 = tbase + 32u * (ex2 & 0xffff), a1 = tbase + 32u * (n0 + (ex2 >> 16)); // 32 bytes per list row
         const float za[4] = {z4[0].x, z4[0].y, z4[0].z, z4[0].w}, zb[4] = {z4[1].x, z4[1].y, z4[1].z, z4[1].w};
@@ -502,20 +505,23 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
                 a1 += 32u;
             }
         }
-        if (lane == 0)
+        if (live && lane == 0)
         {
-            d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
+            d.usum[so + s] = make_int4(ci & 0xff, tsx, tsy, ci >> 8);
             d.und[so + s] = ndt;
             atomicMax(&s_rows, ndt);
         }
     }
     __syncthreads();
+    // copy-out: thread t moves column (t & 7) of rows t>>3, t>>3 + 32, ...: 32-byte sectors, 32-bit indexing
     const int rows = s_rows;
-    const int c = threadIdx.x & 7;
-    if (blockIdx.x * 8 + c < d.spw)
+    const unsigned c = threadIdx.x & 7u;
+    if (blockIdx.x * 8 + c < (unsigned)d.spw)
     {
-        float *dst = d.dlist + (size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c;
-        for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp] = tile[r * 8 + c];
+        float *dst = d.dlist + ((size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c);
+        const unsigned sp = (unsigned)d.Sp;
+#pragma unroll 1
+        for (unsigned r = threadIdx.x >> 3; r < (unsigned)rows; r += 32u) dst[r * sp] = tile[r * 8u + c];
     }
 }
 
@@ -740,16 +746,18 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
     __syncthreads();
     const int W = d.W, H = d.H, Wp = d.Wp;
     const size_t so = (size_t)b * d.S;
-    if (sp_x < d.spw) // warp-uniform
+    const bool live = sp_x < d.spw;
+    // Slots past the last seed column run the same straight-line code on an empty window: every shuffle
+    // below sits in convergent code (a shuffle inside a possibly-divergent branch costs ~10 instructions).
     {
         const size_t fo = (size_t)b * d.px_stride;
         const int32_t *lab = d.labels + fo; // per-frame bases once; 32-bit element offsets below
         const float *dep = d.depth + fo;
         const float *nrx = d.nrm + fo, *nry = nrx + d.nrm_plane, *nrz = nry + d.nrm_plane;
-        const float4 sd = d.seed[so + s]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
+        const float4 sd = d.seed[so + (live ? s : 0)]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
         const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
         const int xq = x0 + 4 * (lane & 3);
-        const bool colin = xq >= 0 && xq < Wp;
+        const bool colin = live && xq >= 0 && xq < Wp;
         const float4 k4 = *reinterpret_cast<const float4 *>(d.kx + (colin ? xq : 0));
         const float kxv[4] = {k4.x, k4.y, k4.z, k4.w};
         int4 l4[2];
@@ -813,17 +821,18 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
         }
         maxd = warp_max_f(maxd);
         nvalid = __reduce_add_sync(FULL, nvalid);
+        snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
+        spx = warp_sum_f(spx), spy = warp_sum_f(spy), spz = warp_sum_f(spz);
         const int c2 = __popc(inl & 0xfu) | (__popc(inl >> 4) << 16);
         int tot2;
         const int ex2 = warp_excl_scan(c2, lane, tot2);
         const int n0 = tot2 & 0xffff, ninl = n0 + (tot2 >> 16);
-        const bool ok = nvalid >= 16 && !((float)ninl / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
+        const bool ok = live && nvalid >= 16 && !((float)ninl / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
         float4 P0 = make_float4(0.f, 0.f, 0.f, maxd), P1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
         if (ok)
         {
-            snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
             const float fn = (float)ninl;
-            const float mxs = warp_sum_f(spx) / fn, mys = warp_sum_f(spy) / fn, mzs = warp_sum_f(spz) / fn; // (:117-119)
+            const float mxs = spx / fn, mys = spy / fn, mzs = spz / fn; // (:117-119)
             const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
 #pragma unroll
             for (int ps = 0; ps < 2; ps++)
@@ -844,7 +853,7 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
             P1 = make_float4(mxs, mys, mzs, __int_as_float(ninl));
             if (lane == 0) atomicMax(&s_rows, ninl);
         }
-        if (lane == 0)
+        if (live && lane == 0)
         {
             d.pfsum[(so + s) * 2] = P0;
             d.pfsum[(so + s) * 2 + 1] = P1;
@@ -852,17 +861,20 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
     }
     __syncthreads();
     const int rows = s_rows;
-    const int c = threadIdx.x & 7;
-    if (blockIdx.x * 8 + c < d.spw)
+    const unsigned c = threadIdx.x & 7u;
+    if (blockIdx.x * 8 + c < (unsigned)d.spw)
     {
         const size_t plane = (size_t)d.B * PF_CAP * d.Sp;
-        float *dst = d.qlist + (size_t)b * PF_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c;
-        for (int r = threadIdx.x >> 3; r < rows; r += 32)
+        float *dx = d.qlist + ((size_t)b * PF_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c);
+        float *dy = dx + plane, *dz = dy + plane;
+        const unsigned sp = (unsigned)d.Sp;
+#pragma unroll 1
+        for (unsigned r = threadIdx.x >> 3; r < (unsigned)rows; r += 32u)
         {
-            const size_t o = (size_t)r * d.Sp;
-            dst[o] = tile[r * 8 + c];
-            dst[plane + o] = tile[PF_CAP * 8 + r * 8 + c];
-            dst[2 * plane + o] = tile[2 * PF_CAP * 8 + r * 8 + c];
+            const unsigned t = r * 8u + c, o = r * sp;
+            dx[o] = tile[t];
+            dy[o] = tile[PF_CAP * 8 + t];
+            dz[o] = tile[2 * PF_CAP * 8 + t];
         }
     }
 }
