@@ -211,7 +211,7 @@ __device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pi
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(256, 5) k_assign(const __grid_constant__ DsmDev d)
 {
     const int b = d.frame0 + blockIdx.z;
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     {
         float *dst = d.dlist + ((size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c);
         const unsigned sp = (unsigned)d.Sp;
-#pragma unroll 1
+#pragma unroll 4
         for (unsigned r = threadIdx.x >> 3; r < (unsigned)rows; r += 32u) dst[r * sp] = tile[r * 8u + c];
     }
 }
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
         float *dx = d.qlist + ((size_t)b * PF_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c);
         float *dy = dx + plane, *dz = dy + plane;
         const unsigned sp = (unsigned)d.Sp;
-#pragma unroll 1
+#pragma unroll 2
         for (unsigned r = threadIdx.x >> 3; r < (unsigned)rows; r += 32u)
         {
             const unsigned t = r * 8u + c, o = r * sp;
