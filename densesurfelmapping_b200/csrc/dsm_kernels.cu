@@ -211,7 +211,7 @@ __device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pi
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(256, 5) k_assign(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDev d)
 {
     const int b = d.frame0 + blockIdx.z;
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
@@ -425,10 +425,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     const int W = d.W, H = d.H, Wp = d.Wp;
     const size_t so = (size_t)b * d.S;
     const bool live = sp_x < d.spw && d.tstable[so + (sp_x < d.spw ? s : 0)] != DSM_STABLE; // stable seeds are skipped (:478-479)
-    // Non-live warps (stable seed, or the few slots past the last seed column) run the same straight-line
-    // code on an empty window instead of branching around it: the shuffles / REDUX below then sit in
-    // convergent code and compile to single instructions.
-    int ndt = 0;
+    if (live) // warp-uniform
     {
         const size_t fo = (size_t)b * d.px_stride;
         const int32_t *lab = d.labels + fo; // per-frame bases once; 32-bit element offsets below
@@ -439,7 +436,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
         const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
         const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
         const int xq = x0 + 4 * (lane & 3);
-        const bool colin = live && xq >= 0 && xq < Wp;
+        const bool colin = xq >= 0 && xq < Wp;
         int4 l4[2];
         float4 z4[2];
         uchar4 g4[2];
@@ -457,7 +454,8 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
             if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
         }
         unsigned mdm = 0; // bit 4*ps+k: member with depth > 0.1
-        int cnt2 = 0, sumx = 0, sumy = 0, sumi = 0;
+        int cnt2 = 0;     // member count, pass 0 in the low half-word, pass 1 in the high one
+        int sumx = 0, sumy = 0, sumi = 0;
 #pragma unroll
         for (int ps = 0; ps < 2; ps++)
         {
@@ -478,16 +476,15 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
             cnt2 += c;
             sumy += c * yy[ps];
         }
-        // count (<= 225) and intensity sum (<= 57375) share one REDUX
-        const int ci = __reduce_add_sync(FULL, cnt2 | (sumi << 8));
+        const int cnt = __reduce_add_sync(FULL, cnt2);
         const int tsx = __reduce_add_sync(FULL, sumx);
         const int tsy = __reduce_add_sync(FULL, sumy);
+        const int tsi = __reduce_add_sync(FULL, sumi);
         // one scan for both passes: pass-0 count in the low half-word, pass-1 count in the high one
         const int c2 = __popc(mdm & 0xfu) | (__popc(mdm >> 4) << 16);
         int tot2;
         const int ex2 = warp_excl_scan(c2, lane, tot2);
-        const int n0 = tot2 & 0xffff;
-        ndt = n0 + (tot2 >> 16);
+        const int n0 = tot2 & 0xffff, ndt = n0 + (tot2 >> 16);
         const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
         unsigned a0 = tbase + 32u * (ex2 & 0xffff), a1 = tbase + 32u * (n0 + (ex2 >> 16)); // 32 bytes per list row
         const float za[4] = {z4[0].x, z4[0].y, z4[0].z, z4[0].w}, zb[4] = {z4[1].x, z4[1].y, z4[1].z, z4[1].w};
@@ -505,23 +502,20 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
                 a1 += 32u;
             }
         }
-        if (live && lane == 0)
+        if (lane == 0)
         {
-            d.usum[so + s] = make_int4(ci & 0xff, tsx, tsy, ci >> 8);
+            d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
             d.und[so + s] = ndt;
             atomicMax(&s_rows, ndt);
         }
     }
     __syncthreads();
-    // copy-out: thread t moves column (t & 7) of rows t>>3, t>>3 + 32, ...: 32-byte sectors, 32-bit indexing
     const int rows = s_rows;
-    const unsigned c = threadIdx.x & 7u;
-    if (blockIdx.x * 8 + c < (unsigned)d.spw)
+    const int c = threadIdx.x & 7;
+    if (blockIdx.x * 8 + c < d.spw)
     {
-        float *dst = d.dlist + ((size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c);
-        const unsigned sp = (unsigned)d.Sp;
-#pragma unroll 4
-        for (unsigned r = threadIdx.x >> 3; r < (unsigned)rows; r += 32u) dst[r * sp] = tile[r * 8u + c];
+        float *dst = d.dlist + (size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c;
+        for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp] = tile[r * 8 + c];
     }
 }
 
