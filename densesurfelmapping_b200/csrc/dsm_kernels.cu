@@ -424,8 +424,11 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
     __syncthreads();
     const int W = d.W, H = d.H, Wp = d.Wp;
     const size_t so = (size_t)b * d.S;
-    const bool live = sp_x < d.spw && d.tstable[so + (sp_x < d.spw ? s : 0)] != DSM_STABLE; // stable seeds are skipped (:478-479)
-    if (live) // warp-uniform
+    // The stable flag is fetched together with the window (not before it): one memory round trip per block
+    // instead of two; the few stable seeds just discard what was loaded (:478-479).
+    const bool inside = sp_x < d.spw;
+    const int tflag = d.tstable[so + (inside ? s : 0)];
+    if (inside) // warp-uniform
     {
         const size_t fo = (size_t)b * d.px_stride;
         const int32_t *lab = d.labels + fo; // per-frame bases once; 32-bit element offsets below
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
             l4[ps] = *reinterpret_cast<const int4 *>(lab + po); // out-of-window lanes read element 0 and are masked below
             z4[ps] = *reinterpret_cast<const float4 *>(dep + po);
             g4[ps] = *reinterpret_cast<const uchar4 *>(gry + po);
-            if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
+            if (!in || tflag == DSM_STABLE) l4[ps] = make_int4(-1, -1, -1, -1);
         }
         unsigned mdm = 0; // bit 4*ps+k: member with depth > 0.1
         int cnt2 = 0;     // member count, pass 0 in the low half-word, pass 1 in the high one
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(256) k_gather_depths(const __grid_constant__ D
                 a1 += 32u;
             }
         }
-        if (lane == 0)
+        if (lane == 0 && tflag != DSM_STABLE)
         {
             d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
             d.und[so + s] = ndt;
