@@ -123,6 +123,11 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    // an asynchronous batch may still be in flight on any of the context's streams
+    if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+    for (int i = 0; i < 4; i++)
+        if (ctx->s_comp[i]) cudaStreamSynchronize(ctx->s_comp[i]);
+    if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &r : ctx->prof_pending)
     {

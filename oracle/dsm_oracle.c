@@ -231,6 +231,10 @@ static void update_pixels(ctx_t *c)
                     }
                 }
             int w = all_has_depth ? idx_d : idx_nd;
+            /* Outside the supported input domain (valid depth < ~0.02 m) every candidate cost can exceed the
+             * 1e6 start value and w stays -1: the reference then indexes superpixel_seeds[-1] (undefined).
+             * The restatement stays memory-safe and labels such a pixel 0, like the CUDA path. */
+            if (w < 0) w = 0;
             c->labels[row * W + col] = w;
             c->seeds[w].stable = 0;
         }
