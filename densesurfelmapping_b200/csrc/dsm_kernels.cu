@@ -223,7 +223,6 @@ __global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDe
     const size_t so = (size_t)b * d.S;
     int win[4] = {-1, -1, -1, -1};
     int L[4] = {0, 0, 0, 0};
-    int TS[4] = {-1, -1, -1, -1};
     if (active)
     {
         const size_t po = fo + (size_t)y * d.Wp + x4;
@@ -233,10 +232,6 @@ __global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDe
         {
             const int4 l4 = *reinterpret_cast<const int4 *>(d.labels + po);
             L[0] = l4.x, L[1] = l4.y, L[2] = l4.z, L[3] = l4.w;
-            // the owners' stable stamps are requested now so that their latency hides under the cost evaluation
-            // (only the SIGN is used, and that never changes during this pass: see the header comment)
-#pragma unroll
-            for (int i = 0; i < 4; i++) TS[i] = d.tstable[so + L[i]];
         }
         const float gi[4] = {(float)g4.x, (float)g4.y, (float)g4.z, (float)g4.w};
         const float zi[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -317,7 +312,7 @@ __global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDe
         {
             if (x4 + i >= d.W || win[i] < 0) continue;
             const int pidx = y * d.Wp + x4 + i;
-            const int ts = TS[i];
+            const int ts = d.tstable[so + L[i]];
             if (ts < 0)
             { // owner unstable since the start of the pass: the reference evaluates this pixel
                 if (win[i] != L[i])
@@ -763,7 +758,7 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
         const float4 k4 = *reinterpret_cast<const float4 *>(d.kx + (colin ? xq : 0));
         const float kxv[4] = {k4.x, k4.y, k4.z, k4.w};
         int4 l4[2];
-        float4 z4[2], na[2], nbv[2], ncv[2];
+        float4 z4[2];
         float kyv[2];
         int yy[2];
         unsigned pof[2];
@@ -777,11 +772,6 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
             pof[ps] = po;
             l4[ps] = *reinterpret_cast<const int4 *>(lab + po); // out-of-window lanes read element 0 and are masked below
             z4[ps] = *reinterpret_cast<const float4 *>(dep + po);
-            // the pixel normals are requested with the labels (not after the member test): one memory round
-            // trip per window instead of two
-            na[ps] = *reinterpret_cast<const float4 *>(nrx + po);
-            nbv[ps] = *reinterpret_cast<const float4 *>(nry + po);
-            ncv[ps] = *reinterpret_cast<const float4 *>(nrz + po);
             kyv[ps] = d.ky[in ? y : 0];
             if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
         }
@@ -816,7 +806,9 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
             }
             if (mi)
             { // pixel normals of this 4-pixel group: three 16-byte loads instead of up to 12 scalar ones
-                const float4 a = na[ps], bb = nbv[ps], c = ncv[ps];
+                const float4 a = *reinterpret_cast<const float4 *>(nrx + pof[ps]);
+                const float4 bb = *reinterpret_cast<const float4 *>(nry + pof[ps]);
+                const float4 c = *reinterpret_cast<const float4 *>(nrz + pof[ps]);
                 const float ax[4] = {a.x, a.y, a.z, a.w}, ay[4] = {bb.x, bb.y, bb.z, bb.w}, az[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
