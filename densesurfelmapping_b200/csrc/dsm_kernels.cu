@@ -12,6 +12,8 @@
 // ":NNN" refer to /root/reference/surfel_fusion/src/fusion_functions.cpp.
 #include "dsm_device.cuh"
 #include <climits>
+#include <cuda/barrier>
+#include <cuda/ptx>
 
 #define HUBER_RANGE 0.4       // fusion_functions.h:13
 #define MAX_ANGLE_COS 0.1     // fusion_functions.h:11
@@ -1175,6 +1177,62 @@ __global__ void __launch_bounds__(128) k_gauss_newton_small(const __grid_constan
 }
 
 // -------------------------------------------------------------------------------------------
+// Staging of a contiguous run of 44-byte surfel records through shared memory for the streaming pool
+// kernels (k_fuse, k_pool_transform).  When the run is 16-byte aligned and a multiple of 16 bytes it
+// moves as ONE TMA 1-D bulk copy each way (cp.async.bulk: UBLKCP in SASS, completion on an mbarrier for
+// the load, a bulk async-group for the store) issued by a single thread -- no per-thread address math,
+// no register staging; otherwise (unaligned slice start, ragged tail) coalesced 4-byte accesses.
+// -------------------------------------------------------------------------------------------
+using dsm_barrier = cuda::barrier<cuda::thread_scope_block>;
+
+__device__ __forceinline__ bool stage_in(float *sm, const float *g, int cnt, dsm_barrier *bar, int nthreads)
+{
+    const unsigned bytes = (unsigned)cnt * 44u;
+    const bool bulk = (bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0u);
+    if (bulk)
+    {
+        if (threadIdx.x == 0)
+        {
+            init(bar, 1);
+            cuda::ptx::fence_proxy_async(cuda::ptx::space_shared); // make the initialised barrier visible to the async proxy
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            cuda::device::memcpy_async_tx(sm, g, cuda::aligned_size_t<16>(bytes), *bar);
+            (void)cuda::device::barrier_arrive_tx(*bar, 1, bytes);
+        }
+        while (!cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(*bar), 0)) {}
+    }
+    else
+    {
+        for (int i = threadIdx.x; i < cnt * 11; i += nthreads) sm[i] = g[i];
+        __syncthreads();
+    }
+    return bulk;
+}
+
+__device__ __forceinline__ void stage_out(float *g, const float *sm, int cnt, bool bulk, int nthreads)
+{
+    if (bulk)
+    {
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared); // this thread's smem writes -> async proxy
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            cuda::ptx::cp_async_bulk(cuda::ptx::space_global, cuda::ptx::space_shared, g, sm, (unsigned)cnt * 44u);
+            cuda::ptx::cp_async_bulk_commit_group();
+            cuda::ptx::cp_async_bulk_wait_group_read(cuda::ptx::n32_t<0>()); // smem must stay alive until it has been read
+        }
+    }
+    else
+    {
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 11; i += nthreads) g[i] = sm[i];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // K5  surfel_fuse — fuse_surfels_kernel (:190-313).  Pure map over the frame's pool slice.
 // The AoS pool (44 B/element, ABI layout) is staged through shared memory with fully coalesced
 // 4-byte accesses; each thread then works on its element at stride 11 words (conflict-free).
@@ -1198,18 +1256,20 @@ __device__ __forceinline__ float get_weight(float depth)
 #define FUSE_BLOCK 256
 __global__ void __launch_bounds__(FUSE_BLOCK) k_fuse(const __grid_constant__ DsmDev d)
 {
-    __shared__ float sm[FUSE_BLOCK * 11];
+    __shared__ alignas(128) float sm[FUSE_BLOCK * 11];
     __shared__ float s_pose[32];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ dsm_barrier bar;
     const int b = d.frame0 + blockIdx.y;
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
     const int first = begin + blockIdx.x * FUSE_BLOCK;
     if (first >= end) return;
     const int cnt = min(FUSE_BLOCK, end - first);
     float *g = reinterpret_cast<float *>(d.pool + first);
-    for (int i = threadIdx.x; i < cnt * 11; i += FUSE_BLOCK) sm[i] = g[i];
     if (threadIdx.x < 16) s_pose[threadIdx.x] = d.pose[b * 16 + threadIdx.x];
     else if (threadIdx.x < 32) s_pose[threadIdx.x] = d.ipose[b * 16 + threadIdx.x - 16];
-    __syncthreads();
+    const bool bulk = stage_in(sm, g, cnt, &bar, FUSE_BLOCK);
+    __syncthreads(); // s_pose
     if (threadIdx.x < cnt)
     {
         float *e = sm + threadIdx.x * 11;
@@ -1286,8 +1346,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK) k_fuse(const __grid_constant__ Dsm
             d.fused[so + sp] = 1; // idempotent multi-writer store (:311)
         } while (0);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < cnt * 11; i += FUSE_BLOCK) g[i] = sm[i];
+    stage_out(g, sm, cnt, bulk, FUSE_BLOCK);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1467,16 +1526,18 @@ __global__ void __launch_bounds__(256) k_pool_append(const __grid_constant__ Dsm
 #define XF_BLOCK 256
 __global__ void __launch_bounds__(XF_BLOCK) k_pool_transform(const __grid_constant__ DsmDev d, int b, const float *Wm)
 {
-    __shared__ float sm[XF_BLOCK * 11];
+    __shared__ alignas(128) float sm[XF_BLOCK * 11];
     __shared__ float s_w[16];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ dsm_barrier bar;
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
     const int first = begin + blockIdx.x * XF_BLOCK;
     if (first >= end) return;
     const int cnt = min(XF_BLOCK, end - first);
     float *g = reinterpret_cast<float *>(d.pool + first);
-    for (int i = threadIdx.x; i < cnt * 11; i += XF_BLOCK) sm[i] = g[i];
     if (threadIdx.x < 16) s_w[threadIdx.x] = Wm[threadIdx.x];
-    __syncthreads();
+    const bool bulk = stage_in(sm, g, cnt, &bar, XF_BLOCK);
+    __syncthreads(); // s_w
     if (threadIdx.x < cnt)
     {
         float *e = sm + threadIdx.x * 11;
@@ -1486,8 +1547,7 @@ __global__ void __launch_bounds__(XF_BLOCK) k_pool_transform(const __grid_consta
         e[0] = pw[0], e[1] = pw[1], e[2] = pw[2];
         e[3] = nw[0], e[4] = nw[1], e[5] = nw[2];
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < cnt * 11; i += XF_BLOCK) g[i] = sm[i];
+    stage_out(g, sm, cnt, bulk, XF_BLOCK);
 }
 
 // -------------------------------------------------------------------------------------------
