@@ -141,3 +141,23 @@ def test_quirks_documented_in_survey_appendix_a():
     lib.dsmor_create.restype = ctypes.c_void_p
     lib.dsmor_create.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_float] * 6
     assert lib.dsmor_create(645, 480, 1.0, 1.0, 1.0, 1.0, 30.0, 0.5) is None
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref/libdsm_ref_serial.so not built")
+@pytest.mark.parametrize("w,h", [(64, 48), (97, 66), (130, 83), (244, 100), (160, 124)])
+def test_restatement_equals_reference_serial_on_odd_shapes(w, h):
+    """Every supported remainder combination (W%8, H%8 in 0..4), tiny frames, a carried pool and a
+    reference-index jump (kills unstable surfels): restatement == serialised reference, byte for byte."""
+    cam = synth.Camera(w, h, 0.8 * w, 0.8 * w, (w - 1) / 2.0, (h - 1) / 2.0, 0.5, 30.0)
+    rs, ro = pyoracle.RefSerial(cam), pyoracle.Restatement(cam)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    for t, ref in enumerate([0, 1, 9]):
+        pose = synth.pose_stream(t)
+        g, d = synth.make_frame(cam, 900 + t, pose, flat=(t == 1))
+        lr, nr = rs.fuse(ref, g, d, pose, pool)
+        lo, no = ro.fuse(ref, g, d, pose, pool)
+        assert (rs.labels() == ro.labels()).all()
+        assert_records_equal(ro.seeds(), rs.seeds(), "seeds")
+        assert_records_equal(lo, lr, "local")
+        assert_records_equal(no, nr, "new")
+        pool = np.concatenate([lr[lr["update_times"] > 0] if len(lr) else lr, nr])
