@@ -246,3 +246,34 @@ def test_async_batch_double_buffering(capi):
             assert cnt[b] == len(want_new[b]) and new[b, :cnt[b]].tobytes() == want_new[b].tobytes()
     for c in ctxs:
         c.close()
+
+
+def test_random_small_images(capi):
+    """40 random 64x48 frames inside the input domain (noise, salt-and-pepper, ramps, holes, exact depth
+    ties): labels bit-exact, clustering state bit-exact, plane fits within tolerance."""
+    cam = synth.Camera(64, 48, 60.0, 60.0, 31.5, 23.5, 0.5, 30.0)
+    orc = oracle_for(cam)
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=64)
+    yy, xx = np.mgrid[0:48, 0:64]
+    pose = synth.identity_pose()
+    for seed in range(40):
+        rng = np.random.RandomState(seed)
+        mode = seed % 3
+        if mode == 0:
+            gray = rng.randint(0, 256, (48, 64)).astype(np.uint8)
+        elif mode == 1:
+            gray = (rng.randint(0, 2, (48, 64)) * 255).astype(np.uint8)
+        else:
+            gray = ((xx * 3 + yy * 2 + rng.randint(0, 4, (48, 64))) % 256).astype(np.uint8)
+        depth = rng.uniform(0.02, 25.0, (48, 64)).astype(np.float32)
+        if seed % 2:
+            depth[rng.rand(48, 64) < 0.4] = 0
+        if seed % 5 == 0:
+            depth = np.round(depth)
+        _, no = orc.fuse(0, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+        _, ng = ctx.fuse_frame(0, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+        nbad = int((orc.labels() != ctx.labels()).sum())
+        assert nbad == 0, f"image {seed}: {nbad} label mismatches"
+        check_seeds(ctx.seeds(), orc.seeds())
+        check_surfels(ng, no, f"image {seed} new")
+    ctx.close()

@@ -68,7 +68,8 @@ def test_golden_vga_two_pass():
         assert (loc1["update_times"] == 2).sum() > 1000  # the pure-fuse pass really fused
 
 
-@pytest.mark.parametrize("key,camname,flat", [("kitti", "kitti", False), ("kitti_flat", "kitti", True), ("vga_flat", "vga", True)])
+@pytest.mark.parametrize("key,camname,flat", [("kitti", "kitti", False), ("kitti_flat", "kitti", True), ("vga_flat", "vga", True),
+                                              ("hd", "hd", False)])
 def test_golden_stream_checksums(key, camname, flat):
     """Larger frames: CRC32 of labels / seeds / surfels over a short stream with a carried pool."""
     sums = json.load(open(os.path.join(GOLD, "checksums.json")))[key]
@@ -161,3 +162,30 @@ def test_restatement_equals_reference_serial_on_odd_shapes(w, h):
         assert_records_equal(lo, lr, "local")
         assert_records_equal(no, nr, "new")
         pool = np.concatenate([lr[lr["update_times"] > 0] if len(lr) else lr, nr])
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref/libdsm_ref_serial.so not built")
+def test_restatement_equals_reference_serial_on_random_images():
+    """60 random 64x48 frames inside the input domain (depth 0 or >= 0.02 m): uniform noise, binary
+    salt-and-pepper, smooth ramps, with and without holes -- labels and seeds byte-identical."""
+    cam = synth.Camera(64, 48, 60.0, 60.0, 31.5, 23.5, 0.5, 30.0)
+    rs, ro = pyoracle.RefSerial(cam), pyoracle.Restatement(cam)
+    yy, xx = np.mgrid[0:48, 0:64]
+    for seed in range(60):
+        rng = np.random.RandomState(seed)
+        mode = seed % 3
+        if mode == 0:
+            gray = rng.randint(0, 256, (48, 64)).astype(np.uint8)
+        elif mode == 1:
+            gray = (rng.randint(0, 2, (48, 64)) * 255).astype(np.uint8)
+        else:
+            gray = ((xx * 3 + yy * 2 + rng.randint(0, 4, (48, 64))) % 256).astype(np.uint8)
+        depth = rng.uniform(0.02, 25.0, (48, 64)).astype(np.float32)
+        if seed % 2:
+            depth[rng.rand(48, 64) < 0.4] = 0
+        if seed % 5 == 0:
+            depth = np.round(depth)  # many exact ties
+        lab_r, seeds_r = rs.superpixels(gray, depth)
+        lab_o, seeds_o = ro.superpixels(gray, depth)
+        assert (lab_r == lab_o).all(), seed
+        assert_records_equal(seeds_o, seeds_r, f"seeds (image {seed})")
