@@ -9,14 +9,14 @@ import ctypes
 import os
 import numpy as np
 
-from .elements import SEED_DTYPE, SURFEL_DTYPE, num_seeds
+from .elements import POINT_DTYPE, SEED_DTYPE, SURFEL_DTYPE, num_seeds
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdsm_b200.so")
 
 DSM_OK = 0
 ERRORS = {-1: "DSM_E_INVALID", -2: "DSM_E_SHAPE", -3: "DSM_E_NODEVICE", -4: "DSM_E_CUDA",
-          -5: "DSM_E_NOMEM", -6: "DSM_E_CAPACITY", -7: "DSM_E_STATE", -8: "DSM_E_NCCL"}
+          -5: "DSM_E_NOMEM", -6: "DSM_E_CAPACITY", -7: "DSM_E_STATE", -8: "DSM_E_NCCL", -9: "DSM_E_IO"}
 NUM_KERNELS = 12
 
 # every symbol include/dsm.h declares (tests/test_abi.py checks the library exports all of them)
@@ -26,6 +26,7 @@ EXPORTS = [
     "dsm_fuse_batch", "dsm_fuse_batch_async", "dsm_batch_wait", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
     "dsm_pool_transform", "dsm_pool_retire", "dsm_pool_append", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
+    "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices",
 ]
 
 
@@ -90,6 +91,11 @@ def load_library():
     L.dsm_profile_reset.argtypes = [vp]
     L.dsm_profile_read.argtypes = [vp, vp, vp]
     L.dsm_device_buffer.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cs)]
+    L.dsm_pool_export_cloud.argtypes = [vp, ci, vp, ci, ctypes.POINTER(ci)]
+    L.dsm_pool_export_surfels.argtypes = [vp, ci, vp, ci, ctypes.POINTER(ci)]
+    L.dsm_write_pcd.argtypes = [ctypes.c_char_p, vp, cs, ci]
+    L.dsm_write_ply_mesh.argtypes = [ctypes.c_char_p, vp, cs]
+    L.dsm_mesh_vertices.argtypes = [vp, cs, vp]
     _lib = L
     return L
 
@@ -222,6 +228,20 @@ class Context:
         self._ck(self.lib.dsm_pool_download(self.h, _ptr(out) if n else None, n, ctypes.byref(c)))
         return out[:c.value]
 
+    def pool_export_cloud(self, min_update_times=5, cap=None):
+        """publish_active_pointcloud & co. (surfel_map.cpp:1398-1417): POINT_DTYPE array in pool order."""
+        return self._pool_export(self.lib.dsm_pool_export_cloud, POINT_DTYPE, min_update_times, cap)
+
+    def pool_export_surfels(self, min_update_times=5, cap=None):
+        return self._pool_export(self.lib.dsm_pool_export_surfels, SURFEL_DTYPE, min_update_times, cap)
+
+    def _pool_export(self, fn, dtype, min_update_times, cap):
+        cap = self.pool_size() if cap is None else cap
+        out = np.zeros(max(cap, 1), dtype=dtype)
+        n = ctypes.c_int(0)
+        self._ck(fn(self.h, int(min_update_times), _ptr(out), cap, ctypes.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
     # ---- parity readback ----
     def labels(self, frame=0):
         out = np.empty((self.cam.height, self.cam.width), dtype=np.int32)
@@ -281,3 +301,29 @@ class FusionFunctions:
         if self._ctx is None:
             raise RuntimeError("initialize() has not been called")
         return self._ctx.fuse_frame(reference_frame_index, image, depth, pose, local_surfels)
+
+
+# ---- output files (host only; no context, no GPU) ----
+def _ck_io(rc, path):
+    if rc != DSM_OK:
+        raise DsmError(rc, f"{load_library().dsm_strerror(rc).decode()}: {path}")
+
+
+def write_pcd(path, points, binary=False):
+    """SurfelMap::save_cloud's file (surfel_map.cpp:1171): PCD v0.7 with fields x y z intensity."""
+    points = np.ascontiguousarray(points, dtype=POINT_DTYPE)
+    _ck_io(load_library().dsm_write_pcd(os.fsencode(path), _ptr(points) if len(points) else None, len(points), int(binary)), path)
+
+
+def write_ply_mesh(path, surfels):
+    """SurfelMap::save_mesh (surfel_map.cpp:1229-1280): one hexagon per surfel, ASCII PLY."""
+    surfels = np.ascontiguousarray(surfels, dtype=SURFEL_DTYPE)
+    _ck_io(load_library().dsm_write_ply_mesh(os.fsencode(path), _ptr(surfels) if len(surfels) else None, len(surfels)), path)
+
+
+def mesh_vertices(surfels):
+    """push_a_surfel (surfel_map.cpp:1175-1226): float32 [n, 6, 6] = 6 vertices x (x, y, z, c, c, c)."""
+    surfels = np.ascontiguousarray(surfels, dtype=SURFEL_DTYPE)
+    out = np.zeros((len(surfels), 6, 6), dtype=np.float32)
+    _ck_io(load_library().dsm_mesh_vertices(_ptr(surfels) if len(surfels) else None, len(surfels), _ptr(out) if len(surfels) else None), "")
+    return out

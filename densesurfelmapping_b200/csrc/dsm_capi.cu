@@ -103,6 +103,7 @@ extern "C" const char *dsm_strerror(int code)
     case DSM_E_CAPACITY: return "surfel capacity exceeded";
     case DSM_E_STATE: return "invalid call sequence";
     case DSM_E_NCCL: return "NCCL error";
+    case DSM_E_IO: return "file could not be opened or written";
     default: return "unknown error";
     }
 }
@@ -909,6 +910,38 @@ extern "C" int dsm_pool_retire(dsm_ctx *ctx, int kf, dsm_surfel_t *out, int cap,
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return DSM_OK;
+}
+
+// publish_*_pointcloud / save_cloud / save_mesh filters on the resident pool (see include/dsm.h)
+static int pool_export(dsm_ctx *ctx, int min_ut, bool as_cloud, void *out, int cap, int *n_out)
+{
+    if (!ctx || !n_out || cap < 0 || (cap > 0 && !out)) return DSM_E_INVALID;
+    if (!ctx->res_active) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    // the alternate pool buffer is free between frames: ordered output (16 or 44 bytes per selected surfel)
+    dsm_launch_pool_export(resident_view(ctx, 0), 0, ctx->res_upper, 2, min_ut, as_cloud, ctx->blkcnt, ctx->blkofs, ctx->newofs,
+                           ctx->pool_snap, ctx->stream);
+    int32_t h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->newofs, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    *n_out = h[0];
+    const int c = h[0] < cap ? h[0] : cap;
+    if (c > 0)
+    {
+        const size_t rec = as_cloud ? sizeof(dsm_point_t) : sizeof(dsm_surfel_t);
+        CK(cudaMemcpyAsync(out, ctx->pool_snap, (size_t)c * rec, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return DSM_OK;
+}
+extern "C" int dsm_pool_export_cloud(dsm_ctx *ctx, int min_update_times, dsm_point_t *out, int cap, int *n_out)
+{
+    return pool_export(ctx, min_update_times, true, out, cap, n_out);
+}
+extern "C" int dsm_pool_export_surfels(dsm_ctx *ctx, int min_update_times, dsm_surfel_t *out, int cap, int *n_out)
+{
+    return pool_export(ctx, min_update_times, false, out, cap, n_out);
 }
 
 extern "C" int dsm_pool_append(dsm_ctx *ctx, const dsm_surfel_t *surfels, int n)

@@ -1441,9 +1441,11 @@ __global__ void __launch_bounds__(1024) k_init_surfels(const __grid_constant__ D
 //   staged through shared memory like k_fuse.
 // -------------------------------------------------------------------------------------------
 // selection predicate of the pool kernels: mode 0 = live surfels (update_times != 0, fuse_map post-step);
-// mode 1 = live surfels last updated by keyframe `key` (move_add_surfels, surfel_map.cpp:1479-1497)
+// mode 1 = live surfels last updated by keyframe `key` (move_add_surfels, surfel_map.cpp:1479-1497);
+// mode 2 = surfels with update_times >= key (the publish/save filters, surfel_map.cpp:1158, :1243, :1406, :1429)
 __device__ __forceinline__ bool pool_pred(const dsm_surfel_t &e, int mode, int key)
 {
+    if (mode == 2) return e.update_times >= key;
     return mode == 0 ? (e.update_times != 0) : (e.update_times > 0 && e.last_update == key);
 }
 
@@ -1514,6 +1516,33 @@ __global__ void __launch_bounds__(256) k_pool_scatter(const __grid_constant__ Ds
     int wofs = 0;
     for (int w = 0; w < warp; w++) wofs += s_warp[w];
     if (live) dst[blkofs[blockIdx.x] + wofs + __popc(bal & ((1u << lane) - 1))] = e;
+}
+
+// k_pool_scatter_cloud — the point-cloud builders of SurfelMap (publish_active_pointcloud surfel_map.cpp:1398-1417,
+//   publish_all_pointcloud :1419-1454, publish_neighbor_pointcloud :1284-1300, save_cloud :1153-1173): every
+//   selected surfel becomes one PointXYZI {px, py, pz, intensity = color}, in pool order like the serial
+//   push_back loops.  Same count/scan as the compaction; 44 B read and 16 B written per surfel.
+__global__ void __launch_bounds__(256) k_pool_scatter_cloud(const __grid_constant__ DsmDev d, int b, const int *blkofs, float4 *dst, int mode, int key)
+{
+    __shared__ int s_warp[8];
+    const int begin = d.poolofs[b], end = d.poolofs[b + 1];
+    const int i = begin + blockIdx.x * 256 + threadIdx.x;
+    if (begin + blockIdx.x * 256 >= end) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool live = false;
+    if (i < end)
+    {
+        const dsm_surfel_t e = d.pool[i];
+        live = pool_pred(e, mode, key);
+        pt = make_float4(e.px, e.py, e.pz, e.color);
+    }
+    const unsigned bal = __ballot_sync(FULL, live);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wofs = 0;
+    for (int w = 0; w < warp; w++) wofs += s_warp[w];
+    if (live) dst[blkofs[blockIdx.x] + wofs + __popc(bal & ((1u << lane) - 1))] = pt;
 }
 
 __global__ void __launch_bounds__(256) k_pool_append(const __grid_constant__ DsmDev d, int b, const int *newofs, dsm_surfel_t *dst)
@@ -1661,6 +1690,19 @@ void dsm_launch_pool_retire(const DsmDev &d, int frame, int upper, int key, int 
     if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt, 1, key);
     k_pool_scan<<<1, 1024, 0, s>>>(d, frame, blkcnt, blkofs, newofs);
     if (nblk > 0) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst, 1, key);
+}
+// publish/save filters (mode/key as pool_pred): as_cloud ? PointXYZI float4 records : whole 44-byte surfels, in pool
+// order to dst (count in newofs[0]); the pool itself is not modified
+void dsm_launch_pool_export(const DsmDev &d, int frame, int upper, int mode, int key, bool as_cloud, int *blkcnt, int *blkofs, int *newofs, void *dst, cudaStream_t s)
+{
+    const int nblk = (upper + 255) / 256;
+    if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt, mode, key);
+    k_pool_scan<<<1, 1024, 0, s>>>(d, frame, blkcnt, blkofs, newofs);
+    if (nblk == 0) return;
+    if (as_cloud)
+        k_pool_scatter_cloud<<<nblk, 256, 0, s>>>(d, frame, blkofs, static_cast<float4 *>(dst), mode, key);
+    else
+        k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, static_cast<dsm_surfel_t *>(dst), mode, key);
 }
 void dsm_launch_pool_transform(const DsmDev &d, int frame, int upper, const float *Wm_dev, cudaStream_t s)
 {

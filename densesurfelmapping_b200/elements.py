@@ -28,7 +28,11 @@ SURFEL_DTYPE = np.dtype(
     }
 )
 
-assert SEED_DTYPE.itemsize == 60 and SURFEL_DTYPE.itemsize == 44
+# pcl::PointXYZI as published/saved by SurfelMap (surfel_map.h:31-32), without PCL's padding:
+# dsm_point_t of include/dsm.h
+POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("intensity", "<f4")])
+
+assert SEED_DTYPE.itemsize == 60 and SURFEL_DTYPE.itemsize == 44 and POINT_DTYPE.itemsize == 16
 
 SURFEL_FLOAT_FIELDS = ["px", "py", "pz", "nx", "ny", "nz", "size", "color", "weight"]
 SEED_FLOAT_FIELDS = ["x", "y", "size", "norm_x", "norm_y", "norm_z", "posi_x", "posi_y", "posi_z",

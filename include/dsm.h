@@ -42,6 +42,7 @@ extern "C" {
 #define DSM_E_CAPACITY (-6)  /* more surfels than the context was created for */
 #define DSM_E_STATE (-7)     /* call sequence error (e.g. download before run) */
 #define DSM_E_NCCL (-8)      /* NCCL unavailable or a collective failed */
+#define DSM_E_IO (-9)        /* a file could not be opened or written (dsm_write_*) */
 
 /* ---- element types: byte-identical to the reference ---- */
 
@@ -181,6 +182,35 @@ int dsm_pool_retire(dsm_ctx *ctx, int keyframe_index, dsm_surfel_t *out, int cap
 int dsm_pool_append(dsm_ctx *ctx, const dsm_surfel_t *surfels, int n);
 int dsm_pool_size(dsm_ctx *ctx, int *n_local);
 int dsm_pool_download(dsm_ctx *ctx, dsm_surfel_t *out, int cap, int *n_local);
+
+/* ---- output side: point clouds and files ----
+ * pcl::PointXYZI as the reference publishes and saves it, without PCL's SSE padding: 16 bytes. */
+typedef struct dsm_point_t
+{
+    float x, y, z;
+    float intensity; /* SurfelElement::color, gray 0-255 */
+} dsm_point_t;
+/*   dsm_pool_export_cloud      the cloud builders of SurfelMap over local_surfels: every pool surfel with
+ *                              update_times >= min_update_times becomes one point {px, py, pz, color}, in pool
+ *                              order like the serial push_back loops.  min_update_times = 5:
+ *                              publish_active_pointcloud (surfel_map.cpp:1398-1417), the local part of
+ *                              publish_all_pointcloud (:1419-1454) and save_cloud (:1153-1173); = 1: the local part
+ *                              of publish_neighbor_pointcloud (:1284-1300, "update_times == 0 -> skip").  Filter and
+ *                              compaction run on the device; only the selected 16-byte points cross PCIe.
+ *                              *n_out = number selected (may exceed cap; min(cap, *n_out) points are written).
+ *   dsm_pool_export_surfels    the same selection returning whole surfels (what save_mesh iterates, :1241-1247).
+ *   Both synchronise and leave the pool untouched.
+ *   dsm_write_pcd              pcl::io::savePCDFile(name, cloud) of surfel_map.cpp:1171 (PCD v0.7, fields
+ *                              x y z intensity; binary = 0 is what the reference writes).  Host only.
+ *   dsm_write_ply_mesh         SurfelMap::save_mesh (:1229-1280): one hexagon (6 vertices, 4 triangles) per
+ *                              surfel via push_a_surfel (:1175-1226), ASCII PLY.  The caller passes the attached
+ *                              surfels of every pose followed by dsm_pool_export_surfels(ctx, 5, ...).  Host only.
+ *   dsm_mesh_vertices          push_a_surfel alone: 36 floats (6 x {x, y, z, c, c, c}) per surfel. */
+int dsm_pool_export_cloud(dsm_ctx *ctx, int min_update_times, dsm_point_t *out, int cap, int *n_out);
+int dsm_pool_export_surfels(dsm_ctx *ctx, int min_update_times, dsm_surfel_t *out, int cap, int *n_out);
+int dsm_write_pcd(const char *path, const dsm_point_t *points, size_t n, int binary);
+int dsm_write_ply_mesh(const char *path, const dsm_surfel_t *surfels, size_t n);
+int dsm_mesh_vertices(const dsm_surfel_t *surfels, size_t n, float *vertices36);
 
 /* ---- parity / debug readback (what the reference keeps private: fusion_functions.h:34-37) ---- */
 int dsm_get_labels(dsm_ctx *ctx, int frame, int32_t *labels_hw);   /* superpixel_index, [H][W] */

@@ -170,6 +170,74 @@ def warp_active(surfels, W_colmajor):
     return out
 
 
+# ---- output side of SurfelMap, restated in numpy: surfel_map.cpp needs ROS + PCL and cannot
+# be compiled here, so these are UNPINNED restatements ----
+def cloud_points(local, min_update_times=5):
+    """The local_surfels loop of publish_active_pointcloud / publish_all_pointcloud / save_cloud
+    (surfel_map.cpp:1403-1412, :1429-1438, :1156-1166; `update_times < 5 -> continue`) and, with
+    min_update_times=1, of publish_neighbor_pointcloud (:1291-1300): [n, 4] float32 x, y, z, intensity=color."""
+    sel = local[local["update_times"] >= min_update_times]
+    return np.stack([sel["px"], sel["py"], sel["pz"], sel["color"]], -1).astype(np.float32).reshape(-1, 4)
+
+
+def mesh_vertices(surfels):
+    """push_a_surfel (surfel_map.cpp:1175-1226) in float32, operation order as written: [n, 6, 6]."""
+    f = np.float32
+    n = len(surfels)
+    col = surfels["color"].astype(np.int32).astype(f)                       # :1177
+    p = np.stack([surfels["px"], surfels["py"], surfels["pz"]], -1).astype(f)
+    nr = np.stack([surfels["nx"], surfels["ny"], surfels["nz"]], -1).astype(f)
+    xd = np.stack([f(-1) * nr[:, 1], nr[:, 0], np.zeros(n, f)], -1)         # :1186-1188
+    z = (xd[:, 0] * xd[:, 0] + xd[:, 1] * xd[:, 1]) + xd[:, 2] * xd[:, 2]   # normalize() :1189 (Eigen skips a zero vector)
+    nz = z > 0
+    with np.errstate(all="ignore"):
+        xd[nz] = xd[nz] / np.sqrt(z[nz])[:, None]
+    yd = np.stack([nr[:, 1] * xd[:, 2] - nr[:, 2] * xd[:, 1],               # cross :1191
+                   nr[:, 2] * xd[:, 0] - nr[:, 0] * xd[:, 2],
+                   nr[:, 0] * xd[:, 1] - nr[:, 1] * xd[:, 0]], -1)
+    r = surfels["size"].astype(f)
+    h_r = (r.astype(np.float64) * 0.5).astype(f)[:, None]                   # :1193
+    t_r = (r.astype(np.float64) * 0.86603).astype(f)[:, None]               # :1194
+    r = r[:, None]
+    pts = [p - xd * h_r - yd * t_r, p + xd * h_r - yd * t_r, p - xd * r,    # :1196-1201
+           p + xd * r, p - xd * h_r + yd * t_r, p + xd * h_r + yd * t_r]
+    out = np.zeros((n, 6, 6), f)
+    for k in range(6):
+        out[:, k, :3] = pts[k]
+        out[:, k, 3:] = col[:, None]
+    return out
+
+
+def _g(v, digits):
+    return "%.*g" % (digits, float(v))
+
+
+def ply_mesh_text(surfels):
+    """SurfelMap::save_mesh (surfel_map.cpp:1229-1280): the exact bytes of the ASCII PLY (ostream default
+    float format = %g with 6 digits; every vertex value is followed by a space)."""
+    v = mesh_vertices(surfels).reshape(-1, 6)
+    n = len(surfels)
+    lines = ["ply", "format ascii 1.0", f"element vertex {n * 6}", "property float x", "property float y",
+             "property float z", "property uchar red", "property uchar green", "property uchar blue",
+             f"element face {n * 4}", "property list uchar int vertex_index", "end_header"]
+    lines += ["".join(_g(x, 6) + " " for x in row) for row in v]
+    for i in range(n):
+        p1, p2, p3, p4, p5, p6 = (i * 6 + k for k in range(6))
+        lines += [f"3 {p1} {p2} {p3}", f"3 {p2} {p4} {p3}", f"3 {p3} {p4} {p5}", f"3 {p5} {p4} {p6}"]
+    return "\n".join(lines) + "\n"
+
+
+def pcd_text(points):
+    """pcl::io::savePCDFile(name, PointCloud<PointXYZI>) as called at surfel_map.cpp:1171 — PCL's ASCII writer
+    (PCD v0.7 header, 8 significant digits, NaN spelled "nan"); PCL is not vendored in the reference tree."""
+    pts = np.asarray(points, dtype=np.float32).reshape(-1, 4)
+    n = len(pts)
+    head = ["# .PCD v0.7 - Point Cloud Data file format", "VERSION 0.7", "FIELDS x y z intensity", "SIZE 4 4 4 4",
+            "TYPE F F F F", "COUNT 1 1 1 1", f"WIDTH {n}", "HEIGHT 1", "VIEWPOINT 0 0 0 1 0 0 0", f"POINTS {n}", "DATA ascii"]
+    body = [" ".join("nan" if np.isnan(x) else _g(x, 8) for x in row) for row in pts]
+    return "\n".join(head + body) + "\n"
+
+
 def have_reference():
     return os.path.exists(os.path.join(REFDIR, "libdsm_ref_serial.so"))
 
