@@ -26,7 +26,7 @@ EXPORTS = [
     "dsm_fuse_batch", "dsm_fuse_batch_async", "dsm_batch_wait", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
     "dsm_pool_transform", "dsm_pool_retire", "dsm_pool_append", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
-    "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices",
+    "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices", "dsm_debug_set_variants",
 ]
 
 
@@ -87,6 +87,7 @@ def load_library():
     L.dsm_get_seeds.argtypes = [vp, ci, vp]
     L.dsm_debug_stop_after.argtypes = [vp, ci]
     L.dsm_debug_invariant_violations.argtypes = [vp, ctypes.POINTER(ci)]
+    L.dsm_debug_set_variants.argtypes = [vp, ctypes.c_uint]
     L.dsm_profile_enable.argtypes = [vp, ctypes.c_uint32]
     L.dsm_profile_reset.argtypes = [vp]
     L.dsm_profile_read.argtypes = [vp, vp, vp]
@@ -255,6 +256,9 @@ class Context:
 
     def debug_stop_after(self, n):
         self._ck(self.lib.dsm_debug_stop_after(self.h, int(n)))
+
+    def debug_set_variants(self, mask):
+        self._ck(self.lib.dsm_debug_set_variants(self.h, int(mask)))
 
     def invariant_violations(self):
         c = ctypes.c_int(0)

@@ -332,6 +332,8 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     d.kx = ctx->kx;
     d.ky = ctx->ky;
     d.max_pool_per_frame = 0;
+    d.variants = 0;
+    if (const char *ev = getenv("DSM_EXPERIMENTAL_VARIANTS")) d.variants = (int)strtol(ev, nullptr, 0); // see dsm_debug_set_variants
     *out = ctx;
     return DSM_OK;
 }
@@ -648,6 +650,18 @@ extern "C" int dsm_debug_stop_after(dsm_ctx *ctx, int n)
 {
     if (!ctx) return DSM_E_INVALID;
     ctx->stop_after = n;
+    return DSM_OK;
+}
+
+extern "C" int dsm_debug_set_variants(dsm_ctx *ctx, unsigned mask)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (ctx->in_flight) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.exec); // captured schedules embed the kernel choice
+    ctx->graphs.clear();
+    ctx->d.variants = (int)mask;
     return DSM_OK;
 }
 

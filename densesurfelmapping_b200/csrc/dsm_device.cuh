@@ -69,7 +69,14 @@ struct DsmDev
     const float *ipose;
     const int32_t *refidx;
     int max_pool_per_frame; // largest per-frame pool slice in this batch (grid sizing)
+    int variants;           // DSM_VARIANT_* bits: experimental kernel variants (0 = the measured default path)
 };
+
+// experimental kernel variants (dsm_debug_set_variants).  All are bit-identical to the default
+// kernels by construction (same arithmetic, same order; only the data movement differs).
+#define DSM_VARIANT_NEWTON_STAGED 1u  // k_newton_staged: list staged once into shared memory with cp.async
+#define DSM_VARIANT_GATHER_TILED 2u   // k_gather_depths_tiled: window tiles by 1-D bulk copies (TMA) into shared memory
+#define DSM_VARIANT_POINTS_TILED 4u   // k_gather_points_tiled: same for the plane-fit gather
 
 enum DsmKernelId
 {

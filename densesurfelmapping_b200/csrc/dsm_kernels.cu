@@ -14,6 +14,7 @@
 #include <climits>
 #include <cuda/barrier>
 #include <cuda/ptx>
+#include <cuda_pipeline.h>
 
 #define HUBER_RANGE 0.4       // fusion_functions.h:13
 #define MAX_ANGLE_COS 0.1     // fusion_functions.h:11
@@ -42,6 +43,7 @@
 // -------------------------------------------------------------------------------------------
 // small helpers
 // -------------------------------------------------------------------------------------------
+using dsm_barrier = cuda::barrier<cuda::thread_scope_block>; // mbarrier for the TMA (cp.async.bulk) stagings
 __device__ __forceinline__ void sts_f32(unsigned addr, float v)
 { // st.shared with a precomputed 32-bit shared-window address (keeps the address math out of the hot loops)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
@@ -630,6 +632,297 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
 }
 
 // -------------------------------------------------------------------------------------------
+// K2a', EXPERIMENTAL (variant bit 1, off by default): k_gather_depths with the window data staged
+// through shared memory by TMA.  The direct-load kernel issues six 16-byte loads per lane whose 32 lanes touch 8
+// image rows each, i.e. 48 L1 wavefronts per seed window, and neighbouring windows fetch their common 8 columns
+// twice.  Here warp 0 fetches the block's whole 16 x 72 strip with 48 1-D bulk copies (cp.async.bulk, completion on
+// an mbarrier), and the 8 warps read their windows with conflict-free LDS.128 (row stride 80 words: the two rows
+// of a quarter-warp fall into different halves of the 32 banks).  Everything after the loads is the text of
+// k_gather_depths, so the results are bit-identical.
+// -------------------------------------------------------------------------------------------
+#define GT_STRIDE 80   // int32 / float elements per tile row (72 used)
+#define GT_GSTRIDE 144 // bytes per gray tile row (96 used; 36 words: 8 rows x 4 quarters hit 32 distinct banks)
+__global__ void __launch_bounds__(256) k_gather_depths_tiled(const __grid_constant__ DsmDev d)
+{
+    // tile[k][seed-in-block]: the 8 warps (one seed each) compact into shared memory, then the block
+    // copies the tile out as full 32-byte sectors of the [k][seed] global list (a direct scatter
+    // would cost one L2 write request per element)
+    __shared__ float tile[DL_CAP * 8];
+    __shared__ alignas(128) int32_t t_lab[16 * GT_STRIDE];
+    __shared__ alignas(128) float t_dep[16 * GT_STRIDE];
+    __shared__ alignas(128) uint8_t t_gry[16 * GT_GSTRIDE];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ dsm_barrier bar;
+    __shared__ int s_rows;
+    const int b = d.frame0 + blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sp_x = blockIdx.x * 8 + warp, sp_y = blockIdx.y;
+    const int s = sp_y * d.spw + sp_x;
+    if (threadIdx.x == 0)
+    {
+        s_rows = 0;
+        init(&bar, 1);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared); // make the initialised barrier visible to the async proxy
+    }
+    __syncthreads();
+    const int W = d.W, H = d.H, Wp = d.Wp;
+    const size_t so = (size_t)b * d.S;
+    // ---- the block's 16 x 72 pixel strip (8 seed windows of 16 columns, neighbours overlap by 8), one 1-D bulk
+    // copy (TMA) per image row and array: labels / depth rows of <= 288 B, gray rows of <= 96 B starting at the
+    // 16-byte boundary left of the strip.  Sources, destinations and sizes are multiples of 16 bytes because
+    // Wp % 16 == 0 and the strip starts at 64*bx - 4.  Rows above / below the image and columns past the pitch are
+    // simply not copied: every consumer below masks them exactly like the direct-load kernel does.
+    const int X0 = blockIdx.x * 64 - 4, Y0 = sp_y * DSM_SP - DSM_SP / 2;
+    if (warp == 0)
+    {
+        const size_t fo = (size_t)b * d.px_stride;
+        const int ya = Y0 > 0 ? Y0 : 0, yz = (Y0 + 16) < H ? (Y0 + 16) : H;
+        const int xs = X0 > 0 ? X0 : 0, xt = (X0 + 72) < Wp ? (X0 + 72) : Wp;
+        const int gs = (X0 - 12) > 0 ? (X0 - 12) : 0, gt = (X0 + 84) < Wp ? (X0 + 84) : Wp; // X0 - 12 = 64*bx - 16
+        const unsigned nb4 = (unsigned)(xt - xs) * 4u, nbg = (unsigned)(gt - gs);
+        if (lane == 0) (void)cuda::device::barrier_arrive_tx(bar, 1, (size_t)(yz - ya) * (2u * nb4 + nbg));
+        __syncwarp();
+        const int y = Y0 + lane;
+        if (lane < 16 && y >= ya && y < yz)
+        {
+            const size_t ro = fo + (size_t)y * Wp;
+            cuda::device::memcpy_async_tx(t_lab + lane * GT_STRIDE + (xs - X0), d.labels + ro + xs, cuda::aligned_size_t<16>(nb4), bar);
+            cuda::device::memcpy_async_tx(t_dep + lane * GT_STRIDE + (xs - X0), d.depth + ro + xs, cuda::aligned_size_t<16>(nb4), bar);
+            cuda::device::memcpy_async_tx(t_gry + lane * GT_GSTRIDE + (gs - (X0 - 12)), d.gray + ro + gs, cuda::aligned_size_t<16>(nbg), bar);
+        }
+    }
+    // The stable flag is fetched together with the window (not before it): one memory round trip per block
+    // instead of two; the few stable seeds just discard what was loaded (:478-479).
+    const bool inside = sp_x < d.spw;
+    const int tflag = d.tstable[so + (inside ? s : 0)];
+    if (inside) // warp-uniform
+    {
+        const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
+        const int xb = x0 > 0 ? x0 : 0, yb = y0 > 0 ? y0 : 0;
+        const int xe = (x0 + 16) < W - 1 ? (x0 + 16) : W - 1; // end-exclusive: last row/col never visited (:488-489)
+        const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
+        const int xq = x0 + 4 * (lane & 3);
+        const bool colin = xq >= 0 && xq < Wp;
+        int4 l4[2];
+        float4 z4[2];
+        uchar4 g4[2];
+        int yy[2];
+#pragma unroll
+        while (!cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(bar), 0)) {}
+        for (int ps = 0; ps < 2; ps++)
+        { // tile row r = 8*ps + lane/4, tile column 8*warp + 4*(lane&3); rows / columns that were not copied hold
+          // unspecified data and are masked by `in` exactly like the out-of-window lanes of the direct-load kernel
+            const int r = 8 * ps + (lane >> 2);
+            const int y = y0 + r;
+            yy[ps] = y;
+            const bool in = colin && y >= yb && y < ye;
+            const int c = 8 * warp + 4 * (lane & 3);
+            l4[ps] = *reinterpret_cast<const int4 *>(t_lab + r * GT_STRIDE + c);
+            z4[ps] = *reinterpret_cast<const float4 *>(t_dep + r * GT_STRIDE + c);
+            g4[ps] = *reinterpret_cast<const uchar4 *>(t_gry + r * GT_GSTRIDE + c + 12);
+            if (!in || tflag == DSM_STABLE) l4[ps] = make_int4(-1, -1, -1, -1);
+        }
+        unsigned mdm = 0; // bit 4*ps+k: member with depth > 0.1
+        int cnt2 = 0;     // member count, pass 0 in the low half-word, pass 1 in the high one
+        int sumx = 0, sumy = 0, sumi = 0;
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++)
+        {
+            const int lk[4] = {l4[ps].x, l4[ps].y, l4[ps].z, l4[ps].w};
+            const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
+            const int gk[4] = {g4[ps].x, g4[ps].y, g4[ps].z, g4[ps].w};
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int x = xq + k;
+                const bool mem = lk[k] == s && x >= xb && x < xe;
+                c += mem ? 1 : 0;
+                sumx += mem ? x : 0;
+                sumi += mem ? gk[k] : 0;
+                if (mem && zk[k] > F_0p1_LO) mdm |= 1u << (4 * ps + k); // (double)depth > 0.1 (:508)
+            }
+            cnt2 += c;
+            sumy += c * yy[ps];
+        }
+        const int cnt = __reduce_add_sync(FULL, cnt2);
+        const int tsx = __reduce_add_sync(FULL, sumx);
+        const int tsy = __reduce_add_sync(FULL, sumy);
+        const int tsi = __reduce_add_sync(FULL, sumi);
+        // one scan for both passes: pass-0 count in the low half-word, pass-1 count in the high one
+        const int c2 = __popc(mdm & 0xfu) | (__popc(mdm >> 4) << 16);
+        int tot2;
+        const int ex2 = warp_excl_scan(c2, lane, tot2);
+        const int n0 = tot2 & 0xffff, ndt = n0 + (tot2 >> 16);
+        const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
+        unsigned a0 = tbase + 32u * (ex2 & 0xffff), a1 = tbase + 32u * (n0 + (ex2 >> 16)); // 32 bytes per list row
+        const float za[4] = {z4[0].x, z4[0].y, z4[0].z, z4[0].w}, zb[4] = {z4[1].x, z4[1].y, z4[1].z, z4[1].w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            if ((mdm >> k) & 1u)
+            {
+                sts_f32(a0, za[k]);
+                a0 += 32u;
+            }
+            if ((mdm >> (4 + k)) & 1u)
+            {
+                sts_f32(a1, zb[k]);
+                a1 += 32u;
+            }
+        }
+        if (lane == 0 && tflag != DSM_STABLE)
+        {
+            d.usum[so + s] = make_int4(cnt, tsx, tsy, tsi);
+            d.und[so + s] = ndt;
+            atomicMax(&s_rows, ndt);
+        }
+    }
+    __syncthreads();
+    const int rows = s_rows;
+    const int c = threadIdx.x & 7;
+    if (blockIdx.x * 8 + c < d.spw)
+    {
+        float *dst = d.dlist + (size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c;
+        for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp] = tile[r * 8 + c];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K2b', EXPERIMENTAL (variant bit 0, off by default): k_newton with the member-depth list
+// staged ONCE into shared memory.  k_newton walks its [k][seed] list six times (mean + up to five Huber-
+// Newton passes); with 16 CTAs per SM the lists do not fit L1, so every pass comes from L2 again
+// (~54 MB per pass per 32-frame launch, the kernel runs at ~5 TB/s of L2 reads).  Here each thread
+// copies its own list column global -> shared with 4-byte cp.async (LDGSTS: no register staging, all
+// copies of a thread in flight at once), waits for its own copies only (a thread never reads another
+// thread's column, so no CTA barrier is needed) and then runs the identical arithmetic, in the identical
+// order, out of shared memory ([k][thread] layout: conflict-free).  Entries past NS_ROWS stay in global.
+// -------------------------------------------------------------------------------------------
+#define NS_ROWS 128
+#define NS_THREADS 64
+__global__ void __launch_bounds__(NS_THREADS) k_newton_staged(const __grid_constant__ DsmDev d)
+{
+    __shared__ float col[NS_ROWS * NS_THREADS]; // 32 KB
+    const int b = d.frame0 + blockIdx.y;
+    const int s = blockIdx.x * NS_THREADS + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.nlist[b] = 0; // the deferred-pixel list of this pass is consumed
+    if (s >= d.S) return;
+    const size_t so = (size_t)b * d.S;
+    if (d.tstable[so + s] == DSM_STABLE) return; // untouched by update_seeds
+    const int4 su = d.usum[so + s];
+    const int n = su.x;
+    if (n == 0)
+    {
+        atomicAdd(&d.errflag[b], 1);
+        d.tstable[so + s] = -1;
+        return;
+    }
+    const int nd = d.und[so + s];
+    const float *dl = d.dlist + (size_t)b * DL_CAP * d.Sp + s;
+    const size_t st = (size_t)d.Sp;
+    float *mycol = col + threadIdx.x;
+    const int ns = nd < NS_ROWS ? nd : NS_ROWS;
+    {
+        const float *pp = dl;
+        float *q = mycol;
+        for (int k = 0; k < ns; k++, pp += st, q += NS_THREADS) __pipeline_memcpy_async(q, pp, 4);
+        __pipeline_commit();
+    }
+    const float fn = (float)n; // sums below are < 2^24 so the reference's float accumulation is exact
+    const float mi = (float)su.w / fn;
+    const float mx = (float)su.y / fn;
+    const float my = (float)su.z / fn;
+    const float4 pre = d.seed[so + s];
+    const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
+    const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
+    __pipeline_wait_prior(0);
+    float md = 0.0f;
+    if (nd > 0)
+    {
+        // The list is walked as two ranges -- [0, ns) from shared memory, [ns, nd) from global memory -- each in
+        // groups of 8 like k_newton.  The grouping only batches the loads: every update of sum_d / sa / sb
+        // happens in list order, and "sb += 16" equals eight exact "+= 2" steps, so the values are identical.
+        auto fsm = [&](int k) -> float { return mycol[k * NS_THREADS]; };
+        auto fgl = [&](int k) -> float { return dl[(size_t)k * st]; };
+        float sum_d = 0.0f;
+        auto mean_range = [&](int k0, int k1, auto get)
+        {
+            int k = k0;
+            for (; k + 8 <= k1; k += 8)
+            {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = get(k + j);
+#pragma unroll
+                for (int j = 0; j < 8; j++) sum_d += v[j]; // raster order (:511)
+            }
+            for (; k < k1; k++) sum_d += get(k);
+        };
+        mean_range(0, ns, fsm);
+        mean_range(ns, nd, fgl);
+        md = sum_d / (float)nd;
+        for (int it = 0; it < 5; it++)
+        { // damped Huber-Newton (:534-554), expression by expression as in k_newton
+            float sa = 0.0f, sb = 0.0f;
+            auto newton_range = [&](int k0, int k1, auto get)
+            {
+                int k = k0;
+                for (; k + 8 <= k1; k += 8)
+                {
+                    float r[8];
+                    bool allin = true;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                    {
+                        r[j] = md - get(k + j);
+                        allin &= r[j] < F_0p4_HI && r[j] > -F_0p4_HI; // (double)r < 0.4 && (double)r > -0.4
+                    }
+                    if (allin)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sa += 2 * r[j];
+                        sb += 16; // eight exact +2 steps
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            if (r[j] < F_0p4_HI && r[j] > -F_0p4_HI)
+                            {
+                                sa += 2 * r[j];
+                                sb += 2;
+                            }
+                            else
+                                sa = (float)((double)sa + (r[j] > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
+                        }
+                    }
+                }
+                for (; k < k1; k++)
+                {
+                    const float r = md - get(k);
+                    if (r < F_0p4_HI && r > -F_0p4_HI)
+                    {
+                        sa += 2 * r;
+                        sb += 2;
+                    }
+                    else
+                        sa = (float)((double)sa + (r > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
+                }
+            };
+            newton_range(0, ns, fsm);
+            newton_range(ns, nd, fgl);
+            const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
+            md = md + delta;
+            if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
+        }
+    }
+    d.seed[so + s] = make_float4(mx, my, mi, md);
+    d.inv_md[so + s] = 1.0 / (double)md;
+    d.tstable[so + s] = newstable ? DSM_STABLE : -1;
+}
+
+// -------------------------------------------------------------------------------------------
 // K3  backproject_normals — calculate_spaces_kernel (:644-662) + calculate_pixels_norms_kernel
 // (:664-712), fused: the reference's 24 B/px fp64 space_map is never materialised.
 //
@@ -811,6 +1104,187 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
                 const float4 a = *reinterpret_cast<const float4 *>(nrx + pof[ps]);
                 const float4 bb = *reinterpret_cast<const float4 *>(nry + pof[ps]);
                 const float4 c = *reinterpret_cast<const float4 *>(nrz + pof[ps]);
+                const float ax[4] = {a.x, a.y, a.z, a.w}, ay[4] = {bb.x, bb.y, bb.z, bb.w}, az[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((mi >> k) & 1u) snx += ax[k], sny += ay[k], snz += az[k];
+                inl |= mi << (4 * ps);
+            }
+        }
+        maxd = warp_max_f(maxd);
+        nvalid = __reduce_add_sync(FULL, nvalid);
+        snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
+        spx = warp_sum_f(spx), spy = warp_sum_f(spy), spz = warp_sum_f(spz);
+        const int c2 = __popc(inl & 0xfu) | (__popc(inl >> 4) << 16);
+        int tot2;
+        const int ex2 = warp_excl_scan(c2, lane, tot2);
+        const int n0 = tot2 & 0xffff, ninl = n0 + (tot2 >> 16);
+        const bool ok = live && nvalid >= 16 && !((float)ninl / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
+        float4 P0 = make_float4(0.f, 0.f, 0.f, maxd), P1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        if (ok)
+        {
+            const float fn = (float)ninl;
+            const float mxs = spx / fn, mys = spy / fn, mzs = spz / fn; // (:117-119)
+            const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
+#pragma unroll
+            for (int ps = 0; ps < 2; ps++)
+            {
+                unsigned a = tbase + 32u * (ps == 0 ? (ex2 & 0xffff) : n0 + (ex2 >> 16)); // 32 bytes per list row
+                const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((inl >> (4 * ps + k)) & 1u)
+                    {
+                        sts_f32(a, kxv[k] * zk[k] - mxs); // centred points (:121-126)
+                        sts_f32(a + 4u * PF_CAP * 8, kyv[ps] * zk[k] - mys);
+                        sts_f32(a + 8u * PF_CAP * 8, zk[k] - mzs);
+                        a += 32u;
+                    }
+            }
+            P0 = make_float4(snx, sny, snz, maxd);
+            P1 = make_float4(mxs, mys, mzs, __int_as_float(ninl));
+            if (lane == 0) atomicMax(&s_rows, ninl);
+        }
+        if (live && lane == 0)
+        {
+            d.pfsum[(so + s) * 2] = P0;
+            d.pfsum[(so + s) * 2 + 1] = P1;
+        }
+    }
+    __syncthreads();
+    const int rows = s_rows;
+    const unsigned c = threadIdx.x & 7u;
+    if (blockIdx.x * 8 + c < (unsigned)d.spw)
+    {
+        const size_t plane = (size_t)d.B * PF_CAP * d.Sp;
+        float *dx = d.qlist + ((size_t)b * PF_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c);
+        float *dy = dx + plane, *dz = dy + plane;
+        const unsigned sp = (unsigned)d.Sp;
+#pragma unroll 2
+        for (unsigned r = threadIdx.x >> 3; r < (unsigned)rows; r += 32u)
+        {
+            const unsigned t = r * 8u + c, o = r * sp;
+            dx[o] = tile[t];
+            dy[o] = tile[PF_CAP * 8 + t];
+            dz[o] = tile[2 * PF_CAP * 8 + t];
+        }
+    }
+}
+
+// K4a', EXPERIMENTAL (variant bit 2, off by default): k_gather_points with labels, depth and the
+// three normal planes of the block's strip staged through shared memory by TMA 1-D bulk copies, like
+// k_gather_depths_tiled.  Everything after the loads is the text of k_gather_points: bit-identical results.
+__global__ void __launch_bounds__(256) k_gather_points_tiled(const __grid_constant__ DsmDev d)
+{
+    // tile[plane][k][seed-in-block]: compacted in shared memory, copied out as full 32-byte sectors
+    __shared__ float tile[3 * PF_CAP * 8];
+    __shared__ alignas(128) int32_t t_lab[16 * GT_STRIDE];
+    __shared__ alignas(128) float t_dep[16 * GT_STRIDE];
+    __shared__ alignas(128) float t_nrm[3 * 16 * GT_STRIDE];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ dsm_barrier bar;
+    __shared__ int s_rows;
+    const int b = d.frame0 + blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sp_x = blockIdx.x * 8 + warp, sp_y = blockIdx.y;
+    const int s = sp_y * d.spw + sp_x;
+    if (threadIdx.x == 0)
+    {
+        s_rows = 0;
+        init(&bar, 1);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared); // make the initialised barrier visible to the async proxy
+    }
+    __syncthreads();
+    const int W = d.W, H = d.H, Wp = d.Wp;
+    const size_t so = (size_t)b * d.S;
+    const bool live = sp_x < d.spw;
+    // the block's 16 x 72 strip of labels, depth and the three normal planes: 80 1-D bulk copies (TMA) of <= 288 B
+    // (see k_gather_depths_tiled); the normals arrive in the same phase as the labels instead of by a second,
+    // dependent round of global loads
+    const int X0 = blockIdx.x * 64 - 4, Y0 = sp_y * DSM_SP - DSM_SP / 2;
+    if (warp == 0)
+    {
+        const size_t fo = (size_t)b * d.px_stride;
+        const int ya = Y0 > 0 ? Y0 : 0, yz = (Y0 + 16) < H ? (Y0 + 16) : H;
+        const int xs = X0 > 0 ? X0 : 0, xt = (X0 + 72) < Wp ? (X0 + 72) : Wp;
+        const unsigned nb4 = (unsigned)(xt - xs) * 4u;
+        if (lane == 0) (void)cuda::device::barrier_arrive_tx(bar, 1, (size_t)(yz - ya) * (5u * nb4));
+        __syncwarp();
+        const int y = Y0 + lane;
+        if (lane < 16 && y >= ya && y < yz)
+        {
+            const size_t ro = fo + (size_t)y * Wp + xs;
+            const int to = lane * GT_STRIDE + (xs - X0);
+            cuda::device::memcpy_async_tx(t_lab + to, d.labels + ro, cuda::aligned_size_t<16>(nb4), bar);
+            cuda::device::memcpy_async_tx(t_dep + to, d.depth + ro, cuda::aligned_size_t<16>(nb4), bar);
+            cuda::device::memcpy_async_tx(t_nrm + to, d.nrm + ro, cuda::aligned_size_t<16>(nb4), bar);
+            cuda::device::memcpy_async_tx(t_nrm + 16 * GT_STRIDE + to, d.nrm + d.nrm_plane + ro, cuda::aligned_size_t<16>(nb4), bar);
+            cuda::device::memcpy_async_tx(t_nrm + 32 * GT_STRIDE + to, d.nrm + 2 * d.nrm_plane + ro, cuda::aligned_size_t<16>(nb4), bar);
+        }
+    }
+    // Slots past the last seed column run the same straight-line code on an empty window: every shuffle
+    // below sits in convergent code (a shuffle inside a possibly-divergent branch costs ~10 instructions).
+    {
+        const float4 sd = d.seed[so + (live ? s : 0)]; // x, y, I, mean_depth (Huber mean after the 3 iterations)
+        const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
+        const int xq = x0 + 4 * (lane & 3);
+        const bool colin = live && xq >= 0 && xq < Wp;
+        const float4 k4 = *reinterpret_cast<const float4 *>(d.kx + (colin ? xq : 0));
+        const float kxv[4] = {k4.x, k4.y, k4.z, k4.w};
+        int4 l4[2];
+        float4 z4[2];
+        float kyv[2];
+        int yy[2];
+        unsigned pof[2];
+#pragma unroll
+        while (!cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(bar), 0)) {}
+        for (int ps = 0; ps < 2; ps++)
+        { // tile row 8*ps + lane/4, tile column 8*warp + 4*(lane&3); positions that were not copied are masked by `in`
+            const int r = 8 * ps + (lane >> 2);
+            const int y = y0 + r;
+            yy[ps] = y;
+            const bool in = colin && y >= 0 && y < H;
+            const unsigned po = (unsigned)(r * GT_STRIDE + 8 * warp + 4 * (lane & 3));
+            pof[ps] = po;
+            l4[ps] = *reinterpret_cast<const int4 *>(t_lab + po);
+            z4[ps] = *reinterpret_cast<const float4 *>(t_dep + po);
+            kyv[ps] = d.ky[in ? y : 0];
+            if (!in) l4[ps] = make_int4(-1, -1, -1, -1);
+        }
+        unsigned inl = 0; // bit 4*ps+k: inlier
+        int nvalid = 0;
+        float maxd = 0.f, snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++)
+        {
+            const int lk[4] = {l4[ps].x, l4[ps].y, l4[ps].z, l4[ps].w};
+            const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
+            unsigned mi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int x = xq + k;
+                if (lk[k] != s || x >= W) continue; // window bounded by the flat index only (:816)
+                const float xd = (float)x - sd.x, yd = (float)yy[ps] - sd.y;
+                const float dist = xd * xd + yd * yd;
+                if (dist > maxd) maxd = dist;
+                const float mz = zk[k];
+                if (!(mz > F_0p05_LO)) continue; // (double)depth > 0.05 (:827)
+                nvalid++;
+                const float r = sd.w - mz;
+                if (r < F_0p4_HI && r > -F_0p4_HI)
+                { // inlier (:849-860)
+                    mi |= 1u << k;
+                    spx += kxv[k] * mz; // back_project in float (:94-96)
+                    spy += kyv[ps] * mz;
+                    spz += mz;
+                }
+            }
+            if (mi)
+            { // pixel normals of this 4-pixel group: three 16-byte loads instead of up to 12 scalar ones
+                const float4 a = *reinterpret_cast<const float4 *>(t_nrm + pof[ps]);
+                const float4 bb = *reinterpret_cast<const float4 *>(t_nrm + 16 * GT_STRIDE + pof[ps]);
+                const float4 c = *reinterpret_cast<const float4 *>(t_nrm + 32 * GT_STRIDE + pof[ps]);
                 const float ax[4] = {a.x, a.y, a.z, a.w}, ay[4] = {bb.x, bb.y, bb.z, bb.w}, az[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
@@ -1183,8 +1657,6 @@ __global__ void __launch_bounds__(128) k_gauss_newton_small(const __grid_constan
 // the load, a bulk async-group for the store) issued by a single thread -- no per-thread address math,
 // no register staging; otherwise (unaligned slice start, ragged tail) coalesced 4-byte accesses.
 // -------------------------------------------------------------------------------------------
-using dsm_barrier = cuda::barrier<cuda::thread_scope_block>;
-
 __device__ __forceinline__ bool stage_in(float *sm, const float *g, int cnt, dsm_barrier *bar, int nthreads)
 {
     const unsigned bytes = (unsigned)cnt * 44u;
@@ -1633,10 +2105,21 @@ void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s) { k_relax<<<nb, 1
 void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s)
 {
     dim3 grid((d.spw + 7) / 8, d.sph, nb);
+    if (d.variants & DSM_VARIANT_GATHER_TILED)
+    {
+        k_gather_depths_tiled<<<grid, 256, 0, s>>>(d);
+        return;
+    }
     k_gather_depths<<<grid, 256, 0, s>>>(d);
 }
 void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s)
 {
+    if (d.variants & DSM_VARIANT_NEWTON_STAGED)
+    {
+        dim3 grid((d.S + NS_THREADS - 1) / NS_THREADS, nb);
+        k_newton_staged<<<grid, NS_THREADS, 0, s>>>(d);
+        return;
+    }
     dim3 grid((d.S + 127) / 128, nb);
     k_newton<<<grid, 128, 0, s>>>(d);
 }
@@ -1649,6 +2132,11 @@ void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s)
 void dsm_launch_gather_points(const DsmDev &d, int nb, cudaStream_t s)
 {
     dim3 grid((d.spw + 7) / 8, d.sph, nb);
+    if (d.variants & DSM_VARIANT_POINTS_TILED)
+    {
+        k_gather_points_tiled<<<grid, 256, 0, s>>>(d);
+        return;
+    }
     k_gather_points<<<grid, 256, 0, s>>>(d);
 }
 void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s)

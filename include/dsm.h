@@ -223,6 +223,13 @@ int dsm_debug_stop_after(dsm_ctx *ctx, int n_kernels);
  * without members); the parity tests assert it is 0. */
 int dsm_debug_invariant_violations(dsm_ctx *ctx, int *count);
 
+/* debug / experiments: select experimental kernel variants (bit mask, 0 = the measured default path; bits in
+ * csrc/dsm_device.cuh, DSM_VARIANT_*).  Every variant computes bit-identical results by construction; they exist so
+ * that a data-movement change can be A/B-timed and parity-checked on the same build (the environment variable
+ * DSM_EXPERIMENTAL_VARIANTS sets the initial mask of every context, so the whole test suite and bench.py can run
+ * under a variant unchanged).  Drops the context's captured CUDA graphs. */
+int dsm_debug_set_variants(dsm_ctx *ctx, unsigned mask);
+
 /* ---- measurement hooks ----
  * Per-kernel CUDA-event timing on the context's stream.  mask selects kernels (bit k = kernel
  * id k, see dsm_kernel_name); 0 disables.  Accumulates until dsm_profile_reset(). */
