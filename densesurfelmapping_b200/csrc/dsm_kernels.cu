@@ -1493,6 +1493,169 @@ __global__ void __launch_bounds__(128) k_gauss_newton(const __grid_constant__ Ds
     pl[2] = r2;
 }
 
+// K4b', EXPERIMENTAL (variant bit 3, off by default): k_gauss_newton with every pass over the point
+// list streamed through thread-private shared-memory columns by double-buffered 4-byte cp.async instead of
+// 4-point register batches whose load latency is exposed once per batch.  Same point order, same arithmetic.
+#define GS_CH 16
+__global__ void __launch_bounds__(128) k_gauss_newton_staged(const __grid_constant__ DsmDev d)
+{
+    __shared__ float stage[2 * 3 * GS_CH * 128]; // [buffer][plane][row][thread]: 48 KB
+    float *mybuf = stage + threadIdx.x;
+    const int b = d.frame0 + blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.S) return;
+    const size_t so = (size_t)b * d.S;
+    const float4 sd = d.seed[so + s];
+    const float4 P0 = d.pfsum[(so + s) * 2], P1 = d.pfsum[(so + s) * 2 + 1];
+    const int n = __float_as_int(P1.w);
+    // default record: plane fit rejected -> zero normal / position / view_cos / size (H6-i), Huber mean depth kept
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r1 = make_float4(0.f, 0.f, 0.f, sd.w);
+    float4 r2 = make_float4(0.f, sd.z, sd.x, sd.y);
+    if (n > 0)
+    {
+        const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
+        float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
+        const float mxs = P1.x, mys = P1.y, mzs = P1.z;
+        const size_t plane = (size_t)d.B * PF_CAP * d.Sp, st = (size_t)d.Sp;
+        const float *qx = d.qlist + (size_t)b * PF_CAP * d.Sp + s;
+        const float *qy = qx + plane, *qz = qy + plane;
+        double hall[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // xx xy xz xw yy yz yw zz zw ww over ALL points
+        // Pass skipping: a pass over the points is only needed to find out which of them fall outside the
+        // Huber range.  With rmax >= max|r_i| of the last evaluated parameters, qmax = max|q_i| and the step
+        // (dn, db) just taken, |r_i(new)| <= rmax + qmax*|dn| + |db|.  If that bound (plus a rounding
+        // slack far above the float error of evaluating r) stays below the range, every point is
+        // provably in range, so H_R = H_all and J = H_all*theta without touching memory.  Results are
+        // bit-identical to evaluating the pass.
+        float rmax = 0.f, qmax2 = 0.f;
+        bool need_pass = true;
+        for (int gn = 0; gn < 5; gn++)
+        {
+            double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // same, over the points outside the Huber range
+            double jo[4] = {0, 0, 0, 0};
+            if (need_pass)
+            {
+                float rm = 0.f;
+                bool rnan = false;
+                auto point = [&](float ax, float ay, float az)
+                {
+                    const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
+                    const bool inr = r < F_0p4_HI && r > -F_0p4_HI;  // (:134)
+                    rm = fmaxf(rm, fabsf(r));
+                    rnan |= !(r == r);
+                    if (gn == 0 || !inr)
+                    {
+                        const double t0 = (double)(2 * ax * ax), t1 = (double)(2 * ax * ay), t2 = (double)(2 * ax * az), t3 = (double)(2 * ax);
+                        const double t4 = (double)(2 * ay * ay), t5 = (double)(2 * ay * az), t6 = (double)(2 * ay);
+                        const double t7 = (double)(2 * az * az), t8 = (double)(2 * az);
+                        if (gn == 0)
+                        {
+                            hall[0] += t0, hall[1] += t1, hall[2] += t2, hall[3] += t3, hall[4] += t4;
+                            hall[5] += t5, hall[6] += t6, hall[7] += t7, hall[8] += t8, hall[9] += 2;
+                            qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
+                        }
+                        if (!inr)
+                        {
+                            ho[0] += t0, ho[1] += t1, ho[2] += t2, ho[3] += t3, ho[4] += t4;
+                            ho[5] += t5, ho[6] += t6, ho[7] += t7, ho[8] += t8, ho[9] += 2;
+                            if (r >= F_0p4_HI)
+                            { // (double)r >= 0.4 (:157-163)
+                                jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
+                                jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                            }
+                            else if (r <= -F_0p4_HI)
+                            { // (double)r <= -0.4 (:164-170)
+                                jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
+                                jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
+                            }
+                        }
+                    }
+                };
+                // the list streams through this thread's private shared-memory columns in chunks of GS_CH points,
+                // double-buffered with cp.async: chunk c+1 is in flight while chunk c is consumed (same point order)
+                const int nch = (n + GS_CH - 1) / GS_CH;
+                auto issue = [&](int c)
+                {
+                    if (c < nch)
+                    {
+                        const int k0 = c * GS_CH, k1 = (k0 + GS_CH) < n ? (k0 + GS_CH) : n;
+                        float *dst = mybuf + (c & 1) * (3 * GS_CH * 128);
+                        for (int k = k0; k < k1; k++, dst += 128)
+                        {
+                            __pipeline_memcpy_async(dst, qx + k * st, 4);
+                            __pipeline_memcpy_async(dst + GS_CH * 128, qy + k * st, 4);
+                            __pipeline_memcpy_async(dst + 2 * GS_CH * 128, qz + k * st, 4);
+                        }
+                    }
+                    __pipeline_commit(); // (possibly empty) group, so that "all but the newest group" below is chunk c
+                };
+                issue(0);
+                for (int c = 0; c < nch; c++)
+                {
+                    issue(c + 1);
+                    __pipeline_wait_prior(1);
+                    const int cnt = (n - c * GS_CH) < GS_CH ? (n - c * GS_CH) : GS_CH;
+                    const float *src = mybuf + (c & 1) * (3 * GS_CH * 128);
+                    for (int r = 0; r < cnt; r++) point(src[r * 128], src[(GS_CH + r) * 128], src[(2 * GS_CH + r) * 128]);
+                }
+                __pipeline_wait_prior(0);
+                rmax = rnan ? __int_as_float(0x7f800000) : rm; // a NaN residual forces every later pass
+            }
+            double hh[10], jj[4];
+#pragma unroll
+            for (int i = 0; i < 10; i++) hh[i] = hall[i] - ho[i];
+            const double tx = (double)nx, ty = (double)ny, tz = (double)nz, tb = (double)nb;
+            jj[0] = ((hh[0] * tx + hh[1] * ty) + hh[2] * tz) + hh[3] * tb + jo[0];
+            jj[1] = ((hh[1] * tx + hh[4] * ty) + hh[5] * tz) + hh[6] * tb + jo[1];
+            jj[2] = ((hh[2] * tx + hh[5] * ty) + hh[7] * tz) + hh[8] * tb + jo[2];
+            jj[3] = ((hh[3] * tx + hh[6] * ty) + hh[8] * tz) + hh[9] * tb + jo[3];
+            hh[0] += 5, hh[4] += 5, hh[7] += 5, hh[9] += 5; // LM damping (:172-175)
+            double u[4];
+            solve4_spd(hh, jj, u);
+            const float ox = nx, oy = ny, oz = nz, ob = nb;
+            nx = (float)((double)nx - u[0]);
+            ny = (float)((double)ny - u[1]);
+            nz = (float)((double)nz - u[2]);
+            nb = (float)((double)nb - u[3]);
+            // can the next pass be skipped?
+            const float dx = nx - ox, dy = ny - oy, dz = nz - oz;
+            const float bound = rmax + sqrtf(qmax2) * sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + fabsf(nb - ob) + 1e-3f;
+            need_pass = !(bound < 0.39f); // NaN-safe: any NaN keeps evaluating
+            rmax = bound;
+        }
+        nb = nb - (nx * mxs + ny * mys + nz * mzs);
+        const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
+        nx /= nl;
+        ny /= nl;
+        nz /= nl;
+        nb /= nl;
+        // centre of the superpixel projected onto the fitted plane (:884-895)
+        const float axf = (sd.x - d.cx) / d.fx * sd.w;
+        const float ayf = (sd.y - d.cy) / d.fy * sd.w;
+        double ax = (double)axf, ay = (double)ayf, az = (double)sd.w;
+        const float kk = (float)(-1 * (ax * (double)nx + ay * (double)ny + az * (double)nz) - (double)nb);
+        ax += (double)(kk * nx);
+        ay += (double)(kk * ny);
+        az += (double)(kk * nz);
+        const float mean_depth = (float)az;
+        float view_cos = (float)(-1.0 * ((double)nx * ax + (double)ny * ay + (double)nz * az) / sqrt(ax * ax + ay * ay + az * az));
+        if (view_cos < 0)
+        {
+            view_cos = -view_cos;
+            nx = -nx;
+            ny = -ny;
+            nz = -nz;
+        }
+        r0 = make_float4(nx, ny, nz, view_cos);
+        r1 = make_float4((float)ax, (float)ay, (float)az, mean_depth);
+        r2.x = sqrtf(P0.w);
+    }
+    float4 *pl = d.plane + (so + s) * 3;
+    pl[0] = r0;
+    pl[1] = r1;
+    pl[2] = r2;
+}
+
 // k_gauss_newton for SMALL batches (single-frame stream): 8 lanes per seed.  Every lane takes every 8th
 // point, the fp64 sums are combined with three width-8 shuffle steps, all lanes of the group then hold
 // the same normal equations and solve them redundantly.  Same algebra, pass skipping and thresholds as
@@ -2148,6 +2311,11 @@ void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s)
         return;
     }
     dim3 grid((d.S + 127) / 128, nb);
+    if (d.variants & DSM_VARIANT_GN_STAGED)
+    {
+        k_gauss_newton_staged<<<grid, 128, 0, s>>>(d);
+        return;
+    }
     k_gauss_newton<<<grid, 128, 0, s>>>(d);
 }
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s)
