@@ -26,7 +26,7 @@ EXPORTS = [
     "dsm_fuse_batch", "dsm_fuse_batch_async", "dsm_batch_wait", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
     "dsm_pool_transform", "dsm_pool_retire", "dsm_pool_append", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
-    "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices", "dsm_debug_set_variants",
+    "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices", "dsm_debug_set_variants", "dsm_fuse_stream_resident",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library():
     L.dsm_pool_upload.argtypes = [vp, vp, ci]
     L.dsm_fuse_frame_resident.argtypes = [vp, ci, vp, cs, vp, cs, vp, ctypes.POINTER(ci)]
     L.dsm_pool_transform.argtypes = [vp, vp]
+    L.dsm_fuse_stream_resident.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.dsm_pool_retire.argtypes = [vp, ci, vp, ci, ctypes.POINTER(ci)]
     L.dsm_pool_append.argtypes = [vp, vp, ci]
     L.dsm_pool_size.argtypes = [vp, ctypes.POINTER(ci)]
@@ -201,6 +202,18 @@ class Context:
         self._ck(self.lib.dsm_fuse_frame_resident(self.h, int(ref_idx), _ptr(gray), gray.strides[0], _ptr(depth), depth.strides[0],
                                                   _ptr(pose), ctypes.byref(n) if want_count else None))
         return n.value if want_count else None
+
+    def fuse_stream_resident(self, ref_idx, gray, depth, poses, want_counts=False):
+        """n consecutive frames of one stream in one call (see include/dsm.h); gray [n,H,W] u8, depth [n,H,W] f32."""
+        ref = np.ascontiguousarray(ref_idx, dtype=np.int32)
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(len(ref), 16)
+        assert gray.shape == (len(ref), self.cam.height, self.cam.width) and depth.shape == gray.shape
+        cnt = np.zeros(len(ref), dtype=np.int32)
+        self._ck(self.lib.dsm_fuse_stream_resident(self.h, len(ref), _ptr(ref), _ptr(gray), _ptr(depth), _ptr(poses),
+                                                   _ptr(cnt) if want_counts else None))
+        return cnt if want_counts else None
 
     def pool_transform(self, W_colmajor):
         w = np.ascontiguousarray(W_colmajor, dtype=np.float32).reshape(16)

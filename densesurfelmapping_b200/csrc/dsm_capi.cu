@@ -22,6 +22,7 @@ struct GraphEntry
     int f0, nf, maxper, compact;
     const void *pool, *poolofs, *alt;
     cudaGraphExec_t exec;
+    int phase;
 };
 
 struct dsm_ctx
@@ -530,7 +531,8 @@ extern "C" int dsm_batch_restore_pool(dsm_ctx *ctx)
 
 // The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79),
 // enqueued for the frame slots [f0, f0 + nf).
-static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame, cudaStream_t st)
+// phase bit 0: the pose- and pool-independent part (superpixels, pixel normals, plane fit); bit 1: fuse + initialise.
+static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame, cudaStream_t st, int phase = 3)
 {
     DsmDev d = ctx->d;
     d.frame0 = f0;
@@ -543,6 +545,8 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
         ProfScope p(ctx, ID, st);       \
         CALL;                           \
     }
+    if (phase & 1)
+    {
     STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
     for (int it = 0; it < 3; it++) // ITERATION_NUM (fusion_functions.h:8)
     {
@@ -561,11 +565,15 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
     STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
     STEP(DSM_K_GATHER_POINTS, dsm_launch_gather_points(d, nb, st));
     STEP(DSM_K_GAUSS_NEWTON, dsm_launch_gauss_newton(d, nb, st));
+    }
+    if (phase & 2)
+    {
     if (max_pool_per_frame > 0)
     {
         STEP(DSM_K_FUSE, dsm_launch_fuse(d, nb, st));
     }
     STEP(DSM_K_INIT_SURFELS, dsm_launch_init_surfels(d, nb, st));
+    }
 #undef STEP
     CK(cudaGetLastError());
     return DSM_OK;
@@ -575,7 +583,7 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
 // The 17-21 launches are captured once per distinct parameter set into a CUDA graph and replayed: the
 // per-launch CPU cost and inter-kernel gaps matter for single frames and small chunks.  Profiling
 // (event pairs around kernels) and the debug kernel budget use plain launches.
-static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream_t st, bool compact = false)
+static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream_t st, bool compact = false, int phase = 3)
 {
     // grids over the pool are sized from `maxper` rounded up to 4 Ki surfels (the kernels take the true
     // ranges from poolofs on the device, surplus blocks exit at once), so that callers whose pool size
@@ -583,7 +591,7 @@ static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream
     if (maxper > 0) maxper = (maxper + 4095) & ~4095;
     auto plain = [&]() -> int
     {
-        int rc = launch_schedule(ctx, f0, nf, maxper, st);
+        int rc = launch_schedule(ctx, f0, nf, maxper, st, phase);
         if (rc != DSM_OK) return rc;
         if (compact)
         {
@@ -596,7 +604,7 @@ static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream
     if (!ctx->use_graphs || ctx->prof_mask != 0 || ctx->stop_after > 0) return plain();
     for (auto &g : ctx->graphs)
         if (g.f0 == f0 && g.nf == nf && g.maxper == maxper && g.compact == (int)compact && g.pool == ctx->d.pool &&
-            g.poolofs == ctx->d.poolofs && g.alt == ctx->pool_snap)
+            g.poolofs == ctx->d.poolofs && g.alt == ctx->pool_snap && g.phase == phase)
         {
             CK(cudaGraphLaunch(g.exec, st));
             return DSM_OK;
@@ -630,7 +638,7 @@ static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream
         cudaGraphExecDestroy(ctx->graphs.front().exec);
         ctx->graphs.erase(ctx->graphs.begin());
     }
-    ctx->graphs.push_back(GraphEntry{f0, nf, maxper, (int)compact, ctx->d.pool, ctx->d.poolofs, ctx->pool_snap, exec});
+    ctx->graphs.push_back(GraphEntry{f0, nf, maxper, (int)compact, ctx->d.pool, ctx->d.poolofs, ctx->pool_snap, exec, phase});
     CK(cudaGraphLaunch(exec, st));
     return DSM_OK;
 }
@@ -1069,6 +1077,101 @@ extern "C" int dsm_fuse_frame_resident(dsm_ctx *ctx, int ref_idx, const uint8_t 
         CK(cudaMemcpyAsync(&c, ctx->d.nnew + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         *n_new = c;
+    }
+    return DSM_OK;
+}
+
+// A run of n consecutive frames of ONE sequential stream on the resident pool.  Results are identical to n calls of
+// dsm_fuse_frame_resident: superpixels, normals and plane fits do not depend on the pose or the pool, so they run
+// for all n frames as one batch (full-width launches instead of n latency-bound single-frame ones); only the fuse /
+// initialise / compaction steps, which carry the pool from frame t to frame t+1, run frame by frame.
+extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_idx, const uint8_t *gray, const float *depth,
+                                        const float *poses, int32_t *n_new)
+{
+    if (!ctx || !ref_idx || !gray || !depth || !poses) return DSM_E_INVALID;
+    if (n < 1 || n > ctx->p.max_batch) return DSM_E_INVALID;
+    if (!ctx->res_active) return DSM_E_STATE;
+    if (ctx->in_flight) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->res_upper + n * ctx->S > ctx->p.max_local_surfels)
+    { // the bound may be loose: fetch the exact size before giving up
+        int cur = 0;
+        int rc = dsm_pool_size(ctx, &cur);
+        if (rc != DSM_OK) return rc;
+        if (cur + n * ctx->S > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
+    }
+    const int W = ctx->p.width, H = ctx->p.height;
+    const size_t fpx = (size_t)H * W;
+    // two staging halves when they fit: the H2D copy of this run overlaps the kernels of the previous one
+    const bool dbl = 2 * n <= ctx->p.max_batch;
+    const int par = dbl ? (ctx->res_frame & 1) : 0;
+    ctx->res_frame++;
+    const int e = 6 + par; // events 6/7: this half's staging buffers and pinned tables are free again
+    CK(cudaEventSynchronize(ctx->ev_done[e]));
+    if (!dbl) CK(cudaEventSynchronize(ctx->ev_done[6 + (1 - par)]));
+    // single-frame calls (dsm_fuse_frame_resident) may still be running out of the same staging buffers
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[0], 0));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[1], 0));
+    const size_t so = (size_t)par * n;
+    for (int t = 0; t < n; t++)
+    {
+        memcpy(ctx->h_pose + (so + t) * 32, poses + (size_t)t * 16, 16 * sizeof(float));
+        inverse4f(poses + (size_t)t * 16, ctx->h_pose + (so + t) * 32 + 16);
+        ctx->h_ref[so + t] = ref_idx[t];
+    }
+    uint8_t *gp = ctx->gray_packed + so * fpx;
+    float *dp = ctx->depth_packed + so * fpx;
+    CK(cudaMemcpyAsync(gp, gray, (size_t)n * fpx, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(dp, depth, (size_t)n * fpx * sizeof(float), cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(ctx->ev_h2d[e], ctx->s_h2d));
+    cudaStream_t st = ctx->stream;
+    // the small tables go on the compute stream: the previous run's kernels read the same device tables
+    CK(cudaMemcpy2DAsync(ctx->pose, 16 * sizeof(float), ctx->h_pose + so * 32, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(ctx->ipose, 16 * sizeof(float), ctx->h_pose + so * 32 + 16, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->refidx, ctx->h_ref + so, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamWaitEvent(st, ctx->ev_h2d[e], 0));
+    {
+        DsmDev d = ctx->d;
+        d.frame0 = 0;
+        ProfScope p(ctx, DSM_K_REPACK);
+        dsm_launch_repack(d, n, gp, dp, st);
+    }
+    ctx->nb = n;
+    ctx->uploaded = true;
+    const int32_t *saved = ctx->d.poolofs;
+    // phase 1: all n frames at once (never touches the pool)
+    int rc = enqueue_schedule(ctx, 0, n, 0, st, false, 1);
+    // phase 2: frame by frame on the resident pool, compaction into the alternate buffer, swap
+    for (int t = 0; t < n && rc == DSM_OK; t++)
+    {
+        ctx->d.poolofs = ctx->res_ofs - t; // kernels read poolofs[b], poolofs[b+1] with b == t
+        int upq = (ctx->res_upper + 65535) / 65536 * 65536;
+        if (upq > ctx->p.max_local_surfels) upq = ctx->p.max_local_surfels;
+        rc = enqueue_schedule(ctx, t, 1, upq, st, true, 2);
+        if (rc != DSM_OK) break;
+        if (cudaMemcpyAsync(ctx->res_ofs + 1, ctx->newofs + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        {
+            rc = DSM_E_CUDA;
+            break;
+        }
+        dsm_surfel_t *tmp = ctx->d.pool;
+        ctx->d.pool = ctx->pool_snap;
+        ctx->pool_snap = tmp;
+        ctx->res_upper += ctx->S;
+    }
+    ctx->d.poolofs = saved;
+    if (rc != DSM_OK) return rc;
+    ctx->ran = true;
+    CK(cudaEventRecord(ctx->ev_done[e], st));
+    CK(cudaEventRecord(ctx->ev_done[0], st)); // dsm_fuse_frame_resident waits on these before reusing slot 0 / 1
+    CK(cudaEventRecord(ctx->ev_done[1], st));
+    CK(cudaGetLastError());
+    // the caller may reuse its image buffers as soon as we return
+    CK(cudaEventSynchronize(ctx->ev_h2d[e]));
+    if (n_new)
+    {
+        CK(cudaMemcpyAsync(n_new, ctx->d.nnew, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
     }
     return DSM_OK;
 }

@@ -177,6 +177,16 @@ int dsm_pool_upload(dsm_ctx *ctx, const dsm_surfel_t *local, int n_local);
 int dsm_fuse_frame_resident(dsm_ctx *ctx, int reference_frame_index,
                             const uint8_t *gray, size_t gray_pitch, const float *depth, size_t depth_pitch,
                             const float pose_colmajor[16], int *n_new);
+/* n consecutive frames of the SAME stream in one call (tightly packed [n][H][W] images, [n][16] poses): results are
+ * those of n calls of dsm_fuse_frame_resident (labels bit-identical; surfels bit-identical while n * seeds <= 20000,
+ * beyond that the plane fit switches to its large-batch kernel whose fp64 sums run in another order, ~1e-16
+ * relative), but the pose- and pool-independent stages (superpixels, normals, plane fit) of all n frames run as one
+ * batch; only fuse / initialise / compaction run frame by frame.  Trades
+ * n-1 frames of latency for throughput (offline sequences, or a node that lags behind its camera).  n <= max_batch;
+ * with 2n <= max_batch the copy of one run overlaps the kernels of the previous one.  n_new (optional, [n]) = new
+ * surfels per frame; passing it synchronises.  EXPERIMENTAL: added after round 1's GPU budget was spent. */
+int dsm_fuse_stream_resident(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_index,
+                             const uint8_t *gray, const float *depth, const float *poses_colmajor, int32_t *n_new);
 int dsm_pool_transform(dsm_ctx *ctx, const float W_colmajor[16]);
 int dsm_pool_retire(dsm_ctx *ctx, int keyframe_index, dsm_surfel_t *out, int cap, int *n_out);
 int dsm_pool_append(dsm_ctx *ctx, const dsm_surfel_t *surfels, int n);

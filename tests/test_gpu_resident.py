@@ -123,3 +123,42 @@ def test_pool_retire_and_append_move_add_surfels():
     after = ctx.pool_download()
     assert len(after) == len(pool) + 100 and after[len(pool):].tobytes() == got_out[:100].tobytes()
     ctx.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DSM_TEST_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: set DSM_TEST_UNVERIFIED=1 to run")
+@pytest.mark.parametrize("chunk", [1, 3, 4])
+def test_stream_chunks_equal_frame_by_frame(chunk):
+    """dsm_fuse_stream_resident (n frames per call) must leave exactly the pool that n calls of
+    dsm_fuse_frame_resident leave: same kernels, same order on the pool, only batched differently
+    (chunk * 4800 seeds <= 20000, so every chunk size here uses the same plane-fit kernel as a single frame)."""
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    T = 8
+    frames = []
+    for t in range(T):
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(cam, 600 + t, pose)
+        frames.append((t // 2, gray, depth, pose))
+    a = capi.Context(cam, max_batch=2, max_local_surfels=100000)
+    a.pool_upload(np.zeros(0, SURFEL_DTYPE))
+    counts_a = [a.fuse_frame_resident(r, g, d, p, want_count=True) for r, g, d, p in frames]
+    want = a.pool_download()
+    a.close()
+    b = capi.Context(cam, max_batch=8, max_local_surfels=100000)
+    b.pool_upload(np.zeros(0, SURFEL_DTYPE))
+    counts_b = []
+    for i in range(0, T, chunk):
+        part = frames[i:i + chunk]
+        c = b.fuse_stream_resident([f[0] for f in part], np.stack([f[1] for f in part]), np.stack([f[2] for f in part]),
+                                   np.stack([f[3] for f in part]), want_counts=True)
+        counts_b += list(c)
+    got = b.pool_download()
+    assert counts_b == counts_a
+    assert got.tobytes() == want.tobytes()
+    # mixing the two entry points on one context keeps working
+    r, g, d, p = frames[0]
+    b.fuse_frame_resident(9, g, d, p)
+    b.fuse_stream_resident([9, 9], np.stack([g, g]), np.stack([d, d]), np.stack([p, p]))
+    assert b.pool_size() > 0
+    b.close()
