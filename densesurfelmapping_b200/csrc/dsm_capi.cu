@@ -1112,7 +1112,7 @@ extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_
     // single-frame calls (dsm_fuse_frame_resident) may still be running out of the same staging buffers
     CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[0], 0));
     CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[1], 0));
-    const size_t so = (size_t)par * n;
+    const size_t so = (size_t)par * (size_t)(ctx->p.max_batch / 2); // fixed halves: runs of different length never overlap
     for (int t = 0; t < n; t++)
     {
         memcpy(ctx->h_pose + (so + t) * 32, poses + (size_t)t * 16, 16 * sizeof(float));
