@@ -292,6 +292,28 @@ def run_extras(cam, local_rank, stream):
     ctx.profile_enable(0)
     kn = capi.kernel_names()
     out["stream"]["kernel_us_per_frame"] = {kn[i]: round(float(pms[i]) / 6 * 1e3, 1) for i in range(len(kn)) if pn[i]}
+    # optional (round-2 experiment, off unless DSM_BENCH_STREAM_CHUNK=n): the same stream through
+    # dsm_fuse_stream_resident, n frames per call (pool-independent stages batched)
+    chunk = int(os.environ.get("DSM_BENCH_STREAM_CHUNK", "0") or 0)
+    if chunk > 0:
+        c2 = capi.Context(cam, max_batch=2 * chunk, max_local_surfels=4_000_000, device=local_rank, cuda_stream=stream.cuda_stream)
+        c2.pool_upload(np.zeros(0, SURFEL_DTYPE))
+        usable = (T // chunk) * chunk
+
+        def drive(rep):
+            for t in range(0, usable, chunk):
+                c2.fuse_stream_resident([(rep * T + t + i) // 4 for i in range(chunk)], hg[t:t + chunk], hd[t:t + chunk], Pz[t:t + chunk])
+        drive(0)
+        c2.sync()
+        e0.record()
+        for rep in range(1, 4):
+            drive(rep)
+        e1.record()
+        c2.sync()
+        msc = e0.elapsed_time(e1)
+        out["stream_chunked"] = {"frames_per_call": chunk, "frames_per_s": 3 * usable / (msc * 1e-3), "ms_per_frame": msc / (3 * usable),
+                                 "final_pool_surfels": c2.pool_size(), "api": "dsm_fuse_stream_resident (C ABI, pinned host frames)"}
+        c2.close()
     # loop-closure transform on a large pool
     n = 4_000_000
     rng = np.random.RandomState(7)
