@@ -2061,6 +2061,70 @@ __global__ void __launch_bounds__(1024) k_init_surfels(const __grid_constant__ D
     if (threadIdx.x == 0) d.nnew[b] = running;
 }
 
+// K6', EXPERIMENTAL (variant bit 4, off by default): initialize_surfels with several CTAs per frame.
+// k_init_surfels keeps the reference's seed-index output order with ONE 1024-thread CTA per frame (32 CTAs for a
+// 32-frame batch on 148 SMs, and a serial ~S/8192-round loop on a single frame's critical path).  Here CTA j owns
+// seeds [1024 j, 1024 j + 1024) and finds its output offset without any inter-CTA communication by re-evaluating
+// the cheap emit predicate over the seeds before its range (<= 36 B per seed, L2-resident), then scans its own
+// range.  Same predicate, same per-surfel arithmetic, same order: byte-identical output.
+__device__ __forceinline__ bool init_emits(const DsmDev &d, size_t so, int s)
+{
+    const float4 *pl = d.plane + (so + s) * 3;
+    const float4 r0 = pl[0];
+    const float md = pl[1].w;
+    return !(md == 0) && !d.fused[so + s] && !((double)r0.w < MAX_ANGLE_COS) && !(r0.x == 0 && r0.y == 0 && r0.z == 0);
+}
+__global__ void __launch_bounds__(1024) k_init_surfels_mb(const __grid_constant__ DsmDev d)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_before[32];
+    __shared__ float s_pose[16];
+    const int b = d.frame0 + blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t so = (size_t)b * d.S;
+    if (threadIdx.x < 16) s_pose[threadIdx.x] = d.pose[b * 16 + threadIdx.x];
+    const int first = blockIdx.x * 1024;
+    // emitted surfels before this CTA's range
+    int before = 0;
+    for (int s = threadIdx.x; s < first; s += 1024) before += init_emits(d, so, s) ? 1 : 0;
+    before = __reduce_add_sync(FULL, before);
+    const int s = first + threadIdx.x;
+    const bool e = s < d.S && init_emits(d, so, s);
+    const unsigned bal = __ballot_sync(FULL, e);
+    if (lane == 0)
+    {
+        s_warp[warp] = __popc(bal);
+        s_before[warp] = before;
+    }
+    __syncthreads();
+    int pos = 0, total = 0;
+    for (int w = 0; w < 32; w++)
+    {
+        const int c = s_warp[w];
+        pos += s_before[w] + (w < warp ? c : 0);
+        total += s_before[w] + c;
+    }
+    if (e)
+    {
+        pos += __popc(bal & ((1u << lane) - 1));
+        const float4 *pl = d.plane + (so + s) * 3;
+        const float4 r0 = pl[0], r1 = pl[1], r2 = pl[2];
+        float pw[4], nw[3];
+        mat4_mul(s_pose, r1.x, r1.y, r1.z, 1.0f, pw);
+        mat3_mul(s_pose, r0.x, r0.y, r0.z, nw);
+        dsm_surfel_t o;
+        o.px = pw[0], o.py = pw[1], o.pz = pw[2];
+        o.nx = nw[0], o.ny = nw[1], o.nz = nw[2];
+        o.size = (float)((double)r2.x * fabs((double)(r1.w / (d.camera_f * r0.w))));
+        o.color = r2.y;
+        o.weight = get_weight(r1.w);
+        o.update_times = 1;
+        o.last_update = d.refidx[b];
+        d.newsurf[so + pos] = o;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) d.nnew[b] = total;
+}
+
 // -------------------------------------------------------------------------------------------
 // GPU-resident pool: what SurfelMap does to `local_surfels` between and
 // after the hot-path calls, kept on the device so a stream never round-trips its pool.
@@ -2324,7 +2388,16 @@ void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s)
     dim3 grid((d.max_pool_per_frame + FUSE_BLOCK - 1) / FUSE_BLOCK, nb);
     k_fuse<<<grid, FUSE_BLOCK, 0, s>>>(d);
 }
-void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s) { k_init_surfels<<<nb, 1024, 0, s>>>(d); }
+void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s)
+{
+    if (d.variants & DSM_VARIANT_INIT_MULTIBLOCK)
+    {
+        dim3 grid((d.S + 1023) / 1024, nb);
+        k_init_surfels_mb<<<grid, 1024, 0, s>>>(d);
+        return;
+    }
+    k_init_surfels<<<nb, 1024, 0, s>>>(d);
+}
 void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, int raw_md, cudaStream_t s)
 {
     k_seeds_export<<<(d.S + 255) / 256, 256, 0, s>>>(d, frame, out_dev, raw_md);
