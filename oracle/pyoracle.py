@@ -238,6 +238,140 @@ def pcd_text(points):
     return "\n".join(head + body) + "\n"
 
 
+# ---- the reference's whole SurfelMap, compiled in place (oracle/ref_map_driver.cpp) ----
+def have_refmap(b200=False):
+    return os.path.exists(os.path.join(REFDIR, "libdsm_refmap_b200.so" if b200 else "libdsm_refmap.so"))
+
+
+def pose_to_ros7(pose_colmajor16):
+    """4x4 T_world<-cam (column-major, as the hot path takes it) -> the 7 numbers of a geometry_msgs::Pose
+    (position xyz, orientation xyzw), i.e. what the pose feed publishes."""
+    from scipy.spatial.transform import Rotation
+    T = np.asarray(pose_colmajor16, np.float64).reshape(4, 4).T
+    q = Rotation.from_matrix(T[:3, :3]).as_quat()  # x, y, z, w
+    return np.array([T[0, 3], T[1, 3], T[2, 3], q[0], q[1], q[2], q[3]], np.float64)
+
+
+class RefMap:
+    """SurfelMap of the reference (surfel_fusion/src/surfel_map.cpp) behind oracle/ref_map_driver.cpp.
+    b200=False: with the reference's own FusionFunctions (threads inlined: deterministic) -- the system-level oracle.
+    b200=True : the same SurfelMap holding the product's dsm::FusionFunctions (INTEGRATION.md's patch); needs a GPU."""
+
+    def __init__(self, cam, drift_free_poses=10, b200=False):
+        vp, ci, cf, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
+        self.lib = L = _lib("libdsm_refmap_b200.so" if b200 else "libdsm_refmap.so")
+        self.cam = cam
+        L.dsmmap_create.restype = vp
+        L.dsmmap_create.argtypes = [ci, ci, cf, cf, cf, cf, cf, cf, ci]
+        L.dsmmap_destroy.argtypes = [vp]
+        L.dsmmap_frame.argtypes = [vp, cd, vp, vp, vp, ci, ci, vp, ci, vp, ci]
+        for name in ("dsmmap_num_local", "dsmmap_num_poses", "dsmmap_num_inactive_points"):
+            getattr(L, name).argtypes = [vp]
+        L.dsmmap_get_local.argtypes = [vp, vp]
+        L.dsmmap_num_attached.argtypes = [vp, ci]
+        L.dsmmap_get_attached.argtypes = [vp, ci, vp]
+        L.dsmmap_get_inactive_points.argtypes = [vp, vp]
+        L.dsmmap_published_points.argtypes = [ctypes.c_char_p, vp, ci]
+        L.dsmmap_save_mesh.argtypes = [vp, ctypes.c_char_p]
+        L.dsmmap_save_cloud.argtypes = [vp, ctypes.c_char_p]
+        L.dsmmap_set_local.argtypes = [vp, vp, ci]
+        L.dsmmap_warp_active.argtypes = [vp, vp]
+        L.dsmmap_fuse_map.argtypes = [vp, vp, vp, vp, ci]
+        L.dsmmap_move_add_surfels.argtypes = [vp, ci]
+        L.dsmmap_publish_clouds.argtypes = [vp, ci]
+        L.dsmmap_local_pose_indexs.argtypes = [vp, vp, ci]
+        L.dsmmap_mesh_vertices.argtypes = [vp, vp, ci, vp]
+        self.h = L.dsmmap_create(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy, cam.far, cam.near, int(drift_free_poses))
+
+    def close(self):
+        if self.h:
+            self.lib.dsmmap_destroy(self.h)
+            self.h = None
+
+    def frame(self, stamp, gray, depth, pose7, is_keyframe, reference_index, path7=(), loops=()):
+        """One synchronised frame through the node's three callbacks (ros_node.cpp): pose feed, image, depth."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        path = np.ascontiguousarray(np.asarray(path7, np.float64).reshape(-1, 7))
+        lp = np.ascontiguousarray(np.asarray(loops, np.int32).reshape(-1))
+        self.lib.dsmmap_frame(self.h, float(stamp), gray.ctypes.data, depth.ctypes.data, pose7.ctypes.data, int(is_keyframe),
+                              int(reference_index), path.ctypes.data if len(path) else None, len(path),
+                              lp.ctypes.data if len(lp) else None, len(lp) // 2)
+
+    def local(self):
+        out = np.zeros(self.lib.dsmmap_num_local(self.h), SURFEL_DTYPE)
+        if len(out):
+            self.lib.dsmmap_get_local(self.h, out.ctypes.data)
+        return out
+
+    def num_poses(self):
+        return self.lib.dsmmap_num_poses(self.h)
+
+    def attached(self, pose):
+        out = np.zeros(self.lib.dsmmap_num_attached(self.h, pose), SURFEL_DTYPE)
+        if len(out):
+            self.lib.dsmmap_get_attached(self.h, pose, out.ctypes.data)
+        return out
+
+    def inactive_points(self):
+        out = np.zeros((self.lib.dsmmap_num_inactive_points(self.h), 4), np.float32)
+        if len(out):
+            self.lib.dsmmap_get_inactive_points(self.h, out.ctypes.data)
+        return out
+
+    def published(self, topic, cap=4_000_000):
+        """Last cloud on a topic ('active_pointcloud', 'inactive_pointcloud', 'pointcloud', 'neighbor_pointcloud',
+        or 'file:<path>' for what save_cloud handed to the PCD writer) as [n, 4] float32, None if never published."""
+        n = self.lib.dsmmap_published_points(topic.encode(), None, 0)
+        if n < 0:
+            return None
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self.lib.dsmmap_published_points(topic.encode(), out.ctypes.data, n)
+        return out[:n]
+
+    def local_pose_indexs(self):
+        out = np.zeros(4096, np.int32)
+        n = self.lib.dsmmap_local_pose_indexs(self.h, out.ctypes.data, len(out))
+        return out[:n].tolist()
+
+    def save_mesh(self, path):
+        self.lib.dsmmap_save_mesh(self.h, os.fsencode(path))
+
+    def save_cloud(self, path):
+        self.lib.dsmmap_save_cloud(self.h, os.fsencode(path))
+        return self.published("file:" + str(path))
+
+    # ---- the members one by one ----
+    def set_local(self, surfels):
+        s = np.ascontiguousarray(surfels, SURFEL_DTYPE)
+        self.lib.dsmmap_set_local(self.h, s.ctypes.data if len(s) else None, len(s))
+
+    def warp_active(self, W_colmajor):
+        w = np.ascontiguousarray(W_colmajor, np.float32).reshape(16)
+        self.lib.dsmmap_warp_active(self.h, w.ctypes.data)
+
+    def fuse_map(self, gray, depth, pose_colmajor16, reference_index):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        p = np.ascontiguousarray(pose_colmajor16, np.float32).reshape(16)
+        self.lib.dsmmap_fuse_map(self.h, gray.ctypes.data, depth.ctypes.data, p.ctypes.data, int(reference_index))
+
+    def move_add_surfels(self, reference_index):
+        self.lib.dsmmap_move_add_surfels(self.h, int(reference_index))
+
+    def publish_clouds(self, reference_index):
+        self.lib.dsmmap_publish_clouds(self.h, int(reference_index))
+
+    def mesh_vertices(self, surfels):
+        s = np.ascontiguousarray(surfels, SURFEL_DTYPE)
+        out = np.zeros((len(s), 6, 6), np.float32)
+        if len(s):
+            n = self.lib.dsmmap_mesh_vertices(self.h, s.ctypes.data, len(s), out.ctypes.data)
+            assert n == 36 * len(s)
+        return out
+
+
 def have_reference():
     return os.path.exists(os.path.join(REFDIR, "libdsm_ref_serial.so"))
 
