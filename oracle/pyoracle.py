@@ -289,13 +289,15 @@ class RefMap:
             self.h = None
 
     def frame(self, stamp, gray, depth, pose7, is_keyframe, reference_index, path7=(), loops=()):
-        """One synchronised frame through the node's three callbacks (ros_node.cpp): pose feed, image, depth."""
-        gray = np.ascontiguousarray(gray, np.uint8)
-        depth = np.ascontiguousarray(depth, np.float32)
+        """One synchronised frame through the node's three callbacks (ros_node.cpp): pose feed, image, depth
+        (gray=None: the pose feed callback only)."""
+        gray = None if gray is None else np.ascontiguousarray(gray, np.uint8)
+        depth = None if depth is None else np.ascontiguousarray(depth, np.float32)
         pose7 = np.ascontiguousarray(pose7, np.float64)
         path = np.ascontiguousarray(np.asarray(path7, np.float64).reshape(-1, 7))
         lp = np.ascontiguousarray(np.asarray(loops, np.int32).reshape(-1))
-        self.lib.dsmmap_frame(self.h, float(stamp), gray.ctypes.data, depth.ctypes.data, pose7.ctypes.data, int(is_keyframe),
+        self.lib.dsmmap_frame(self.h, float(stamp), None if gray is None else gray.ctypes.data,
+                              None if depth is None else depth.ctypes.data, pose7.ctypes.data, int(is_keyframe),
                               int(reference_index), path.ctypes.data if len(path) else None, len(path),
                               lp.ctypes.data if len(lp) else None, len(lp) // 2)
 

@@ -92,6 +92,7 @@ extern "C"
         od->pose.covariance[0] = is_keyframe ? 1.0 : 0.0;
         od->pose.covariance[1] = (double)reference_index;
         r->map->orb_results_input(ls, path, od);
+        if (!gray || !depth) return; // pose feed only (lets a test look at the state between the callbacks)
         r->map->image_input(make_image(stamp, W, H, gray, false));
         r->map->depth_input(make_image(stamp, W, H, depth, true));
     }

@@ -119,6 +119,50 @@ def test_move_add_surfels_and_cloud_builders_are_pinned(tmp_path):
     m.close()
 
 
+def ros7_to_matrix(p7):
+    from scipy.spatial.transform import Rotation
+    T = np.eye(4)
+    T[:3, :3] = Rotation.from_quat(p7[3:7]).as_matrix()
+    T[:3, 3] = p7[:3]
+    return T
+
+
+def test_loop_closure_warps_the_active_surfels():
+    """A corrected loop path arrives on the pose feed: orb_results_input -> warp_surfels (surfel_map.cpp:795-824) moves
+    every active surfel by W = T_loop * T_cam^-1 of the oldest local keyframe.  Checks the restated warp (and the W
+    the product's dsm_pool_transform is handed) against the node's own state, in the node's re-based world frame."""
+    m = pyoracle.RefMap(CAM, drift_free_poses=10)
+    drive(m, 4)
+    before = m.local()
+    path = [pyoracle.pose_to_ros7(synth.pose_stream(t)) for t in range(4)]
+    a = np.deg2rad(1.5)
+    C = np.eye(4)   # the correction the loop closure applies to every keyframe
+    C[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+    C[:3, 3] = [0.3, 0.0, -0.2]
+    from scipy.spatial.transform import Rotation
+    corrected = []
+    for p7 in path:
+        T = C @ ros7_to_matrix(p7)
+        q = Rotation.from_matrix(T[:3, :3]).as_quat()
+        corrected.append(np.concatenate([T[:3, 3], q]))
+    pose4 = pyoracle.pose_to_ros7(synth.pose_stream(4))
+    m.frame(100.4, None, None, pose4, True, 3, path7=np.array(corrected))   # pose feed only: no fuse after the warp
+    after = m.local()
+    assert len(after) == len(before)
+    # the node re-bases the world with K = idea * T_first^-1 (surfel_map.cpp:214-232); in that frame W = K C K^-1
+    idea = np.zeros((4, 4))
+    idea[0, 0], idea[1, 2], idea[2, 1], idea[3, 3] = 1.0, 1.0, -1.0, 1.0
+    K = idea @ np.linalg.inv(ros7_to_matrix(path[0]))
+    Wm = K @ C @ np.linalg.inv(K)
+    w = np.ascontiguousarray(Wm.T.astype(np.float32).reshape(16))
+    want = pyoracle.warp_active(before, w)
+    e = pyoracle.surfel_errors(after, want)
+    assert e["pos"] < 2e-5 and e["nrm"] < 2e-5 and e["int_mismatch"] == 0, e
+    moved = np.abs(after["px"] - before["px"]).max()
+    assert moved > 0.05, "the loop correction did not move anything"
+    m.close()
+
+
 def test_product_mesh_writer_equals_reference_save_mesh(tmp_path):
     """dsm_write_ply_mesh / dsm_mesh_vertices (product, host code) against SurfelMap::save_mesh / push_a_surfel of the
     reference compiled in place: byte-identical file, bit-identical vertices."""
