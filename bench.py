@@ -314,6 +314,28 @@ def run_extras(cam, local_rank, stream):
         out["stream_chunked"] = {"frames_per_call": chunk, "frames_per_s": 3 * usable / (msc * 1e-3), "ms_per_frame": msc / (3 * usable),
                                  "final_pool_surfels": c2.pool_size(), "api": "dsm_fuse_stream_resident (C ABI, pinned host frames)"}
         c2.close()
+    # optional (round-2 experiment, off unless DSM_BENCH_NODE=1): the reference's own SurfelMap node logic, compiled
+    # in place with the product's adapter under it (oracle/_ref/libdsm_refmap_b200.so, INTEGRATION.md's three-line
+    # patch): frames/s of the whole node callback chain on the KITTI-shaped stream
+    if os.environ.get("DSM_BENCH_NODE") == "1":
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle"))
+        import pyoracle
+        if pyoracle.have_refmap(b200=True):
+            node = pyoracle.RefMap(cam, drift_free_poses=10, b200=True)
+            path, t0 = [], None
+            for t in range(T):
+                if t == warm:
+                    t0 = time.perf_counter()
+                p7 = pyoracle.pose_to_ros7(Pz[t])
+                node.frame(10.0 + 0.1 * t, hg[t], hd[t], p7, t % 4 == 0, max(len(path) - 1, 0), path7=np.array(path).reshape(-1, 7))
+                if t % 4 == 0:
+                    path.append(p7)
+            dt = time.perf_counter() - t0
+            out["reference_node_over_product"] = {"frames_per_s": (T - warm) / dt, "ms_per_frame": dt / (T - warm) * 1e3,
+                                                  "local_surfels": len(node.local()),
+                                                  "what": "unmodified surfel_map.cpp callbacks (pose feed, image, depth) with dsm::FusionFunctions "
+                                                          "in place of FusionFunctions; host-pointer dsm_fuse_frame per frame, wall clock"}
+            node.close()
     # loop-closure transform on a large pool
     n = 4_000_000
     rng = np.random.RandomState(7)
