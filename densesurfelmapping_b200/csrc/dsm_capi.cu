@@ -61,6 +61,8 @@ struct dsm_ctx
     int *blkcnt, *blkofs, *newofs;
     float *wmat;        // device copy of the 4x4 of dsm_pool_transform
     cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
+    cudaStream_t s_fork[5];              // experimental (variant bit 5): side stream per compute stream for the forked pixel-normal pass
+    cudaEvent_t ev_fork_a[5], ev_fork_b[5];
     // pinned host staging for the small per-batch tables
     float *h_pose; // [B][32]: pose then inverse
     int32_t *h_ofs;
@@ -184,12 +186,20 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    for (int i = 0; i < 5; i++)
+    {
+        if (ctx->s_fork[i]) cudaStreamSynchronize(ctx->s_fork[i]), cudaStreamDestroy(ctx->s_fork[i]);
+        if (ctx->ev_fork_a[i]) cudaEventDestroy(ctx->ev_fork_a[i]);
+        if (ctx->ev_fork_b[i]) cudaEventDestroy(ctx->ev_fork_b[i]);
+    }
     cudaFreeHost(ctx->h_pose);
     cudaFreeHost(ctx->h_ofs);
     cudaFreeHost(ctx->h_ref);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+static int ensure_fork_streams(dsm_ctx *ctx);
 
 extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_stream, dsm_ctx **out)
 {
@@ -226,6 +236,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->s_h2d = ctx->s_d2h = nullptr;
     for (int i = 0; i < 4; i++) ctx->s_comp[i] = nullptr;
     ctx->ev_start = nullptr;
+    for (int i = 0; i < 5; i++) ctx->s_fork[i] = nullptr, ctx->ev_fork_a[i] = ctx->ev_fork_b[i] = nullptr;
     for (int i = 0; i < 8; i++) ctx->ev_h2d[i] = ctx->ev_done[i] = nullptr;
     ctx->gray_packed = nullptr;
     ctx->res_upper = 0;
@@ -335,6 +346,11 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     d.max_pool_per_frame = 0;
     d.variants = 0;
     if (const char *ev = getenv("DSM_EXPERIMENTAL_VARIANTS")) d.variants = (int)strtol(ev, nullptr, 0); // see dsm_debug_set_variants
+    if ((d.variants & DSM_VARIANT_NORMALS_FORK) && ensure_fork_streams(ctx) != DSM_OK)
+    {
+        dsm_destroy(ctx);
+        return DSM_E_CUDA;
+    }
     *out = ctx;
     return DSM_OK;
 }
@@ -529,6 +545,18 @@ extern "C" int dsm_batch_restore_pool(dsm_ctx *ctx)
     return DSM_OK;
 }
 
+// side streams / events of the forked pixel-normal pass; created outside any stream capture
+static int ensure_fork_streams(dsm_ctx *ctx)
+{
+    for (int i = 0; i < 5; i++)
+    {
+        if (!ctx->s_fork[i]) CK(cudaStreamCreateWithFlags(&ctx->s_fork[i], cudaStreamNonBlocking));
+        if (!ctx->ev_fork_a[i]) CK(cudaEventCreateWithFlags(&ctx->ev_fork_a[i], cudaEventDisableTiming));
+        if (!ctx->ev_fork_b[i]) CK(cudaEventCreateWithFlags(&ctx->ev_fork_b[i], cudaEventDisableTiming));
+    }
+    return DSM_OK;
+}
+
 // The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79),
 // enqueued for the frame slots [f0, f0 + nf).
 // phase bit 0: the pose- and pool-independent part (superpixels, pixel normals, plane fit); bit 1: fuse + initialise.
@@ -544,6 +572,27 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
     {                                   \
         ProfScope p(ctx, ID, st);       \
         CALL;                           \
+    }
+    // EXPERIMENTAL (variant bit 5): the pixel-normal pass depends on the depth image only, so it is
+    // forked onto a side stream at the start of the schedule and joined before the plane-fit gather; it then fills
+    // the SMs that the one-CTA-per-frame kernels (relax, seed init) and the latency-bound per-seed kernels leave idle.
+    int fk = -1;
+    if ((d.variants & DSM_VARIANT_NORMALS_FORK) && (phase & 1) && ctx->stop_after <= 0)
+    {
+        fk = 4;
+        for (int i = 0; i < 4; i++)
+            if (st == ctx->s_comp[i]) fk = i;
+        if (!ctx->s_fork[fk] || !ctx->ev_fork_a[fk] || !ctx->ev_fork_b[fk]) fk = -1; // created by ensure_fork_streams()
+    }
+    if (fk >= 0)
+    {
+        CK(cudaEventRecord(ctx->ev_fork_a[fk], st));
+        CK(cudaStreamWaitEvent(ctx->s_fork[fk], ctx->ev_fork_a[fk], 0));
+        {
+            ProfScope p(ctx, DSM_K_PIXEL_NORMALS, ctx->s_fork[fk]);
+            dsm_launch_pixel_normals(d, nb, ctx->s_fork[fk]);
+        }
+        CK(cudaEventRecord(ctx->ev_fork_b[fk], ctx->s_fork[fk]));
     }
     if (phase & 1)
     {
@@ -562,7 +611,14 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
         STEP(DSM_K_GATHER_DEPTHS, dsm_launch_gather_depths(d, nb, st));
         STEP(DSM_K_NEWTON, dsm_launch_newton(d, nb, st));
     }
-    STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
+    if (fk >= 0)
+    {
+        CK(cudaStreamWaitEvent(st, ctx->ev_fork_b[fk], 0));
+    }
+    else
+    {
+        STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
+    }
     STEP(DSM_K_GATHER_POINTS, dsm_launch_gather_points(d, nb, st));
     STEP(DSM_K_GAUSS_NEWTON, dsm_launch_gauss_newton(d, nb, st));
     }
@@ -670,6 +726,7 @@ extern "C" int dsm_debug_set_variants(dsm_ctx *ctx, unsigned mask)
     for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.exec); // captured schedules embed the kernel choice
     ctx->graphs.clear();
     ctx->d.variants = (int)mask;
+    if (mask & DSM_VARIANT_NORMALS_FORK) return ensure_fork_streams(ctx);
     return DSM_OK;
 }
 
