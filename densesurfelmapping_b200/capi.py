@@ -27,6 +27,8 @@ EXPORTS = [
     "dsm_pool_transform", "dsm_pool_retire", "dsm_pool_append", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
     "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices", "dsm_debug_set_variants", "dsm_fuse_stream_resident",
+    "dsm_inactive_reserve", "dsm_inactive_retire", "dsm_inactive_reactivate", "dsm_inactive_transform", "dsm_inactive_export_cloud",
+    "dsm_inactive_download", "dsm_inactive_size",
 ]
 
 
@@ -80,6 +82,13 @@ def load_library():
     L.dsm_fuse_frame_resident.argtypes = [vp, ci, vp, cs, vp, cs, vp, ctypes.POINTER(ci)]
     L.dsm_pool_transform.argtypes = [vp, vp]
     L.dsm_fuse_stream_resident.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+    L.dsm_inactive_reserve.argtypes = [vp, ci]
+    L.dsm_inactive_retire.argtypes = [vp, ci, ctypes.POINTER(ci)]
+    L.dsm_inactive_reactivate.argtypes = [vp, ci, ctypes.POINTER(ci)]
+    L.dsm_inactive_transform.argtypes = [vp, ci, vp]
+    L.dsm_inactive_export_cloud.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
+    L.dsm_inactive_download.argtypes = [vp, ci, vp, ci, ctypes.POINTER(ci)]
+    L.dsm_inactive_size.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     L.dsm_pool_retire.argtypes = [vp, ci, vp, ci, ctypes.POINTER(ci)]
     L.dsm_pool_append.argtypes = [vp, vp, ci]
     L.dsm_pool_size.argtypes = [vp, ctypes.POINTER(ci)]
@@ -254,6 +263,43 @@ class Context:
         out = np.zeros(max(cap, 1), dtype=dtype)
         n = ctypes.c_int(0)
         self._ck(fn(self.h, int(min_update_times), _ptr(out), cap, ctypes.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    # ---- inactive store (experimental) ----
+    def inactive_reserve(self, n):
+        self._ck(self.lib.dsm_inactive_reserve(self.h, int(n)))
+
+    def inactive_retire(self, keyframe_index):
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_inactive_retire(self.h, int(keyframe_index), ctypes.byref(n)))
+        return n.value
+
+    def inactive_reactivate(self, keyframe_index):
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_inactive_reactivate(self.h, int(keyframe_index), ctypes.byref(n)))
+        return n.value
+
+    def inactive_transform(self, keyframe_index, W_colmajor):
+        w = np.ascontiguousarray(W_colmajor, dtype=np.float32).reshape(16)
+        self._ck(self.lib.dsm_inactive_transform(self.h, int(keyframe_index), _ptr(w)))
+
+    def inactive_size(self):
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        self._ck(self.lib.dsm_inactive_size(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def inactive_download(self, keyframe_index=-1):
+        cap = self.inactive_size()[0]
+        out = np.zeros(max(cap, 1), dtype=SURFEL_DTYPE)
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_inactive_download(self.h, int(keyframe_index), _ptr(out), cap, ctypes.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    def inactive_export_cloud(self):
+        cap = self.inactive_size()[0]
+        out = np.zeros(max(cap, 1), dtype=POINT_DTYPE)
+        n = ctypes.c_int(0)
+        self._ck(self.lib.dsm_inactive_export_cloud(self.h, _ptr(out), cap, ctypes.byref(n)))
         return out[:min(n.value, cap)].copy()
 
     # ---- parity readback ----

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cstdint>
 #include <new>
 #include <vector>
 
@@ -60,6 +61,16 @@ struct dsm_ctx
     int32_t *res_ofs;   // device [2]: {0, resident pool size}
     int *blkcnt, *blkofs, *newofs;
     float *wmat;        // device copy of the 4x4 of dsm_pool_transform
+    // inactive store (EXPERIMENTAL, dsm_inactive_*): the attached_surfels of every pose outside the drift-free window,
+    // dense on the device in retirement order; the (keyframe, offset, count) segment list lives on the host
+    dsm_surfel_t *inact;
+    int inact_cap, inact_size;
+    int32_t *inact_ofs; // device [2]
+    struct InactSeg
+    {
+        int kf, ofs, cnt;
+    };
+    std::vector<InactSeg> inact_segs;
     cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
     cudaStream_t s_fork[5];              // experimental (variant bit 5): side stream per compute stream for the forked pixel-normal pass
     cudaEvent_t ev_fork_a[5], ev_fork_b[5];
@@ -174,6 +185,8 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(ctx->blkofs);
     cudaFree(ctx->newofs);
     cudaFree(ctx->wmat);
+    cudaFree(ctx->inact);
+    cudaFree(ctx->inact_ofs);
     cudaFree(ctx->res_ofs);
     cudaFree(ctx->depth_packed);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -245,6 +258,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->res_ofs = nullptr;
     ctx->blkcnt = ctx->blkofs = ctx->newofs = nullptr;
     ctx->wmat = nullptr;
+    ctx->inact = nullptr, ctx->inact_ofs = nullptr, ctx->inact_cap = ctx->inact_size = 0;
     ctx->depth_packed = nullptr;
     ctx->own_stream = (cuda_stream == nullptr);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -1135,6 +1149,182 @@ extern "C" int dsm_fuse_frame_resident(dsm_ctx *ctx, int ref_idx, const uint8_t 
         CK(cudaStreamSynchronize(ctx->stream));
         *n_new = c;
     }
+    return DSM_OK;
+}
+
+// ---- inactive store (EXPERIMENTAL) ----
+// What SurfelMap keeps per pose in attached_surfels / inactive_pointcloud (surfel_map.cpp:1479-1497, :1583-1587,
+// :681-748), resident on the device.  Only host orchestration over the pool kernels: retirement is the ordered
+// compaction of dsm_pool_retire writing straight into the store, the per-pose warp is k_pool_transform over one
+// segment, the inactive cloud is k_pool_scatter_cloud over the store.
+static DsmDev inactive_view(dsm_ctx *ctx)
+{
+    DsmDev d = ctx->d;
+    d.frame0 = 0;
+    d.pool = ctx->inact;
+    d.poolofs = ctx->inact_ofs; // {first, last} of the range a call works on, set in stream order by k_set2
+    return d;
+}
+
+extern "C" int dsm_inactive_reserve(dsm_ctx *ctx, int max_inactive_surfels)
+{
+    if (!ctx || max_inactive_surfels < 1) return DSM_E_INVALID;
+    if (ctx->inact_size > 0) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->inact);
+    ctx->inact = nullptr;
+    ctx->inact_cap = 0;
+    if (!ctx->inact_ofs && dmalloc(&ctx->inact_ofs, 2) != cudaSuccess) return DSM_E_NOMEM;
+    if (dmalloc(&ctx->inact, (size_t)max_inactive_surfels) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return DSM_E_NOMEM;
+    }
+    ctx->inact_cap = max_inactive_surfels;
+    ctx->inact_segs.clear();
+    return DSM_OK;
+}
+
+extern "C" int dsm_inactive_size(dsm_ctx *ctx, int *n_surfels, int *n_segments)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (n_surfels) *n_surfels = ctx->inact_size;
+    if (n_segments) *n_segments = (int)ctx->inact_segs.size();
+    return DSM_OK;
+}
+
+// move_add_surfels, removal loop: local surfels last updated by keyframe kf -> a new segment of the store
+extern "C" int dsm_inactive_retire(dsm_ctx *ctx, int kf, int *n_moved)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (!ctx->res_active || !ctx->inact) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int cur = 0;
+    int rc = dsm_pool_size(ctx, &cur); // exact pool size: bounds the segment
+    if (rc != DSM_OK) return rc;
+    if (ctx->inact_size + cur > ctx->inact_cap) return DSM_E_CAPACITY;
+    dsm_launch_pool_retire(resident_view(ctx, 0), 0, ctx->res_upper, kf, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->inact + ctx->inact_size, ctx->stream);
+    int32_t h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->newofs, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (h[0] > 0)
+    {
+        ctx->inact_segs.push_back(dsm_ctx::InactSeg{kf, ctx->inact_size, h[0]});
+        ctx->inact_size += h[0];
+    }
+    if (n_moved) *n_moved = h[0];
+    return DSM_OK;
+}
+
+// move_add_surfels, insertion: the pose re-enters the drift-free window, its surfels go back to the end of the pool
+extern "C" int dsm_inactive_reactivate(dsm_ctx *ctx, int kf, int *n_moved)
+{
+    if (!ctx) return DSM_E_INVALID;
+    if (!ctx->res_active || !ctx->inact) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int total = 0;
+    for (const auto &sg : ctx->inact_segs)
+        if (sg.kf == kf) total += sg.cnt;
+    if (n_moved) *n_moved = total;
+    if (total == 0) return DSM_OK;
+    int cur = 0;
+    int rc = dsm_pool_size(ctx, &cur);
+    if (rc != DSM_OK) return rc;
+    if (cur + total > ctx->p.max_local_surfels) return DSM_E_CAPACITY;
+    cudaStream_t st = ctx->stream;
+    const int npool = ctx->p.max_local_surfels > 0 ? ctx->p.max_local_surfels : 1;
+    for (size_t i = 0; i < ctx->inact_segs.size();)
+    {
+        const dsm_ctx::InactSeg sg = ctx->inact_segs[i];
+        if (sg.kf != kf)
+        {
+            i++;
+            continue;
+        }
+        CK(cudaMemcpyAsync(ctx->d.pool + cur, ctx->inact + sg.ofs, (size_t)sg.cnt * sizeof(dsm_surfel_t), cudaMemcpyDeviceToDevice, st));
+        cur += sg.cnt;
+        // close the gap: move the tail down through the alternate pool buffer (free between frames), chunk by chunk
+        int src = sg.ofs + sg.cnt;
+        const int end = ctx->inact_size;
+        while (src < end)
+        {
+            const int len = (end - src) < npool ? (end - src) : npool;
+            CK(cudaMemcpyAsync(ctx->pool_snap, ctx->inact + src, (size_t)len * sizeof(dsm_surfel_t), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(ctx->inact + src - sg.cnt, ctx->pool_snap, (size_t)len * sizeof(dsm_surfel_t), cudaMemcpyDeviceToDevice, st));
+            src += len;
+        }
+        ctx->inact_size -= sg.cnt;
+        ctx->inact_segs.erase(ctx->inact_segs.begin() + (long)i);
+        for (size_t j = i; j < ctx->inact_segs.size(); j++) ctx->inact_segs[j].ofs -= sg.cnt;
+    }
+    dsm_launch_set2(ctx->res_ofs, 0, cur, st);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->res_upper = cur;
+    return DSM_OK;
+}
+
+// warp_inactive_surfels_cpu_kernel for ONE pose (surfel_map.cpp:704-733): p <- W p, n <- R_W n over its segment(s),
+// W = (T_loop * T_cam^-1) computed by the caller in fp64 and cast to float, column-major.  Asynchronous.
+extern "C" int dsm_inactive_transform(dsm_ctx *ctx, int kf, const float Wm[16])
+{
+    if (!ctx || !Wm) return DSM_E_INVALID;
+    if (!ctx->inact) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    bool first = true;
+    for (const auto &sg : ctx->inact_segs)
+    {
+        if (sg.kf != kf) continue;
+        if (first) CK(cudaMemcpyAsync(ctx->wmat, Wm, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        first = false;
+        dsm_launch_set2(ctx->inact_ofs, sg.ofs, sg.ofs + sg.cnt, ctx->stream);
+        dsm_launch_pool_transform(inactive_view(ctx), 0, sg.cnt, ctx->wmat, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    return DSM_OK;
+}
+
+// attached_surfels of one pose (kf >= 0) or of every pose in store order (kf < 0), e.g. for save_mesh
+extern "C" int dsm_inactive_download(dsm_ctx *ctx, int kf, dsm_surfel_t *out, int cap, int *n_out)
+{
+    if (!ctx || !n_out || cap < 0 || (cap > 0 && !out)) return DSM_E_INVALID;
+    if (!ctx->inact) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int n = 0;
+    for (const auto &sg : ctx->inact_segs)
+    {
+        if (kf >= 0 && sg.kf != kf) continue;
+        const int c = (n + sg.cnt <= cap) ? sg.cnt : (cap > n ? cap - n : 0);
+        if (c > 0) CK(cudaMemcpyAsync(out + n, ctx->inact + sg.ofs, (size_t)c * sizeof(dsm_surfel_t), cudaMemcpyDeviceToHost, ctx->stream));
+        n += sg.cnt;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return DSM_OK;
+}
+
+// inactive_pointcloud (publish_inactive_pointcloud surfel_map.cpp:1385-1396, the tail of publish_all_pointcloud and
+// save_cloud): one PointXYZI per stored surfel, store order
+extern "C" int dsm_inactive_export_cloud(dsm_ctx *ctx, dsm_point_t *out, int cap, int *n_out)
+{
+    if (!ctx || !n_out || cap < 0 || (cap > 0 && !out)) return DSM_E_INVALID;
+    if (!ctx->inact) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    *n_out = ctx->inact_size;
+    const int want = ctx->inact_size < cap ? ctx->inact_size : cap;
+    const int npool = ctx->p.max_local_surfels > 0 ? ctx->p.max_local_surfels : 1;
+    const DsmDev d = inactive_view(ctx);
+    for (int c0 = 0; c0 < want; c0 += npool)
+    { // chunks sized for the block tables and the alternate pool buffer (16-byte points into 44-byte slots)
+        const int len = (want - c0) < npool ? (want - c0) : npool;
+        dsm_launch_set2(ctx->inact_ofs, c0, c0 + len, ctx->stream);
+        dsm_launch_pool_export(d, 0, len, 2, INT32_MIN, true, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
+        CK(cudaMemcpyAsync(out + c0, ctx->pool_snap, (size_t)len * sizeof(dsm_point_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
     return DSM_OK;
 }
 

@@ -2278,6 +2278,14 @@ __global__ void __launch_bounds__(XF_BLOCK) k_pool_transform(const __grid_consta
     stage_out(g, sm, cnt, bulk, XF_BLOCK);
 }
 
+// two-entry offset table {a, b} written in stream order (the pool kernels take their range from device memory)
+__global__ void k_set2(int32_t *p, int a, int b)
+{
+    p[0] = a;
+    p[1] = b;
+}
+void dsm_launch_set2(int32_t *p, int a, int b, cudaStream_t s) { k_set2<<<1, 1, 0, s>>>(p, a, b); }
+
 // -------------------------------------------------------------------------------------------
 // parity readback: rebuild the reference's 60-byte Superpixel_seed records for one frame
 // -------------------------------------------------------------------------------------------

@@ -222,6 +222,28 @@ int dsm_write_pcd(const char *path, const dsm_point_t *points, size_t n, int bin
 int dsm_write_ply_mesh(const char *path, const dsm_surfel_t *surfels, size_t n);
 int dsm_mesh_vertices(const dsm_surfel_t *surfels, size_t n, float *vertices36);
 
+/* ---- inactive store (EXPERIMENTAL: written after round 1's GPU budget was spent) ----
+ * What SurfelMap keeps per pose outside the drift-free window -- PoseElement::attached_surfels and the mirror
+ * inactive_pointcloud (surfel_map.h:36-46) -- resident on the device next to the local pool, so that
+ * move_add_surfels and the loop-closure warp of the inactive surfels never cross PCIe.  Host orchestration over the
+ * pool kernels; segments are kept dense in retirement order.
+ *   dsm_inactive_reserve      capacity in surfels (once, while the store is empty)
+ *   dsm_inactive_retire       move_add_surfels removal loop (surfel_map.cpp:1479-1497): local surfels with
+ *                             update_times > 0 and last_update == keyframe_index become that pose's segment (pool
+ *                             order) and are flagged dead in the pool.  Synchronises; *n_moved optional.
+ *   dsm_inactive_reactivate   insertion (surfel_map.cpp:1583-1587): the pose's segment returns to the end of the pool
+ *   dsm_inactive_transform    warp_inactive_surfels_cpu_kernel for one pose (surfel_map.cpp:704-733), asynchronous
+ *   dsm_inactive_export_cloud inactive_pointcloud as the node publishes / saves it (store order)
+ *   dsm_inactive_download     attached_surfels of one pose (keyframe_index >= 0) or of all poses (< 0; save_mesh)
+ *   dsm_inactive_size         surfels / segments currently stored */
+int dsm_inactive_reserve(dsm_ctx *ctx, int max_inactive_surfels);
+int dsm_inactive_retire(dsm_ctx *ctx, int keyframe_index, int *n_moved);
+int dsm_inactive_reactivate(dsm_ctx *ctx, int keyframe_index, int *n_moved);
+int dsm_inactive_transform(dsm_ctx *ctx, int keyframe_index, const float W_colmajor[16]);
+int dsm_inactive_export_cloud(dsm_ctx *ctx, dsm_point_t *out, int cap, int *n_out);
+int dsm_inactive_download(dsm_ctx *ctx, int keyframe_index, dsm_surfel_t *out, int cap, int *n_out);
+int dsm_inactive_size(dsm_ctx *ctx, int *n_surfels, int *n_segments);
+
 /* ---- parity / debug readback (what the reference keeps private: fusion_functions.h:34-37) ---- */
 int dsm_get_labels(dsm_ctx *ctx, int frame, int32_t *labels_hw);   /* superpixel_index, [H][W] */
 int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds_s);   /* superpixel_seeds, [S] */

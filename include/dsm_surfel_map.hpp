@@ -171,6 +171,62 @@ class ResidentSurfelPool
         return report("save_mesh");
     }
 
+    // ---- device-resident attached_surfels / inactive_pointcloud (EXPERIMENTAL, see include/dsm.h "inactive store") ----
+    // Call reserve_inactive() once after initialize(); then the removal / insertion halves of move_add_surfels and the
+    // per-pose inactive warp never move surfels across PCIe.
+    int reserve_inactive(int max_inactive_surfels)
+    {
+        if (!ready("reserve_inactive")) return err_;
+        err_ = dsm_inactive_reserve(ctx_, max_inactive_surfels);
+        return report("reserve_inactive");
+    }
+    // move_add_surfels(), removal (surfel_map.cpp:1479-1497) without the host copy; returns the surfel count or -1
+    int retire_surfels_resident(int inactive_index)
+    {
+        if (!ready("retire_surfels_resident")) return -1;
+        int n = 0;
+        err_ = dsm_inactive_retire(ctx_, inactive_index, &n);
+        return report("retire_surfels_resident") == DSM_OK ? n : -1;
+    }
+    // move_add_surfels(), insertion (surfel_map.cpp:1583-1587)
+    int add_surfels_resident(int pose_index)
+    {
+        if (!ready("add_surfels_resident")) return -1;
+        int n = 0;
+        err_ = dsm_inactive_reactivate(ctx_, pose_index, &n);
+        return report("add_surfels_resident") == DSM_OK ? n : -1;
+    }
+    // warp_inactive_surfels_cpu_kernel for one pose (surfel_map.cpp:704-733): warp_matrix = (after * pre^-1).cast<float>()
+    template <class Mat4f>
+    int warp_inactive_surfels(int pose_index, Mat4f &warp_matrix)
+    {
+        if (!ready("warp_inactive_surfels")) return err_;
+        err_ = dsm_inactive_transform(ctx_, pose_index, warp_matrix.data());
+        return report("warp_inactive_surfels");
+    }
+    // inactive_pointcloud appended to `points` (publish_inactive_pointcloud / publish_all_pointcloud / save_cloud)
+    template <class Point>
+    int inactive_points(std::vector<Point> &points)
+    {
+        if (!ready("inactive_points")) return err_;
+        int n = 0;
+        err_ = dsm_inactive_size(ctx_, &n, nullptr);
+        if (err_ != DSM_OK) return report("inactive_points");
+        scratch_.resize((size_t)(n > 0 ? n : 1));
+        int got = 0;
+        err_ = dsm_inactive_export_cloud(ctx_, scratch_.data(), n, &got);
+        if (err_ != DSM_OK) return report("inactive_points");
+        points.reserve(points.size() + (size_t)got);
+        for (int i = 0; i < got; i++)
+        {
+            Point p;
+            p.x = scratch_[(size_t)i].x, p.y = scratch_[(size_t)i].y, p.z = scratch_[(size_t)i].z;
+            p.intensity = scratch_[(size_t)i].intensity;
+            points.push_back(p);
+        }
+        return DSM_OK;
+    }
+
     // local_surfels as a host vector (debugging, or a caller that still wants the whole pool)
     template <class Surfel>
     int download(std::vector<Surfel> &local_surfels)

@@ -162,3 +162,50 @@ def test_stream_chunks_equal_frame_by_frame(chunk):
     b.fuse_stream_resident([9, 9], np.stack([g, g]), np.stack([d, d]), np.stack([p, p]))
     assert b.pool_size() > 0
     b.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DSM_TEST_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: set DSM_TEST_UNVERIFIED=1 to run")
+def test_inactive_store_round_trip():
+    """Device-resident attached_surfels: retire two keyframes into the store, warp one of them, publish the inactive
+    cloud, bring one back -- against the restated (and reference-pinned, tests/test_refmap.py) SurfelMap members."""
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    orc = oracle_for(cam)
+    pool = np.zeros(0, SURFEL_DTYPE)
+    for t in range(3):
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(cam, 500 + t, pose)
+        lo, no = orc.fuse(t, gray, depth, pose, pool)
+        pool = pyoracle.fuse_map_poststep(lo, no)
+    ctx = capi.Context(cam, max_batch=2, max_local_surfels=len(pool) + 5000)
+    ctx.pool_upload(pool)
+    ctx.inactive_reserve(3 * len(pool))
+    loc1, out1 = pyoracle.retire(pool, 1)
+    loc0, out0 = pyoracle.retire(loc1, 0)
+    assert len(out1) > 0 and len(out0) > 0
+    assert ctx.inactive_retire(1) == len(out1) and ctx.inactive_retire(0) == len(out0)
+    assert ctx.inactive_retire(77) == 0
+    assert ctx.inactive_size() == (len(out1) + len(out0), 2)
+    assert ctx.pool_download().tobytes() == loc0.tobytes()
+    assert ctx.inactive_download(1).tobytes() == out1.tobytes() and ctx.inactive_download(0).tobytes() == out0.tobytes()
+    assert ctx.inactive_download().tobytes() == np.concatenate([out1, out0]).tobytes()
+    a = np.deg2rad(2.0)
+    Wm = np.eye(4)
+    Wm[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+    Wm[:3, 3] = [0.5, -0.1, 0.25]
+    w = np.ascontiguousarray(Wm.T.astype(np.float32).reshape(16))
+    ctx.inactive_transform(1, w)
+    warped1 = pyoracle.warp_active(out1, w)
+    check_surfels(ctx.inactive_download(1), warped1, "warped segment")
+    assert ctx.inactive_download(0).tobytes() == out0.tobytes()            # the other pose did not move
+    store = ctx.inactive_download()
+    pts = ctx.inactive_export_cloud()
+    assert pts.tobytes() == pyoracle.cloud_points(store, -(2 ** 31)).tobytes()
+    seg1 = ctx.inactive_download(1)
+    assert ctx.inactive_reactivate(1) == len(out1)
+    assert ctx.inactive_size() == (len(out0), 1)
+    assert ctx.inactive_download().tobytes() == out0.tobytes()             # the gap was closed
+    after = ctx.pool_download()
+    assert len(after) == len(loc0) + len(seg1) and after[len(loc0):].tobytes() == seg1.tobytes()
+    ctx.close()
