@@ -119,6 +119,35 @@ def test_move_add_surfels_and_cloud_builders_are_pinned(tmp_path):
     m.close()
 
 
+def test_move_add_surfels_insertion_is_an_append():
+    """A loop edge brings an old keyframe back into the drift-free window: its attached_surfels are appended to
+    local_surfels in order and leave the inactive cloud (surfel_map.cpp:1526-1590) -- the semantics of
+    dsm_pool_append / dsm_inactive_reactivate."""
+    m = pyoracle.RefMap(CAM, drift_free_poses=2)
+    drive(m, 5)
+    att0, local_before, inactive_before = m.attached(0), m.local(), m.inactive_points()
+    assert len(att0) > 0 and 0 not in m.local_pose_indexs()
+    path = [pyoracle.pose_to_ros7(synth.pose_stream(t)) for t in range(5)]
+    m.frame(100.5, None, None, pyoracle.pose_to_ros7(synth.pose_stream(5)), False, 4, path7=np.array(path), loops=[4, 0])
+    window_before = m.local_pose_indexs()
+    m.move_add_surfels(4)
+    assert 0 in m.local_pose_indexs() and len(m.attached(0)) == 0
+    # the same call retires whatever left the window rooted at pose 4 (removal runs before insertion)
+    want_local, retired = local_before, []
+    for p in [q for q in window_before if q not in m.local_pose_indexs()]:
+        want_local, out = pyoracle.retire(want_local, p)
+        assert m.attached(p).tobytes() == out.tobytes()
+        retired.append(out)
+    after = m.local()
+    assert after.tobytes() == np.concatenate([want_local, att0]).tobytes()
+    inactive_after = m.inactive_points()
+    # pose 0 was the first segment of the inactive cloud: the rest moved down unchanged, new segments follow
+    assert inactive_before[:len(att0)].tobytes() == pyoracle.cloud_points(att0, -(2 ** 31)).tobytes()
+    want_inactive = np.concatenate([inactive_before[len(att0):]] + [pyoracle.cloud_points(o, -(2 ** 31)) for o in retired])
+    assert inactive_after.tobytes() == want_inactive.tobytes()
+    m.close()
+
+
 def ros7_to_matrix(p7):
     from scipy.spatial.transform import Rotation
     T = np.eye(4)
