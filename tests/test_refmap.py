@@ -244,3 +244,52 @@ def test_reference_node_over_the_product_matches_the_reference_node():
         assert abs(len(a.attached(p)) - len(b.attached(p))) <= max(2, len(a.attached(p)) // 200)
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("DSM_TEST_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: set DSM_TEST_UNVERIFIED=1 to run")
+def test_device_resident_map_tracks_the_reference_node():
+    """System level, INTEGRATION.md steps 2+3: the reference node runs a drive on the CPU; the same frames go through
+    the product with local_surfels AND attached_surfels resident on the device, replaying the node's own window
+    decisions (which keyframes leave / re-enter).  After every frame the device's local pool and inactive store
+    equal the node's local_surfels / inactive_pointcloud as sets, within the surfel tolerance."""
+    from test_gpu_resident import match_as_sets
+    ref = pyoracle.RefMap(CAM, drift_free_poses=2)
+    ctx = capi.Context(CAM, max_batch=2, max_local_surfels=60000)
+    ctx.pool_upload(np.zeros(0, SURFEL_DTYPE))
+    ctx.inactive_reserve(200000)
+    idea = np.zeros((4, 4))
+    idea[0, 0], idea[1, 2], idea[2, 1], idea[3, 3] = 1.0, 1.0, -1.0, 1.0
+    K = idea @ np.linalg.inv(ros7_to_matrix(pyoracle.pose_to_ros7(synth.pose_stream(0))))  # surfel_map.cpp:214-232
+    path, window_prev, stored = [], [], set()
+    T = 7
+    for t in range(T):
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(CAM, 1000 + t, pose)
+        p7 = pyoracle.pose_to_ros7(pose)
+        ref_index = t - 1 if t else 0
+        loops = [4, 0] if t == 5 else ()   # a loop edge 4-0 brings keyframe 0 back into the window at frame 5
+        ref.frame(100.0 + 0.1 * t, gray, depth, p7, True, ref_index, path7=np.array(path).reshape(-1, 7), loops=loops)
+        path.append(p7)
+        window = ref.local_pose_indexs()
+        for p in [q for q in window_prev if q not in window]:          # move_add_surfels: removal first ...
+            if ctx.inactive_retire(p) > 0:
+                stored.add(p)
+        for p in [q for q in window if q not in window_prev and q in stored]:   # ... then insertion
+            ctx.inactive_reactivate(p)
+            stored.discard(p)
+        window_prev = window
+        fuse_pose = (K @ ros7_to_matrix(p7)).astype(np.float32)       # what synchronize_msgs hands to fuse_map
+        ctx.fuse_frame_resident(ref_index, gray, depth, np.ascontiguousarray(fuse_pose.T.reshape(16)))
+        want = ref.local()
+        got = ctx.pool_download()
+        got = got[got["update_times"] > 0]
+        assert abs(len(got) - len(want)) <= max(2, len(want) // 300), f"frame {t}: {len(got)} vs {len(want)} local surfels"
+        if len(got) == len(want):
+            match_as_sets(got, want, tol=1e-3)
+        n_in = ctx.inactive_size()[0]
+        assert abs(n_in - len(ref.inactive_points())) <= max(2, n_in // 300), f"frame {t}: inactive {n_in}"
+    assert ctx.inactive_size()[0] > 0, "the drive never retired a keyframe"
+    ctx.close()
+    ref.close()
