@@ -44,6 +44,13 @@
 // small helpers
 // -------------------------------------------------------------------------------------------
 using dsm_barrier = cuda::barrier<cuda::thread_scope_block>; // mbarrier for the TMA (cp.async.bulk) stagings
+// Wait for phase 0 of a tile barrier.  Experimental kernels only: a byte-count mistake would otherwise spin forever and
+// take the GPU with it, so the wait is bounded (each try_wait already blocks for a hardware time slice) and traps.
+__device__ __forceinline__ void tile_wait(dsm_barrier &bar)
+{
+    for (unsigned spin = 0; !cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(bar), 0); spin++)
+        if (spin > (1u << 22)) __trap();
+}
 __device__ __forceinline__ void sts_f32(unsigned addr, float v)
 { // st.shared with a precomputed 32-bit shared-window address (keeps the address math out of the hot loops)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
@@ -707,8 +714,8 @@ __global__ void __launch_bounds__(256) k_gather_depths_tiled(const __grid_consta
         float4 z4[2];
         uchar4 g4[2];
         int yy[2];
+        tile_wait(bar);
 #pragma unroll
-        while (!cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(bar), 0)) {}
         for (int ps = 0; ps < 2; ps++)
         { // tile row r = 8*ps + lane/4, tile column 8*warp + 4*(lane&3); rows / columns that were not copied hold
           // unspecified data and are masked by `in` exactly like the out-of-window lanes of the direct-load kernel
@@ -1236,8 +1243,8 @@ __global__ void __launch_bounds__(256) k_gather_points_tiled(const __grid_consta
         float kyv[2];
         int yy[2];
         unsigned pof[2];
+        tile_wait(bar);
 #pragma unroll
-        while (!cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(bar), 0)) {}
         for (int ps = 0; ps < 2; ps++)
         { // tile row 8*ps + lane/4, tile column 8*warp + 4*(lane&3); positions that were not copied are masked by `in`
             const int r = 8 * ps + (lane >> 2);
