@@ -174,6 +174,71 @@ __global__ void __launch_bounds__(256) k_seed_init(const __grid_constant__ DsmDe
     d.fused[o] = 0;                 // fused = false
 }
 
+// K0', EXPERIMENTAL (variant bit 6, off by default): k_seed_init whose hole search requests the
+// whole window at once.  k_seed_init walks the window of a seed that sits on a depth hole 32 pixels per step with an
+// early exit, i.e. up to 8 dependent memory round trips per hole seed and warp; on a frame with large invalid regions
+// that is the single slowest kernel of a one-frame stream (42 us).  Same result: first valid depth in raster order.
+__global__ void __launch_bounds__(256) k_seed_init_wide(const __grid_constant__ DsmDev d)
+{
+    const int b = d.frame0 + blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        d.nlist[b] = 0;
+        d.nnew[b] = 0;
+        d.errflag[b] = 0;
+    }
+    const int W = d.W, H = d.H, Wp = d.Wp;
+    const uint8_t *gray = d.gray + (size_t)b * d.px_stride;
+    const float *depth = d.depth + (size_t)b * d.px_stride;
+    const bool live = s < d.S;
+    const int sp_x = live ? s % d.spw : 0, sp_y = live ? s / d.spw : 0;
+    int ix = sp_x * DSM_SP + DSM_SP / 2, iy = sp_y * DSM_SP + DSM_SP / 2;
+    ix = ix < W - 1 ? ix : W - 1;
+    iy = iy < H - 1 ? iy : H - 1;
+    float md = live ? depth[iy * Wp + ix] : 1.0f;
+    // seeds sitting on a hole: first depth > 0.01 in raster order of the clamped END-EXCLUSIVE window
+    // (:602-625).  The warp serves its hole seeds one at a time, 32 window pixels per step.
+    unsigned todo = __ballot_sync(FULL, live && (double)md < 0.01);
+    while (todo)
+    {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int hx = __shfl_sync(FULL, sp_x, src), hy = __shfl_sync(FULL, sp_y, src);
+        int xb = hx * DSM_SP + DSM_SP / 2 - DSM_SP, yb = hy * DSM_SP + DSM_SP / 2 - DSM_SP;
+        int xe = xb + DSM_SP * 2, ye = yb + DSM_SP * 2;
+        xb = xb > 0 ? xb : 0;
+        yb = yb > 0 ? yb : 0;
+        xe = xe < W - 1 ? xe : W - 1;
+        ye = ye < H - 1 ? ye : H - 1;
+        const int ww = xe - xb, n = ww * (ye - yb);
+        // all (at most 8 x 32 = 256) window pixels are requested at once; the first hit in raster order is the
+        // smallest flat index, found with one warp-wide integer minimum
+        float tv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const int i = lane + 32 * k;
+            tv[k] = (i < n) ? depth[(yb + i / ww) * Wp + xb + i % ww] : 0.f;
+        }
+        int first = INT_MAX;
+        float val = 0.f;
+#pragma unroll
+        for (int k = 7; k >= 0; k--)
+            if ((double)tv[k] > 0.01) first = lane + 32 * k, val = tv[k]; // descending k: the smallest index of this lane wins
+        const int wmin = __reduce_min_sync(FULL, first);
+        const float found = __shfl_sync(FULL, val, wmin & 31);
+        if (wmin != INT_MAX && lane == src) md = found;
+    }
+    if (!live) return;
+    const size_t o = (size_t)b * d.S + s;
+    d.seed[o] = make_float4((float)ix, (float)iy, (float)gray[iy * Wp + ix], md);
+    d.inv_md[o] = 1.0 / (double)md; // only consumed when md > 0 (:378)
+    d.tstable[o] = -1;              // stable = false
+    d.fused[o] = 0;                 // fused = false
+}
+
 // -------------------------------------------------------------------------------------------
 // K1  slic_assign — update_pixels_kernel (:389-453) + calculate_cost (:364-387)
 //
@@ -2331,6 +2396,12 @@ void dsm_launch_repack(const DsmDev &d, int nb, const uint8_t *gray_packed, cons
 }
 void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s)
 {
+    if (d.variants & DSM_VARIANT_SEED_INIT_WIDE)
+    {
+        dim3 g((d.S + 255) / 256, nb);
+        k_seed_init_wide<<<g, 256, 0, s>>>(d);
+        return;
+    }
     dim3 grid((d.S + 255) / 256, nb);
     k_seed_init<<<grid, 256, 0, s>>>(d);
 }
