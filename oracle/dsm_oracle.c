@@ -755,8 +755,8 @@ static int initialize_surfels(ctx_t *c, int ref_idx, const float *pose, surfel_t
 }
 
 /* ---- the caller-side steps the GPU-resident pool mode takes over ----
- * These two follow surfel_fusion/src/surfel_map.cpp, which cannot be compiled here (ROS/PCL), so they
- * are restatements only: "parity unpinned" against the reference binary for these two functions. */
+ * These follow surfel_fusion/src/surfel_map.cpp and are pinned byte for byte against that file compiled in place
+ * behind stand-in ROS / PCL headers (oracle/ref_map_driver.cpp -> oracle/_ref/libdsm_refmap.so, tests/test_refmap.py). */
 
 /* SurfelMap::fuse_map post-step (surfel_map.cpp:1077-1109): recycle deleted slots from the highest
  * index for the new surfels, push_back the rest, then swap-with-back the leftover deleted slots.

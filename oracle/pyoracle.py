@@ -170,8 +170,9 @@ def warp_active(surfels, W_colmajor):
     return out
 
 
-# ---- output side of SurfelMap, restated in numpy: surfel_map.cpp needs ROS + PCL and cannot
-# be compiled here, so these are UNPINNED restatements ----
+# ---- output side of SurfelMap, restated in numpy.  cloud_points, mesh_vertices and
+# ply_mesh_text are pinned byte for byte against the reference's own SurfelMap compiled in place (RefMap below,
+# tests/test_refmap.py); pcd_text restates PCL's published PCD v0.7 ASCII layout (PCL is not vendored in the reference) ----
 def cloud_points(local, min_update_times=5):
     """The local_surfels loop of publish_active_pointcloud / publish_all_pointcloud / save_cloud
     (surfel_map.cpp:1403-1412, :1429-1438, :1156-1166; `update_times < 5 -> continue`) and, with
