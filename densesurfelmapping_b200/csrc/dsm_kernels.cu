@@ -716,9 +716,8 @@ __global__ void __launch_bounds__(128) k_newton(const __grid_constant__ DsmDev d
 #define GT_GSTRIDE 144 // bytes per gray tile row (96 used; 36 words: 8 rows x 4 quarters hit 32 distinct banks)
 __global__ void __launch_bounds__(256) k_gather_depths_tiled(const __grid_constant__ DsmDev d)
 {
-    // tile[k][seed-in-block]: the 8 warps (one seed each) compact into shared memory, then the block
-    // copies the tile out as full 32-byte sectors of the [k][seed] global list (a direct scatter
-    // would cost one L2 write request per element)
+    // tile[seed-in-block][k]: the 8 warps (one seed each) compact into shared memory, then the block
+    // copies the tile out as full 32-byte sectors of the [k][seed] global list
     __shared__ float tile[DL_CAP * 8];
     __shared__ alignas(128) int32_t t_lab[16 * GT_STRIDE];
     __shared__ alignas(128) float t_dep[16 * GT_STRIDE];
@@ -826,8 +825,11 @@ __global__ void __launch_bounds__(256) k_gather_depths_tiled(const __grid_consta
         int tot2;
         const int ex2 = warp_excl_scan(c2, lane, tot2);
         const int n0 = tot2 & 0xffff, ndt = n0 + (tot2 >> 16);
-        const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
-        unsigned a0 = tbase + 32u * (ex2 & 0xffff), a1 = tbase + 32u * (n0 + (ex2 >> 16)); // 32 bytes per list row
+        // list tile laid out [seed][k] here (the direct-load kernel uses [k][seed]): the lanes of one compaction store
+        // write consecutive list positions = consecutive banks; ncu counted 5.3 M bank-conflict wavefronts per launch
+        // for the [k][seed] stores (4 banks per warp), about a fifth of the kernel's L1 data-pipe load
+        const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * DL_CAP * warp;
+        unsigned a0 = tbase + 4u * (ex2 & 0xffff), a1 = tbase + 4u * (n0 + (ex2 >> 16));
         const float za[4] = {z4[0].x, z4[0].y, z4[0].z, z4[0].w}, zb[4] = {z4[1].x, z4[1].y, z4[1].z, z4[1].w};
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -835,12 +837,12 @@ __global__ void __launch_bounds__(256) k_gather_depths_tiled(const __grid_consta
             if ((mdm >> k) & 1u)
             {
                 sts_f32(a0, za[k]);
-                a0 += 32u;
+                a0 += 4u;
             }
             if ((mdm >> (4 + k)) & 1u)
             {
                 sts_f32(a1, zb[k]);
-                a1 += 32u;
+                a1 += 4u;
             }
         }
         if (lane == 0 && tflag != DSM_STABLE)
@@ -856,7 +858,7 @@ __global__ void __launch_bounds__(256) k_gather_depths_tiled(const __grid_consta
     if (blockIdx.x * 8 + c < d.spw)
     {
         float *dst = d.dlist + (size_t)b * DL_CAP * d.Sp + sp_y * d.spw + blockIdx.x * 8 + c;
-        for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp] = tile[r * 8 + c];
+        for (int r = threadIdx.x >> 3; r < rows; r += 32) dst[(size_t)r * d.Sp] = tile[c * DL_CAP + r]; // DL_CAP % 32 == 4: conflict-free
     }
 }
 
@@ -1248,7 +1250,7 @@ __global__ void __launch_bounds__(256) k_gather_points(const __grid_constant__ D
 // k_gather_depths_tiled.  Everything after the loads is the text of k_gather_points: bit-identical results.
 __global__ void __launch_bounds__(256) k_gather_points_tiled(const __grid_constant__ DsmDev d)
 {
-    // tile[plane][k][seed-in-block]: compacted in shared memory, copied out as full 32-byte sectors
+    // tile[plane][seed-in-block][k]: compacted in shared memory, copied out as full 32-byte sectors
     __shared__ float tile[3 * PF_CAP * 8];
     __shared__ alignas(128) int32_t t_lab[16 * GT_STRIDE];
     __shared__ alignas(128) float t_dep[16 * GT_STRIDE];
@@ -1378,11 +1380,13 @@ __global__ void __launch_bounds__(256) k_gather_points_tiled(const __grid_consta
         {
             const float fn = (float)ninl;
             const float mxs = spx / fn, mys = spy / fn, mzs = spz / fn; // (:117-119)
-            const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * warp;
+            // [plane][seed][k] instead of [plane][k][seed]: conflict-free compaction stores (see k_gather_depths_tiled;
+            // ncu: 13.6 M store bank-conflict wavefronts per launch in the direct-load kernel)
+            const unsigned tbase = (unsigned)__cvta_generic_to_shared(tile) + 4u * PF_CAP * warp;
 #pragma unroll
             for (int ps = 0; ps < 2; ps++)
             {
-                unsigned a = tbase + 32u * (ps == 0 ? (ex2 & 0xffff) : n0 + (ex2 >> 16)); // 32 bytes per list row
+                unsigned a = tbase + 4u * (ps == 0 ? (ex2 & 0xffff) : n0 + (ex2 >> 16));
                 const float zk[4] = {z4[ps].x, z4[ps].y, z4[ps].z, z4[ps].w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
@@ -1391,7 +1395,7 @@ __global__ void __launch_bounds__(256) k_gather_points_tiled(const __grid_consta
                         sts_f32(a, kxv[k] * zk[k] - mxs); // centred points (:121-126)
                         sts_f32(a + 4u * PF_CAP * 8, kyv[ps] * zk[k] - mys);
                         sts_f32(a + 8u * PF_CAP * 8, zk[k] - mzs);
-                        a += 32u;
+                        a += 4u;
                     }
             }
             P0 = make_float4(snx, sny, snz, maxd);
@@ -1416,7 +1420,7 @@ __global__ void __launch_bounds__(256) k_gather_points_tiled(const __grid_consta
 #pragma unroll 2
         for (unsigned r = threadIdx.x >> 3; r < (unsigned)rows; r += 32u)
         {
-            const unsigned t = r * 8u + c, o = r * sp;
+            const unsigned t = c * PF_CAP + r, o = r * sp; // PF_CAP % 32 == 4: conflict-free
             dx[o] = tile[t];
             dy[o] = tile[PF_CAP * 8 + t];
             dz[o] = tile[2 * PF_CAP * 8 + t];

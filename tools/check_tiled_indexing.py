@@ -83,8 +83,21 @@ def bank_check():
             assert len(banks) == 32
 
 
+def compaction_tile_check(cap=228):
+    """[seed][k] list tile of the tiled gathers: the copy-out (thread t reads tile[(t & 7) * cap + (t >> 3) + 32 j]) must
+    hit 32 distinct banks per warp, and a compaction store whose lanes write consecutive positions is conflict-free."""
+    for j in range(8):
+        for w in range(8):
+            banks = {(((t & 7) * cap + (t >> 3) + 32 * j) % 32) for t in range(32 * w, 32 * w + 32)}
+            assert len(banks) == 32
+    for w in range(8):
+        for start in (0, 5, 31, 100):
+            assert len({(w * cap + start + l) % 32 for l in range(32)}) == 32
+
+
 if __name__ == "__main__":
     bank_check()
+    compaction_tile_check()
     for (W, H) in [(1226, 370), (1241, 376), (640, 480), (1280, 720), (64, 48), (36, 28), (24, 24), (68, 44), (132, 100)]:
         for pts in (False, True):
             print(W, H, "points" if pts else "depths", check(W, H, pts), "lane reads verified")
