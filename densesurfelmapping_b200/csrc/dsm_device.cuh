@@ -80,6 +80,7 @@ struct DsmDev
 #define DSM_VARIANT_INIT_MULTIBLOCK 16u // k_init_surfels_mb: several CTAs per frame, offsets by re-evaluating the emit predicate
 #define DSM_VARIANT_NORMALS_FORK 32u   // host schedule: the pixel-normal pass runs on a side stream concurrently with the clustering
 #define DSM_VARIANT_SEED_INIT_WIDE 64u  // k_seed_init_wide: hole search with the whole window in flight
+#define DSM_VARIANT_ASSIGN_FEWER_CVT 128u // k_assign_x: two of the seven float<->double conversions per candidate done on the fp64 pipe
 #define DSM_VARIANT_GN_STAGED 8u      // k_gauss_newton_staged: point list streamed through shared memory (cp.async, double-buffered)
 
 enum DsmKernelId

@@ -286,6 +286,174 @@ __device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pi
     return has;
 }
 
+// K1', EXPERIMENTAL (variant bit 7, off by default): the assign pass with 4 instead of 7
+// float<->double conversions per (pixel, candidate).  The pass is bound by the conversion unit (XU at 74-85 % of peak,
+// profiles/r1_final_pipes.csv).  Two of the reference's roundings to float -- (float)nd at :376 and the final (float) at
+// :381 -- only exist to be widened again or compared, so they are done without leaving the fp64 pipe:
+//     M = 1.5 * 2^(exponent(x) + 29),   rn24(x) = (x + M) - M
+// (the fp64 adder performs the round-to-nearest-even to 24 significant bits; M comes from the high word of x with two
+// integer ops).  For non-negative x whose float image is zero or normal this equals (double)(float)x bit for bit
+// (tools/check_rn24_magic.py: 1e8 random values, exact ties and their neighbours); costs are >= 0 and either 0 or
+// >= 1e-7, values >= 1e6 never win, so overflow to inf and the subnormal grid cannot matter.  The costs stay
+// float-valued doubles and are compared as doubles, which orders them exactly like the float comparisons.
+__device__ __forceinline__ double rn24(double x)
+{
+    const double M = __hiloint2double((__double2hiint(x) & 0x7ff00000) + 0x01d80000, 0);
+    return (x + M) - M;
+}
+__device__ __forceinline__ bool calc_cost_x(const SeedC &sd, float pix_i, float pix_inv, double pix_inv_d, float fx, float fy,
+                                            double &nodepth, double &withdepth)
+{
+    const float ax = sd.x - fx, ay = sd.y - fy;
+    const float dist = ax * ax + ay * ay;
+    const float n = dist * 0.0625f; // (:374)
+    const float idf = sd.I - pix_i;
+    const double a = (double)(idf * idf);
+    const double q0 = a * 0.01;
+    const double q = __fma_rn(__fma_rn(-q0, 100.0, a), 0.01, q0); // a / 100.0, correctly rounded (see calc_cost)
+    const double nr = rn24((double)n + q);                         // (double)(float)nd of (:376), no conversion
+    nodepth = nr;
+    const bool has = sd.md > 0 && pix_inv > 0; // (:378)
+    const float idd = (float)(sd.inv - pix_inv_d);                 // (:380)
+    const double wr = rn24(nr + (double)(idd * idd) * 400.0);      // (:381)
+    withdepth = has ? wr : nr;
+    return has;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256, 4) k_assign_x(const __grid_constant__ DsmDev d)
+{
+    const int b = d.frame0 + blockIdx.z;
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int lane = threadIdx.x & 31;
+    const bool active = (x4 < d.W) && (y < d.H);
+
+    const size_t fo = (size_t)b * d.px_stride;
+    const size_t so = (size_t)b * d.S;
+    int win[4] = {-1, -1, -1, -1};
+    int L[4] = {0, 0, 0, 0};
+    if (active)
+    {
+        const size_t po = fo + (size_t)y * d.Wp + x4;
+        const uchar4 g4 = *reinterpret_cast<const uchar4 *>(d.gray + po);
+        const float4 z4 = *reinterpret_cast<const float4 *>(d.depth + po);
+        if (!FIRST)
+        {
+            const int4 l4 = *reinterpret_cast<const int4 *>(d.labels + po);
+            L[0] = l4.x, L[1] = l4.y, L[2] = l4.z, L[3] = l4.w;
+        }
+        const float gi[4] = {(float)g4.x, (float)g4.y, (float)g4.z, (float)g4.w};
+        const float zi[4] = {z4.x, z4.y, z4.z, z4.w};
+        const int bx = x4 >> 3, by = y >> 3, rx0 = x4 & 7, ry = y & 7;
+        const int xa = (rx0 == 0) ? bx - 1 : bx, xb = xa + 1;
+        const int ya = (ry < 4) ? by - 1 : by, yb = ya + 1;
+        const bool vxa = xa >= 0 && xa < d.spw, vxb = xb >= 0 && xb < d.spw;
+        const bool vya = ya >= 0 && ya < d.sph, vyb = (ry != 4) && yb >= 0 && yb < d.sph;
+        // candidate c = 2*ix + iy  -> (xa,ya) (xa,yb) (xb,ya) (xb,yb): dx outer, dy inner
+        SeedC sc[4];
+        bool sv[4];
+        int sidx[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+        {
+            const int cx = (c >> 1) ? xb : xa, cy = (c & 1) ? yb : ya;
+            sv[c] = ((c >> 1) ? vxb : vxa) && ((c & 1) ? vyb : vya);
+            sidx[c] = cy * d.spw + cx;
+            const int li = sv[c] ? sidx[c] : 0; // invalid candidates read seed 0 and are masked out below
+            const float4 s4 = d.seed[so + li];
+            sc[c].x = s4.x, sc[c].y = s4.y, sc[c].I = s4.z, sc[c].md = s4.w;
+            sc[c].inv = d.inv_md[so + li];
+        }
+        const float fy = (float)y;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            const int x = x4 + i;
+            const float my_i = gi[i];
+            // (:404-405) my_inv = (float)(1.0 / (double)depth) for depth > 0.01.  53 >= 2*24+2 bits, so the
+            // double rounding is innocuous and the IEEE float reciprocal gives the same value.
+            // (__frcp_rn is the correctly rounded reciprocal, subnormal results included; -ftz=false)
+            const float my_inv = (zi[i] > F_0p01_LO) ? __frcp_rn(zi[i]) : 0.0f;
+            const double my_inv_d = (double)my_inv;
+            const float fx = (float)x;
+            double min_d = 1e6, min_nd = 1e6; // float-valued doubles: same order as the float comparisons
+            int idx_d = -1, idx_nd = -1;
+            bool all_has_depth = true;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+            { // branch-free: an invalid candidate gets cost +inf (never < the running minimum) and does not
+              // touch all_has_depth; x%8 == 4 sees only its own column (rx0==4, i==0 -> only xa)
+                const bool valid = sv[c] && ((c >> 1) ? !(rx0 == 4 && i == 0) : true);
+                double cnd, cd;
+                const bool has = calc_cost_x(sc[c], my_i, my_inv, my_inv_d, fx, fy, cnd, cd);
+                all_has_depth &= has || !valid;
+                const bool bd = valid && cd < min_d, bn = valid && cnd < min_nd; // validity folded into the compare predicate
+                min_d = bd ? cd : min_d;
+                idx_d = bd ? sidx[c] : idx_d;
+                min_nd = bn ? cnd : min_nd;
+                idx_nd = bn ? sidx[c] : idx_nd;
+            }
+            win[i] = (x < d.W) ? (all_has_depth ? idx_d : idx_nd) : -1;
+        }
+    }
+
+    if (FIRST)
+    {
+        if (active)
+        {
+            const size_t po = fo + (size_t)y * d.Wp + x4;
+            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(win[0] < 0 ? 0 : win[0], win[1] < 0 ? 0 : win[1],
+                                                                 win[2] < 0 ? 0 : win[2], win[3] < 0 ? 0 : win[3]);
+        }
+        return;
+    }
+
+    // ---- iterations 2..: commit / defer
+    int2 ent[4];
+    int nent = 0;
+    if (active)
+    {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            if (x4 + i >= d.W || win[i] < 0) continue;
+            const int pidx = y * d.Wp + x4 + i;
+            const int ts = d.tstable[so + L[i]];
+            if (ts < 0)
+            { // owner unstable since the start of the pass: the reference evaluates this pixel
+                if (win[i] != L[i])
+                {
+                    L[i] = win[i];
+                    changed = true;
+                }
+                if (d.tstable[so + win[i]] > pidx) atomicMin(&d.tstable[so + win[i]], pidx); // stable = false at time pidx (:445/:450)
+            }
+            else
+            {
+                ent[nent++] = make_int2(pidx, win[i]);
+            }
+        }
+        if (changed)
+        {
+            const size_t po = fo + (size_t)y * d.Wp + x4;
+            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(L[0], L[1], L[2], L[3]);
+        }
+    }
+    // warp-aggregated append of the deferred pixels
+    int total;
+    const int excl = warp_excl_scan(nent, lane, total);
+    if (total > 0)
+    {
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&d.nlist[b], total);
+        base = __shfl_sync(FULL, base, 31);
+        int2 *list = d.list + fo;
+        for (int j = 0; j < nent; j++) list[base + excl + j] = ent[j];
+    }
+}
+
 template <bool FIRST>
 __global__ void __launch_bounds__(256, 4) k_assign(const __grid_constant__ DsmDev d)
 {
@@ -2413,6 +2581,14 @@ void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s)
 {
     dim3 block(64, 4);
     dim3 grid((d.W + 255) / 256, (d.H + 3) / 4, nb);
+    if (d.variants & DSM_VARIANT_ASSIGN_FEWER_CVT)
+    {
+        if (first)
+            k_assign_x<true><<<grid, block, 0, s>>>(d);
+        else
+            k_assign_x<false><<<grid, block, 0, s>>>(d);
+        return;
+    }
     if (first)
         k_assign<true><<<grid, block, 0, s>>>(d);
     else

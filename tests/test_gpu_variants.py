@@ -13,7 +13,7 @@ from densesurfelmapping_b200.elements import SURFEL_DTYPE
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("DSM_TEST_VARIANTS") != "1", reason="experimental variants: set DSM_TEST_VARIANTS=1")]
 
-MASKS = [1, 2, 4, 8, 16, 32, 64, 127]
+MASKS = [1, 2, 4, 8, 16, 32, 64, 128, 255]
 
 
 def run_all_masks(cam, frames, pool):

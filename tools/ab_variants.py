@@ -1,6 +1,6 @@
 """A/B harness for the experimental kernel variants (dsm_debug_set_variants).
 
-For every variant mask given on the command line (default: 0 1 2 4 8 16 32 64 127) on one resident batch of B KITTI-shaped frames:
+For every variant mask given on the command line (default: 0 1 2 4 8 16 32 64 128 255) on one resident batch of B KITTI-shaped frames:
   * parity: labels, clustering state and surfels of every frame must be BYTE-IDENTICAL to mask 0 (the measured
     default path) -- the variants only change data movement;
   * timing: wall time of N graph-replayed steps (CUDA-event based profile off), then the per-kernel CUDA-event
@@ -29,7 +29,7 @@ def snapshot(ctx, B):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-    masks = [int(a, 0) for a in sys.argv[3:]] or [0, 1, 2, 4, 8, 16, 32, 64, 127]
+    masks = [int(a, 0) for a in sys.argv[3:]] or [0, 1, 2, 4, 8, 16, 32, 64, 128, 255]
     if masks[0] != 0:
         masks = [0] + masks
     cam = synth.KITTI
