@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSM_VERSION 100 /* 0.1.0 */
+#define DSM_VERSION 110 /* 0.1.10: + output formats, stream chunks, inactive store, debug variants */
 
 /* ---- error codes ---- */
 #define DSM_OK 0
