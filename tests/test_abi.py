@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
     lib = capi.load_library()  # built by __graft_entry__.build(); raises if missing (no fallback)
     for name in declared_functions():
         assert hasattr(lib, name), f"libdsm_b200.so does not export {name}"
-    assert lib.dsm_version() == 100
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dsm.h")).read()
+    assert lib.dsm_version() == int(re.search(r"#define DSM_VERSION (\d+)", header).group(1))  # library built from this header
     assert lib.dsm_strerror(-2).decode().startswith("unsupported image shape")
     assert capi.kernel_names()[:3] == ["seed_init", "slic_assign_first", "slic_assign"]
 
