@@ -384,6 +384,9 @@ __global__ void __launch_bounds__(256, 4) k_assign_x(const __grid_constant__ Dsm
             for (int c = 0; c < 4; c++)
             { // branch-free: an invalid candidate gets cost +inf (never < the running minimum) and does not
               // touch all_has_depth; x%8 == 4 sees only its own column (rx0==4, i==0 -> only xa)
+                // a warp covers 128 pixels of ONE image row, so the row part of the validity test is warp-uniform: on rows
+                // with y % 8 == 4 (and on the border rows) two of the four candidates are skipped without divergence
+                if (!((c & 1) ? vyb : vya)) continue;
                 const bool valid = sv[c] && ((c >> 1) ? !(rx0 == 4 && i == 0) : true);
                 double cnd, cd;
                 const bool has = calc_cost_x(sc[c], my_i, my_inv, my_inv_d, fx, fy, cnd, cd);
