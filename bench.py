@@ -235,6 +235,10 @@ def kernel_alg_bytes(name, P, S, npool, nnew):
         "pixel_normals": 4 * P + 12 * P,
         "plane_gather_points": 8 * P + 12 * P + 16 * S + 32 * S + 12 * 0.9 * P,
         "plane_gauss_newton": 12 * 0.9 * P + 48 * S + 48 * S,
+        # tile schedule
+        "slic_update": 9 * P + 24 * S + 28 * S,          # labels + depth + gray read once, seeds read and written
+        "plane_gather": 8 * P + 16 * S + 112 * S + 12 * 0.9 * P,  # labels + depth, seed in, per-seed sums + H out, centred points out
+        "plane_solve": 112 * S + 16 * S + 48 * S,
         "surfel_fuse": 88 * npool + 48 * S,
         "surfel_init": 52 * S + 44 * nnew,
     }.get(name, 0)
@@ -284,7 +288,7 @@ def run_extras(cam, local_rank, stream):
                      "frames_per_s": nt / (ms * 1e-3), "ms_per_frame": ms / nt, "final_pool_surfels": ctx.pool_size(),
                      "h2d_bytes_per_frame": int(cam.width * cam.height * 5 + 140), "api": "dsm_fuse_frame_resident (C ABI, pinned host frames)"}
     # where a single frame's time goes (plain launches with event pairs; latency-bound at batch 1)
-    ctx.profile_enable(0xFFF)
+    ctx.profile_enable((1 << capi.NUM_KERNELS) - 1)
     ctx.profile_reset()
     for t in range(warm, warm + 6):
         ctx.fuse_frame_resident(200 + t // 4, hg[t], hd[t], Pz[t])
@@ -477,7 +481,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up; per-kernel breakdown measured during the warm-up steps
-    ctx.profile_enable(0xDFF)
+    ctx.profile_enable(((1 << capi.NUM_KERNELS) - 1) & ~(1 << 9))
     ctx.profile_reset()
     for _ in range(max(args.warmup, 3)):
         step()

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdsm_b200.so")
-SOURCES = ["dsm_kernels.cu", "dsm_capi.cu", "dsm_io.cpp"]
+SOURCES = ["dsm_kernels.cu", "dsm_tile.cu", "dsm_capi.cu", "dsm_io.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
@@ -33,7 +33,8 @@ def needs_build():
 def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = LIB + ".tmp"  # linked next to the target and renamed: a concurrent reader (gpurun snapshot) never sees a half-written library
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(" ".join(cmd))
@@ -41,6 +42,7 @@ def build(force=False, verbose=False, extra=()):
         print(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed")
+    os.replace(tmp, LIB)
     return LIB
 
 

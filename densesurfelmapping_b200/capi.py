@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libdsm_b200.so")
 DSM_OK = 0
 ERRORS = {-1: "DSM_E_INVALID", -2: "DSM_E_SHAPE", -3: "DSM_E_NODEVICE", -4: "DSM_E_CUDA",
           -5: "DSM_E_NOMEM", -6: "DSM_E_CAPACITY", -7: "DSM_E_STATE", -8: "DSM_E_NCCL", -9: "DSM_E_IO"}
-NUM_KERNELS = 12
+NUM_KERNELS = 15
 
 # every symbol include/dsm.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [

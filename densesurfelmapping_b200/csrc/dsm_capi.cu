@@ -33,6 +33,7 @@ struct dsm_ctx
     cudaStream_t stream;
     bool own_stream;
     DsmDev d;
+    DsmMaps maps;  // TMA descriptors of labels / depth / gray for the tile kernels
     int S, Wp;
     size_t px;    // pitched pixels per frame
     int nb;       // frames in the current batch
@@ -89,7 +90,8 @@ struct dsm_ctx
 
 static const char *kKernelNames[DSM_NUM_KERNELS] = {
     "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_gather_depths", "slic_newton",
-    "plane_gather_points", "surfel_fuse", "surfel_init", "repack", "pixel_normals", "plane_gauss_newton"};
+    "plane_gather_points", "surfel_fuse", "surfel_init", "repack", "pixel_normals", "plane_gauss_newton",
+    "slic_update", "plane_gather", "plane_solve"};
 
 #define CK(call)                                                                                         \
     do                                                                                                   \
@@ -157,6 +159,10 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(d.labels);
     cudaFree(d.seed);
     cudaFree(d.inv_md);
+    cudaFree(d.invd);
+    cudaFree(d.seed_hl);
+    cudaFree(d.done);
+    cudaFree(d.hrec);
     cudaFree(d.tstable);
     cudaFree(d.usum);
     cudaFree(d.und);
@@ -213,6 +219,51 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
 }
 
 static int ensure_fork_streams(dsm_ctx *ctx);
+
+// TMA descriptors for the tile kernels: each per-pixel array as a [B][H][Wp] tensor, box = one 8x4-seed tile plus
+// halo (DSM_TILE_W x DSM_TILE_H elements; out-of-image parts of a box are zero-filled by the copy engine).
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so the library keeps linking
+// against cudart only.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tile_maps(dsm_ctx *ctx)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "cuTensorMapEncodeTiled is not available in this driver");
+        return DSM_E_CUDA;
+    }
+    PFN_encodeTiled enc = (PFN_encodeTiled)fn;
+    const DsmDev &d = ctx->d;
+    struct
+    {
+        CUtensorMap *map;
+        void *base;
+        CUtensorMapDataType type;
+        unsigned esize, boxw;
+    } specs[3] = {{&ctx->maps.lab, d.labels, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, DSM_TILE_W},
+                  {&ctx->maps.dep, ctx->depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, DSM_TILE_W},
+                  {&ctx->maps.gry, ctx->gray, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, DSM_TILE_GW}};
+    for (auto &sp : specs)
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)d.Wp, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        const cuuint64_t strides[2] = {(cuuint64_t)d.Wp * sp.esize, (cuuint64_t)d.px_stride * sp.esize}; // bytes, multiples of 16 (Wp % 16 == 0)
+        const cuuint32_t box[3] = {sp.boxw, DSM_TILE_H, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(sp.map, sp.type, 3, sp.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+        {
+            snprintf(ctx->err, sizeof(ctx->err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+            return DSM_E_CUDA;
+        }
+    }
+    return DSM_OK;
+}
 
 extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_stream, dsm_ctx **out)
 {
@@ -291,6 +342,10 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.labels, B * px + 64);
     ALLOC(d.seed, (size_t)B * S);
     ALLOC(d.inv_md, (size_t)B * S);
+    ALLOC(d.invd, B * px + 64);
+    ALLOC(d.seed_hl, (size_t)B * S);
+    ALLOC(d.done, (size_t)B);
+    ALLOC(d.hrec, (size_t)B * S * 10);
     ALLOC(d.tstable, (size_t)B * S);
     ALLOC(d.usum, (size_t)B * S);
     ALLOC(d.und, (size_t)B * S);
@@ -341,9 +396,9 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
         e = cudaMemcpy(ctx->kx, hx.data(), hx.size() * sizeof(float), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(ctx->ky, hy.data(), hy.size() * sizeof(float), cudaMemcpyHostToDevice);
     }
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_pose, (size_t)B * 32 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_pose, (size_t)2 * B * 32 * sizeof(float)); // second half: dsm_fuse_stream_resident's own tables
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ofs, ((size_t)B + 1) * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ref, (size_t)B * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ref, (size_t)2 * B * sizeof(int32_t));
     if (e != cudaSuccess)
     {
         dsm_destroy(ctx);
@@ -359,6 +414,11 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     d.ky = ctx->ky;
     d.max_pool_per_frame = 0;
     d.variants = 0;
+    if (make_tile_maps(ctx) != DSM_OK || dsm_tile_setup() != 0)
+    {
+        dsm_destroy(ctx);
+        return DSM_E_CUDA;
+    }
     if (const char *ev = getenv("DSM_EXPERIMENTAL_VARIANTS")) d.variants = (int)strtol(ev, nullptr, 0); // see dsm_debug_set_variants
     if ((d.variants & DSM_VARIANT_NORMALS_FORK) && ensure_fork_streams(ctx) != DSM_OK)
     {
@@ -608,7 +668,18 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
         }
         CK(cudaEventRecord(ctx->ev_fork_b[fk], ctx->s_fork[fk]));
     }
-    if (phase & 1)
+    if ((phase & 1) && !(d.variants & DSM_VARIANT_LEGACY))
+    { // tile schedule (dsm_tile.cu): 9 launches for generate_super_pixels (:960-975)
+        STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
+        for (int it = 0; it < 3; it++) // ITERATION_NUM (fusion_functions.h:8)
+        {
+            STEP(it == 0 ? DSM_K_ASSIGN_FIRST : DSM_K_ASSIGN, dsm_launch_assign2(d, nb, it == 0, st)); // relax folded in
+            STEP(DSM_K_UPDATE, dsm_launch_update(d, ctx->maps, nb, st));
+        }
+        STEP(DSM_K_PLANE_GATHER, dsm_launch_plane_gather(d, ctx->maps, nb, st));
+        STEP(DSM_K_PLANE_SOLVE, dsm_launch_gn_solve(d, nb, st));
+    }
+    else if (phase & 1)
     {
     STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
     for (int it = 0; it < 3; it++) // ITERATION_NUM (fusion_functions.h:8)
@@ -877,6 +948,7 @@ extern "C" int dsm_fuse_batch_async(dsm_ctx *ctx, int n, const int32_t *ref, con
     ctx->uploaded = true;
     ctx->ran = true;
     ctx->in_flight = true;
+    ctx->res_active = false; // the pool buffer now holds this batch's slices: a resident pool (if any) is gone
     CK(cudaGetLastError());
     return DSM_OK;
 }
@@ -900,7 +972,13 @@ extern "C" int dsm_fuse_frame(dsm_ctx *ctx, int ref_idx, const uint8_t *gray, si
     const int W = ctx->p.width, H = ctx->p.height;
     if (gray_pitch < (size_t)W || depth_pitch < (size_t)W * 4) return DSM_E_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->in_flight)
+    { // an asynchronous batch still owns the buffers: finish it first
+        int rcw = dsm_batch_wait(ctx);
+        if (rcw != DSM_OK) return rcw;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->res_active = false; // the caller's surfels replace whatever the pool buffer held (a resident pool included)
     int32_t ref = ref_idx;
     int rc = upload_tables(ctx, 1, &ref, pose, nullptr, n_local);
     if (rc != DSM_OK) return rc;
@@ -989,13 +1067,17 @@ extern "C" int dsm_pool_retire(dsm_ctx *ctx, int kf, dsm_surfel_t *out, int cap,
     if (!ctx || !n_out || cap < 0 || (cap > 0 && !out)) return DSM_E_INVALID;
     if (!ctx->res_active) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    // the alternate pool buffer is free between frames: use it as the ordered output
-    dsm_launch_pool_retire(resident_view(ctx, 0), 0, ctx->res_upper, kf, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
+    // count first: nothing is flagged dead unless every retired surfel fits the caller's buffer
     int32_t h[2] = {0, 0};
+    dsm_launch_pool_retire(resident_view(ctx, 0), 0, ctx->res_upper, kf, ctx->blkcnt, ctx->blkofs, ctx->newofs, nullptr, ctx->stream);
     CK(cudaMemcpyAsync(h, ctx->newofs, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     *n_out = h[0];
+    if (h[0] > cap) return DSM_E_CAPACITY; // pool untouched; call again with cap >= *n_out
+    // the alternate pool buffer is free between frames: use it as the ordered output
+    dsm_launch_pool_retire(resident_view(ctx, 0), 0, ctx->res_upper, kf, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->stream);
+    CK(cudaGetLastError());
     const int c = h[0] < cap ? h[0] : cap;
     if (c > 0)
     {
@@ -1360,11 +1442,15 @@ extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_
     CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[0], 0));
     CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[1], 0));
     const size_t so = (size_t)par * (size_t)(ctx->p.max_batch / 2); // fixed halves: runs of different length never overlap
+    // pinned tables of this mode live in the second half of h_pose / h_ref (the first half belongs to the single-frame
+    // and batch calls, which only wait for their own copies before rewriting it); this half's previous table copy ran
+    // before ev_done[e], which has been waited for above
+    const size_t ho = (size_t)ctx->p.max_batch + so;
     for (int t = 0; t < n; t++)
     {
-        memcpy(ctx->h_pose + (so + t) * 32, poses + (size_t)t * 16, 16 * sizeof(float));
-        inverse4f(poses + (size_t)t * 16, ctx->h_pose + (so + t) * 32 + 16);
-        ctx->h_ref[so + t] = ref_idx[t];
+        memcpy(ctx->h_pose + (ho + t) * 32, poses + (size_t)t * 16, 16 * sizeof(float));
+        inverse4f(poses + (size_t)t * 16, ctx->h_pose + (ho + t) * 32 + 16);
+        ctx->h_ref[ho + t] = ref_idx[t];
     }
     uint8_t *gp = ctx->gray_packed + so * fpx;
     float *dp = ctx->depth_packed + so * fpx;
@@ -1373,9 +1459,9 @@ extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_
     CK(cudaEventRecord(ctx->ev_h2d[e], ctx->s_h2d));
     cudaStream_t st = ctx->stream;
     // the small tables go on the compute stream: the previous run's kernels read the same device tables
-    CK(cudaMemcpy2DAsync(ctx->pose, 16 * sizeof(float), ctx->h_pose + so * 32, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpy2DAsync(ctx->ipose, 16 * sizeof(float), ctx->h_pose + so * 32 + 16, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->refidx, ctx->h_ref + so, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(ctx->pose, 16 * sizeof(float), ctx->h_pose + ho * 32, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(ctx->ipose, 16 * sizeof(float), ctx->h_pose + ho * 32 + 16, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->refidx, ctx->h_ref + ho, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaStreamWaitEvent(st, ctx->ev_h2d[e], 0));
     {
         DsmDev d = ctx->d;
@@ -1441,7 +1527,8 @@ extern "C" int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds)
     if (!ctx || !seeds || frame < 0 || frame >= ctx->p.max_batch) return DSM_E_INVALID;
     if (!ctx->ran) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < 15) ? 1 : 0, ctx->stream);
+    const int plane_done = (ctx->d.variants & DSM_VARIANT_LEGACY) ? 15 : 9; // kernels of the schedule up to and including the plane fit
+    dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < plane_done) ? 1 : 0, ctx->stream);
     CK(cudaMemcpyAsync(seeds, ctx->seed_export, (size_t)ctx->S * sizeof(dsm_seed_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());

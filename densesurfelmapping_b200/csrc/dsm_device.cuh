@@ -25,6 +25,7 @@
 //   pose/ipose f32 [B][16] column-major, refidx i32 [B]
 #pragma once
 #include <cstdint>
+#include <cuda.h> // CUtensorMap (types only; the encoder is resolved through the runtime, no libcuda link dependency)
 #include <cuda_runtime.h>
 #include "../../include/dsm.h"
 
@@ -69,6 +70,11 @@ struct DsmDev
     const float *ipose;
     const int32_t *refidx;
     int max_pool_per_frame; // largest per-frame pool slice in this batch (grid sizing)
+    // tile path (dsm_tile.cu)
+    float *invd;        // [B][H][Wp] (float)(1.0 / (double)depth) for depth > 0.01, else 0 (:404-405), written by the first assign pass
+    float2 *seed_hl;    // [B][S] 1.0 / (double)mean_depth split into two floats (hi, lo) for the filtered assign pass
+    int32_t *done;      // [B] frame-completion tickets of the assign pass (the last CTA of a frame runs the stable relaxation)
+    double *hrec;       // [B][S][10] plane fit: sum 2 q q^T over the centred inliers (9 entries) + packed (rmax, qmax2) of the first residual pass
     int variants;           // DSM_VARIANT_* bits: experimental kernel variants (0 = the measured default path)
 };
 
@@ -81,7 +87,21 @@ struct DsmDev
 #define DSM_VARIANT_NORMALS_FORK 32u   // host schedule: the pixel-normal pass runs on a side stream concurrently with the clustering
 #define DSM_VARIANT_SEED_INIT_WIDE 64u  // k_seed_init_wide: hole search with the whole window in flight
 #define DSM_VARIANT_ASSIGN_FEWER_CVT 128u // k_assign_x: two of the seven float<->double conversions per candidate done on the fp64 pipe
+#define DSM_VARIANT_LEGACY 256u       // round-1 schedule (17 launches, kernels of dsm_kernels.cu) instead of the tile schedule
 #define DSM_VARIANT_GN_STAGED 8u      // k_gauss_newton_staged: point list streamed through shared memory (cp.async, double-buffered)
+
+// TMA descriptors (cuTensorMapEncodeTiled) of the three per-pixel arrays as [B][H][Wp] tensors; box = one seed tile plus halo
+struct DsmMaps
+{
+    CUtensorMap lab, dep, gry;
+};
+// seed tile of the tile kernels: 8 x 4 superpixels = 64 x 32 pixels, plus a 4-pixel halo (the 16 x 16 windows of
+// update_seeds_kernel :481-489 and calculate_sp_depth_norms_kernel :806-811 overlap their neighbours by 8)
+#define DSM_TILE_SX 8
+#define DSM_TILE_SY 4
+#define DSM_TILE_W 76  // box width in elements: 72 used; row pitch 76 words = 12 mod 32, so a quarter-warp reading 16 bytes per lane from 8 consecutive rows hits 32 distinct banks
+#define DSM_TILE_H 41  // box height: 40 rows + the down neighbour of the last row (pixel normals)
+#define DSM_TILE_GW 80 // gray box width in bytes (multiple of 16; 20 words: conflict-free for the same access pattern)
 
 enum DsmKernelId
 {
@@ -97,6 +117,9 @@ enum DsmKernelId
     DSM_K_REPACK = 9,
     DSM_K_PIXEL_NORMALS = 10,
     DSM_K_GAUSS_NEWTON = 11,
+    DSM_K_UPDATE = 12,       // tile schedule: window gather + Huber-Newton
+    DSM_K_PLANE_GATHER = 13, // tile schedule: pixel normals + plane-fit gather
+    DSM_K_PLANE_SOLVE = 14,  // tile schedule: plane-fit solver
 };
 
 // launchers (dsm_kernels.cu); nb = frames in this batch
@@ -116,4 +139,10 @@ void dsm_launch_pool_compact(const DsmDev &d, int frame, int upper, int *blkcnt,
 void dsm_launch_pool_transform(const DsmDev &d, int frame, int upper, const float *Wm_dev, cudaStream_t s);
 void dsm_launch_pool_export(const DsmDev &d, int frame, int upper, int mode, int key, bool as_cloud, int *blkcnt, int *blkofs, int *newofs, void *dst, cudaStream_t s);
 void dsm_launch_set2(int32_t *p, int a, int b, cudaStream_t s);
+// tile path (dsm_tile.cu)
+int dsm_tile_setup(); // raises the dynamic shared-memory limits of the tile kernels (once per process and device)
+void dsm_launch_assign2(const DsmDev &d, int nb, bool first, cudaStream_t s);
+void dsm_launch_update(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s);
+void dsm_launch_plane_gather(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s);
+void dsm_launch_gn_solve(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_pool_retire(const DsmDev &d, int frame, int upper, int key, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, cudaStream_t s);

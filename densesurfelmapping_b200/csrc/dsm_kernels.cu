@@ -10,75 +10,8 @@
 // (-prec-div/-prec-sqrt defaults, no fast-math, no FTZ) and spells out every float<->double
 // promotion exactly where the reference's C++ expressions have them.  All citations
 // ":NNN" refer to /root/reference/surfel_fusion/src/fusion_functions.cpp.
-#include "dsm_device.cuh"
-#include <climits>
-#include <cuda/barrier>
-#include <cuda/ptx>
+#include "dsm_exact.cuh"
 #include <cuda_pipeline.h>
-
-#define HUBER_RANGE 0.4       // fusion_functions.h:13
-#define MAX_ANGLE_COS 0.1     // fusion_functions.h:11
-#define BASELINE 0.5          // fusion_functions.h:14
-#define DISPARITY_ERROR 4.0   // fusion_functions.h:15
-#define MIN_TOLERATE_DIFF 0.1 // fusion_functions.h:16
-
-#define FULL 0xffffffffu
-
-// Comparisons of a float against a double literal (the reference promotes the float): for a
-// literal c that is not a float, with c_lo/c_hi the neighbouring floats,
-//   (double)x <  c  <=>  x <  c_hi        (double)x >  c  <=>  x >  c_lo
-//   (double)x >= c  <=>  x >= c_hi        (double)x <= c  <=>  x <= c_lo
-// and for -c by symmetry (x > -c <=> x > -c_hi).  Used in the hot loops to keep the FP64 pipe for
-// the arithmetic that really needs it; tests/test_abi.py re-derives every constant.
-#define F_0p4_HI __uint_as_float(0x3ecccccdu)
-#define F_0p4_LO __uint_as_float(0x3eccccccu)
-#define F_0p1_HI __uint_as_float(0x3dcccccdu)
-#define F_0p1_LO __uint_as_float(0x3dccccccu)
-#define F_0p01_HI __uint_as_float(0x3c23d70bu)
-#define F_0p01_LO __uint_as_float(0x3c23d70au)
-#define F_0p05_LO __uint_as_float(0x3d4cccccu)
-#define F_0p2_HI __uint_as_float(0x3e4ccccdu)
-#define F_0p8_HI __uint_as_float(0x3f4ccccdu)
-
-// -------------------------------------------------------------------------------------------
-// small helpers
-// -------------------------------------------------------------------------------------------
-using dsm_barrier = cuda::barrier<cuda::thread_scope_block>; // mbarrier for the TMA (cp.async.bulk) stagings
-// Wait for phase 0 of a tile barrier.  Experimental kernels only: a byte-count mistake would otherwise spin forever and
-// take the GPU with it, so the wait is bounded (each try_wait already blocks for a hardware time slice) and traps.
-__device__ __forceinline__ void tile_wait(dsm_barrier &bar)
-{
-    for (unsigned spin = 0; !cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(bar), 0); spin++)
-        if (spin > (1u << 22)) __trap();
-}
-__device__ __forceinline__ void sts_f32(unsigned addr, float v)
-{ // st.shared with a precomputed 32-bit shared-window address (keeps the address math out of the hot loops)
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
-}
-__device__ __forceinline__ float warp_sum_f(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max_f(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total)
-{
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        int n = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += n;
-    }
-    total = __shfl_sync(FULL, incl, 31);
-    return incl - v;
-}
 
 // -------------------------------------------------------------------------------------------
 // Kin  repack — the caller's tightly packed [n][H][W] gray / depth arrive by ONE contiguous H2D copy
@@ -125,6 +58,7 @@ __global__ void __launch_bounds__(256) k_seed_init(const __grid_constant__ DsmDe
         d.nlist[b] = 0;
         d.nnew[b] = 0;
         d.errflag[b] = 0;
+        d.done[b] = 0;
     }
     const int W = d.W, H = d.H, Wp = d.Wp;
     const uint8_t *gray = d.gray + (size_t)b * d.px_stride;
@@ -170,6 +104,7 @@ __global__ void __launch_bounds__(256) k_seed_init(const __grid_constant__ DsmDe
     const size_t o = (size_t)b * d.S + s;
     d.seed[o] = make_float4((float)ix, (float)iy, (float)gray[iy * Wp + ix], md);
     d.inv_md[o] = 1.0 / (double)md; // only consumed when md > 0 (:378)
+    d.seed_hl[o] = split_inverse(md);
     d.tstable[o] = -1;              // stable = false
     d.fused[o] = 0;                 // fused = false
 }
@@ -188,6 +123,7 @@ __global__ void __launch_bounds__(256) k_seed_init_wide(const __grid_constant__ 
         d.nlist[b] = 0;
         d.nnew[b] = 0;
         d.errflag[b] = 0;
+        d.done[b] = 0;
     }
     const int W = d.W, H = d.H, Wp = d.Wp;
     const uint8_t *gray = d.gray + (size_t)b * d.px_stride;
@@ -235,6 +171,7 @@ __global__ void __launch_bounds__(256) k_seed_init_wide(const __grid_constant__ 
     const size_t o = (size_t)b * d.S + s;
     d.seed[o] = make_float4((float)ix, (float)iy, (float)gray[iy * Wp + ix], md);
     d.inv_md[o] = 1.0 / (double)md; // only consumed when md > 0 (:378)
+    d.seed_hl[o] = split_inverse(md);
     d.tstable[o] = -1;              // stable = false
     d.fused[o] = 0;                 // fused = false
 }
@@ -255,37 +192,6 @@ __global__ void __launch_bounds__(256) k_seed_init_wide(const __grid_constant__ 
 // k_relax resolves which of them the sequential raster scan would have evaluated.
 // In the first iteration every label is 0 and seed 0 is unstable, so everything commits.
 // -------------------------------------------------------------------------------------------
-struct SeedC
-{
-    float x, y, I, md;
-    double inv;
-};
-
-// Branch-free: both costs and the has-depth predicate are always computed; the caller selects.
-// (When mean_depth <= 0 the hoisted 1/mean_depth is inf/NaN; the result is discarded by the select.)
-__device__ __forceinline__ bool calc_cost(const SeedC &sd, float pix_i, float pix_inv, double pix_inv_d, float fx, float fy,
-                                          float &nodepth, float &withdepth)
-{
-    const float ax = sd.x - fx, ay = sd.y - fy;
-    const float dist = ax * ax + ay * ay;
-    float n = dist * 0.0625f; // / (SP_SIZE/2)^2, exact power of two (:374)
-    const float idf = sd.I - pix_i;
-    // (double)(idf*idf) / 100.0 (:376), correctly rounded without the division subroutine:
-    // q0 = RN(a*y), r = a - 100*q0 (exact in one FMA), q = RN(q0 + r*y) with y = RN(1/100) is the
-    // correctly rounded quotient (Markstein); checked against x/100.0 on 3.7e8 inputs.
-    const double a = (double)(idf * idf);
-    const double q0 = a * 0.01;
-    const double q = __fma_rn(__fma_rn(-q0, 100.0, a), 0.01, q0);
-    const double nd = (double)n + q;
-    n = (float)nd;
-    nodepth = n;
-    const bool has = sd.md > 0 && pix_inv > 0; // (:378)
-    const float idd = (float)(sd.inv - pix_inv_d);                  // (:380)
-    const float wd = (float)((double)n + (double)(idd * idd) * 400.0); // (:381)
-    withdepth = has ? wd : n;
-    return has;
-}
-
 // K1', EXPERIMENTAL (variant bit 7, off by default): the assign pass with 4 instead of 7
 // float<->double conversions per (pixel, candidate).  The pass is bound by the conversion unit (XU at 74-85 % of peak,
 // profiles/r1_final_pipes.csv).  Two of the reference's roundings to float -- (float)nd at :376 and the final (float) at
@@ -2687,7 +2593,7 @@ void dsm_launch_pool_retire(const DsmDev &d, int frame, int upper, int key, int 
     const int nblk = (upper + 255) / 256;
     if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt, 1, key);
     k_pool_scan<<<1, 1024, 0, s>>>(d, frame, blkcnt, blkofs, newofs);
-    if (nblk > 0) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst, 1, key);
+    if (nblk > 0 && dst) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst, 1, key); // dst == nullptr: count only
 }
 // publish/save filters (mode/key as pool_pred): as_cloud ? PointXYZI float4 records : whole 44-byte surfels, in pool
 // order to dst (count in newofs[0]); the pool itself is not modified

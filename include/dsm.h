@@ -265,7 +265,7 @@ int dsm_debug_set_variants(dsm_ctx *ctx, unsigned mask);
 /* ---- measurement hooks ----
  * Per-kernel CUDA-event timing on the context's stream.  mask selects kernels (bit k = kernel
  * id k, see dsm_kernel_name); 0 disables.  Accumulates until dsm_profile_reset(). */
-#define DSM_NUM_KERNELS 12
+#define DSM_NUM_KERNELS 15
 int dsm_profile_enable(dsm_ctx *ctx, uint32_t kernel_mask);
 int dsm_profile_reset(dsm_ctx *ctx);
 /* resolves pending events (synchronises); ms_total/launches are [DSM_NUM_KERNELS] */

@@ -66,9 +66,9 @@ def test_synthetic_generator_is_deterministic():
 
 
 def test_float_bounds_for_double_literal_compares():
-    """csrc/dsm_kernels.cu replaces `(double)x < c` by `x < c_hi` (and `> c` by `> c_lo`) in hot loops;
+    """csrc/dsm_exact.cuh (used by every kernel file) replaces `(double)x < c` by `x < c_hi` (and `> c` by `> c_lo`) in hot loops;
     every F_<c>_HI / _LO constant must be the float neighbour of the double literal c."""
-    src = open(os.path.join(ROOT, "densesurfelmapping_b200", "csrc", "dsm_kernels.cu")).read()
+    src = open(os.path.join(ROOT, "densesurfelmapping_b200", "csrc", "dsm_exact.cuh")).read()
     found = re.findall(r"#define F_(\d+)p(\d+)_(HI|LO) __uint_as_float\(0x([0-9a-f]+)u\)", src)
     assert len(found) >= 8
     for ip, fp, kind, hexv in found:
