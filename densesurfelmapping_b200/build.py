@@ -7,11 +7,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdsm_b200.so")
-SOURCES = ["dsm_kernels.cu", "dsm_tile.cu", "dsm_capi.cu", "dsm_io.cpp"]
+SOURCES = ["dsm_kernels.cu", "dsm_tile.cu", "dsm_capi.cu", "dsm_comm.cu", "dsm_io.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "shared",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "shared", "-ldl",
 ]
 
 

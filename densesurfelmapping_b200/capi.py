@@ -29,6 +29,8 @@ EXPORTS = [
     "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices", "dsm_debug_set_variants", "dsm_fuse_stream_resident",
     "dsm_inactive_reserve", "dsm_inactive_retire", "dsm_inactive_reactivate", "dsm_inactive_transform", "dsm_inactive_export_cloud",
     "dsm_inactive_download", "dsm_inactive_size",
+    "dsm_comm_unique_id", "dsm_comm_init", "dsm_comm_destroy", "dsm_gather_deltas", "dsm_gather_wait", "dsm_gathered_device",
+    "dsm_gathered_rank_bytes", "dsm_gathered_download",
 ]
 
 
@@ -107,8 +109,26 @@ def load_library():
     L.dsm_write_pcd.argtypes = [ctypes.c_char_p, vp, cs, ci]
     L.dsm_write_ply_mesh.argtypes = [ctypes.c_char_p, vp, cs]
     L.dsm_mesh_vertices.argtypes = [vp, cs, vp]
+    L.dsm_comm_unique_id.argtypes = [vp]
+    L.dsm_comm_init.argtypes = [vp, vp, ci, ci]
+    L.dsm_comm_destroy.argtypes = [vp]
+    L.dsm_gather_deltas.argtypes = [vp, ci]
+    L.dsm_gather_wait.argtypes = [vp]
+    L.dsm_gathered_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(cs)]
+    L.dsm_gathered_rank_bytes.argtypes = [vp, ci, ctypes.POINTER(cs)]
+    L.dsm_gathered_download.argtypes = [vp, ci, vp, cs]
     _lib = L
     return L
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it and hands it to the other ranks out of band)."""
+    L = load_library()
+    buf = ctypes.create_string_buffer(128)
+    rc = L.dsm_comm_unique_id(buf)
+    if rc != DSM_OK:
+        raise DsmError(rc, L.dsm_strerror(rc).decode())
+    return buf.raw
 
 
 def kernel_names():
@@ -197,6 +217,27 @@ class Context:
         self.batch_upload(ref_idx, gray, depth, poses, local, offsets)
         self.batch_run()
         return self.batch_download()
+
+    # ---- multi-GPU gather of the surfel deltas (csrc/dsm_comm.cu) ----
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        assert len(unique_id) == 128
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.dsm_comm_init(self.h, buf, int(rank), int(nranks)))
+        self.comm_rank, self.comm_size = rank, nranks
+
+    def gather_deltas(self, root=0):
+        self._ck(self.lib.dsm_gather_deltas(self.h, int(root)))
+
+    def gather_wait(self):
+        self._ck(self.lib.dsm_gather_wait(self.h))
+
+    def gathered_payload(self, rank):
+        """root only: the payload rank `rank` sent in the last gather, as a uint8 array (see gather.unpack_payload)."""
+        n = ctypes.c_size_t(0)
+        self._ck(self.lib.dsm_gathered_rank_bytes(self.h, int(rank), ctypes.byref(n)))
+        out = np.zeros(n.value, np.uint8)
+        self._ck(self.lib.dsm_gathered_download(self.h, int(rank), _ptr(out), n.value))
+        return out
 
     # ---- GPU-resident pool (stream mode) ----
     def pool_upload(self, local):

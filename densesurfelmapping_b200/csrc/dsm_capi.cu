@@ -2,7 +2,7 @@
 // kernel schedule (mirrors FusionFunctions::fuse_initialize_map / generate_super_pixels,
 // fusion_functions.cpp:30-83, :960-975) and the copies either side of it.
 // No CPU implementation of any phase lives here: if CUDA is unavailable every call fails.
-#include "dsm_device.cuh"
+#include "dsm_ctx.hpp"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -11,98 +11,10 @@
 #include <new>
 #include <vector>
 
-struct ProfRec
-{
-    int id;
-    cudaEvent_t e0, e1;
-};
-
-// A captured kernel schedule, replayable while every launch parameter is unchanged.
-struct GraphEntry
-{
-    int f0, nf, maxper, compact;
-    const void *pool, *poolofs, *alt;
-    cudaGraphExec_t exec;
-    int phase;
-};
-
-struct dsm_ctx
-{
-    dsm_params p;
-    int device;
-    cudaStream_t stream;
-    bool own_stream;
-    DsmDev d;
-    DsmMaps maps;  // TMA descriptors of labels / depth / gray for the tile kernels
-    int S, Wp;
-    size_t px;    // pitched pixels per frame
-    int nb;       // frames in the current batch
-    int n_pool;   // local surfels in the current batch
-    bool uploaded, ran;
-    bool in_flight; // a dsm_fuse_batch_async batch has been enqueued and not yet waited for
-    int stop_after; // debug: number of kernels to enqueue (<= 0: all)
-    std::vector<GraphEntry> graphs; // CUDA-graph cache of the kernel schedule (launch-bound single-frame / small-chunk runs)
-    bool use_graphs;
-    // raw allocations (non-const views of what DsmDev holds)
-    uint8_t *gray;
-    float *depth;
-    dsm_surfel_t *pool_snap;
-    int32_t *poolofs, *refidx;
-    float *pose, *ipose;
-    dsm_seed_t *seed_export;
-    float *kx, *ky;
-    // end-to-end pipeline (dsm_fuse_batch): packed staging + copy streams + per-chunk events
-    uint8_t *gray_packed; // [B][H][W]
-    float *depth_packed;  // [B][H][W]
-    cudaStream_t s_h2d, s_d2h, s_comp[4];
-    // resident pool (stream mode)
-    int res_upper;      // host-side upper bound of the resident pool size (exact after a sync)
-    bool res_active;
-    int res_frame;      // frames fused in resident mode so far (selects the frame slot)
-    int32_t *res_ofs;   // device [2]: {0, resident pool size}
-    int *blkcnt, *blkofs, *newofs;
-    float *wmat;        // device copy of the 4x4 of dsm_pool_transform
-    // inactive store (EXPERIMENTAL, dsm_inactive_*): the attached_surfels of every pose outside the drift-free window,
-    // dense on the device in retirement order; the (keyframe, offset, count) segment list lives on the host
-    dsm_surfel_t *inact;
-    int inact_cap, inact_size;
-    int32_t *inact_ofs; // device [2]
-    struct InactSeg
-    {
-        int kf, ofs, cnt;
-    };
-    std::vector<InactSeg> inact_segs;
-    cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
-    cudaStream_t s_fork[5];              // experimental (variant bit 5): side stream per compute stream for the forked pixel-normal pass
-    cudaEvent_t ev_fork_a[5], ev_fork_b[5];
-    // pinned host staging for the small per-batch tables
-    float *h_pose; // [B][32]: pose then inverse
-    int32_t *h_ofs;
-    int32_t *h_ref;
-    // profiling
-    uint32_t prof_mask;
-    std::vector<ProfRec> prof_pending;
-    std::vector<cudaEvent_t> ev_free;
-    float prof_ms[DSM_NUM_KERNELS];
-    int32_t prof_n[DSM_NUM_KERNELS];
-    char err[512];
-};
-
 static const char *kKernelNames[DSM_NUM_KERNELS] = {
     "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_gather_depths", "slic_newton",
     "plane_gather_points", "surfel_fuse", "surfel_init", "repack", "pixel_normals", "plane_gauss_newton",
-    "slic_update", "plane_gather", "plane_solve"};
-
-#define CK(call)                                                                                         \
-    do                                                                                                   \
-    {                                                                                                    \
-        cudaError_t _e = (call);                                                                         \
-        if (_e != cudaSuccess)                                                                           \
-        {                                                                                                \
-            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
-            return DSM_E_CUDA;                                                                           \
-        }                                                                                                \
-    } while (0)
+    "slic_gather", "plane_gather", "plane_solve"};
 
 extern "C" int dsm_version(void) { return DSM_VERSION; }
 
@@ -140,6 +52,7 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    dsm_comm_destroy(ctx);
     // an asynchronous batch may still be in flight on any of the context's streams
     if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
     for (int i = 0; i < 4; i++)
@@ -283,6 +196,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     if (!ctx) return DSM_E_NOMEM;
     memset(&ctx->d, 0, sizeof(ctx->d));
     ctx->p = *params;
+    ctx->comm = nullptr;
     ctx->device = device;
     ctx->err[0] = 0;
     ctx->prof_mask = 0;
@@ -345,13 +259,13 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.invd, B * px + 64);
     ALLOC(d.seed_hl, (size_t)B * S);
     ALLOC(d.done, (size_t)B);
-    ALLOC(d.hrec, (size_t)B * S * 10);
+    ALLOC(d.hrec, (size_t)B * S * 24);
     ALLOC(d.tstable, (size_t)B * S);
     ALLOC(d.usum, (size_t)B * S);
     ALLOC(d.und, (size_t)B * S);
-    ALLOC(d.dlist, (size_t)B * 228 * ((S + 31) / 32 * 32));
+    ALLOC(d.dlist, (size_t)B * 232 * ((S + 31) / 32 * 32)); // tile schedule: [B][S][232]; round-1 schedule: [B][228][Sp]
     ALLOC(d.errflag, (size_t)B);
-    ALLOC(d.qlist, (size_t)3 * B * 228 * ((S + 31) / 32 * 32));
+    ALLOC(d.qlist, (size_t)3 * B * 232 * ((S + 31) / 32 * 32)); // tile schedule: [B][S][3][232]; round-1 schedule: [3][B][228][Sp]
     ALLOC(d.pfsum, (size_t)B * S * 2);
     ALLOC(d.plane, (size_t)B * S * 3);
     ALLOC(d.fused, (size_t)B * S);
@@ -669,12 +583,13 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
         CK(cudaEventRecord(ctx->ev_fork_b[fk], ctx->s_fork[fk]));
     }
     if ((phase & 1) && !(d.variants & DSM_VARIANT_LEGACY))
-    { // tile schedule (dsm_tile.cu): 9 launches for generate_super_pixels (:960-975)
+    { // tile schedule (dsm_tile.cu): 12 launches for generate_super_pixels (:960-975)
         STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
         for (int it = 0; it < 3; it++) // ITERATION_NUM (fusion_functions.h:8)
         {
             STEP(it == 0 ? DSM_K_ASSIGN_FIRST : DSM_K_ASSIGN, dsm_launch_assign2(d, nb, it == 0, st)); // relax folded in
-            STEP(DSM_K_UPDATE, dsm_launch_update(d, ctx->maps, nb, st));
+            STEP(DSM_K_UPDATE, dsm_launch_gather(d, ctx->maps, nb, st));
+            STEP(DSM_K_NEWTON, dsm_launch_newton2(d, nb, st));
         }
         STEP(DSM_K_PLANE_GATHER, dsm_launch_plane_gather(d, ctx->maps, nb, st));
         STEP(DSM_K_PLANE_SOLVE, dsm_launch_gn_solve(d, nb, st));
@@ -1527,7 +1442,7 @@ extern "C" int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds)
     if (!ctx || !seeds || frame < 0 || frame >= ctx->p.max_batch) return DSM_E_INVALID;
     if (!ctx->ran) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    const int plane_done = (ctx->d.variants & DSM_VARIANT_LEGACY) ? 15 : 9; // kernels of the schedule up to and including the plane fit
+    const int plane_done = (ctx->d.variants & DSM_VARIANT_LEGACY) ? 15 : 12; // kernels of the schedule up to and including the plane fit
     dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < plane_done) ? 1 : 0, ctx->stream);
     CK(cudaMemcpyAsync(seeds, ctx->seed_export, (size_t)ctx->S * sizeof(dsm_seed_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

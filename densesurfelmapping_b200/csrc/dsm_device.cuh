@@ -74,7 +74,7 @@ struct DsmDev
     float *invd;        // [B][H][Wp] (float)(1.0 / (double)depth) for depth > 0.01, else 0 (:404-405), written by the first assign pass
     float2 *seed_hl;    // [B][S] 1.0 / (double)mean_depth split into two floats (hi, lo) for the filtered assign pass
     int32_t *done;      // [B] frame-completion tickets of the assign pass (the last CTA of a frame runs the stable relaxation)
-    double *hrec;       // [B][S][10] plane fit: sum 2 q q^T over the centred inliers (9 entries) + packed (rmax, qmax2) of the first residual pass
+    double *hrec;       // [B][S][24] plane fit, first residual pass: H = sum 2 q q^T (9), the same over out-of-range points (10), their clamped gradient (4), packed (margin, qmax2)
     int variants;           // DSM_VARIANT_* bits: experimental kernel variants (0 = the measured default path)
 };
 
@@ -101,7 +101,10 @@ struct DsmMaps
 #define DSM_TILE_SY 4
 #define DSM_TILE_W 76  // box width in elements: 72 used; row pitch 76 words = 12 mod 32, so a quarter-warp reading 16 bytes per lane from 8 consecutive rows hits 32 distinct banks
 #define DSM_TILE_H 41  // box height: 40 rows + the down neighbour of the last row (pixel normals)
-#define DSM_TILE_GW 80 // gray box width in bytes (multiple of 16; 20 words: conflict-free for the same access pattern)
+// gray (u8) box: TMA needs the box start 16-byte aligned in global memory, which 64 bx - 4 is for the 4-byte arrays but
+// not for bytes, so the gray box starts DSM_TILE_GX = 12 pixels further left (64 bx - 16) and is 112 bytes wide
+#define DSM_TILE_GW 112
+#define DSM_TILE_GX 12
 
 enum DsmKernelId
 {
@@ -117,7 +120,7 @@ enum DsmKernelId
     DSM_K_REPACK = 9,
     DSM_K_PIXEL_NORMALS = 10,
     DSM_K_GAUSS_NEWTON = 11,
-    DSM_K_UPDATE = 12,       // tile schedule: window gather + Huber-Newton
+    DSM_K_UPDATE = 12,       // tile schedule: window gather (the Huber-Newton solve reports as slic_newton)
     DSM_K_PLANE_GATHER = 13, // tile schedule: pixel normals + plane-fit gather
     DSM_K_PLANE_SOLVE = 14,  // tile schedule: plane-fit solver
 };
@@ -142,7 +145,8 @@ void dsm_launch_set2(int32_t *p, int a, int b, cudaStream_t s);
 // tile path (dsm_tile.cu)
 int dsm_tile_setup(); // raises the dynamic shared-memory limits of the tile kernels (once per process and device)
 void dsm_launch_assign2(const DsmDev &d, int nb, bool first, cudaStream_t s);
-void dsm_launch_update(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s);
+void dsm_launch_gather(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s);
+void dsm_launch_newton2(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_plane_gather(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s);
 void dsm_launch_gn_solve(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_pool_retire(const DsmDev &d, int frame, int upper, int key, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, cudaStream_t s);

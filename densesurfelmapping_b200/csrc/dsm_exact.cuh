@@ -71,13 +71,13 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total)
 }
 
 // (hi, lo) split of 1.0 / (double)mean_depth for the fp32 cost filter.  mean_depth <= 0 (or NaN): the candidate has no
-// depth term (:378), the pair is unused.  mean_depth < 2^-10: hi = +inf -- the depth term of such a seed exceeds 1e6 for
+// depth term (:378), the pair is unused.  mean_depth < 2^-10: hi = 1e18 (its square is still finite, so a zero depth weight cannot produce a NaN) -- the depth term of such a seed exceeds 1e6 for
 // every valid pixel depth (> 0.01 m, i.e. inverse < 100), so it can never be the minimum (:408, :427) and the filter
 // may ignore it; if NO candidate stays below 1e6 the pixel goes to the exact path anyway.
 __device__ __forceinline__ float2 split_inverse(float md)
 {
     if (!(md > 0.f)) return make_float2(0.f, 0.f);
-    if (md < 0.0009765625f) return make_float2(__int_as_float(0x7f800000), 0.f);
+    if (md < 0.0009765625f) return make_float2(1e18f, 0.f);
     const double inv = 1.0 / (double)md;
     const float hi = (float)inv;
     return make_float2(hi, (float)(inv - (double)hi));

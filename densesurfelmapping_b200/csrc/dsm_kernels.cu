@@ -2565,8 +2565,8 @@ void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s)
 }
 void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s)
 {
-    if (d.variants & DSM_VARIANT_INIT_MULTIBLOCK)
-    {
+    if (!(d.variants & DSM_VARIANT_LEGACY) || (d.variants & DSM_VARIANT_INIT_MULTIBLOCK))
+    { // several CTAs per frame (verified byte-identical on the B200, round 2); the one-CTA kernel stays with the round-1 schedule
         dim3 grid((d.S + 1023) / 1024, nb);
         k_init_surfels_mb<<<grid, 1024, 0, s>>>(d);
         return;

@@ -107,8 +107,13 @@ __device__ __forceinline__ void relax_frame(const DsmDev &d, int b, int tid, int
     }
 }
 
+__device__ __forceinline__ float pick4(float a0, float a1, float a2, float a3, int i)
+{
+    return i == 0 ? a0 : (i == 1 ? a1 : (i == 2 ? a2 : a3));
+}
+
 template <bool FIRST>
-__global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmDev d)
 {
     __shared__ int s_last;
     const int b = d.frame0 + blockIdx.z;
@@ -150,80 +155,81 @@ __global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmD
         const bool vxa = xa >= 0 && xa < d.spw, vxb = xb >= 0 && xb < d.spw;
         const bool vya = ya >= 0 && ya < d.sph, vyb = (ry != 4) && yb >= 0 && yb < d.sph;
         // candidate c = 2*ix + iy  -> (xa,ya) (xa,yb) (xb,ya) (xb,yb): dx outer, dy inner (:413-414)
-        float4 sd[4];
-        float2 hl[4];
+        // fast-path operands, shared by the thread's 4 pixels.  Coordinates are pre-scaled by 1/4 (exact), so that
+        // dist/16 (:374) is ax'^2 + ay'^2; an invalid candidate sits 1e18 away: its cost (~1e36, finite) is never the minimum
+        // and the filter arithmetic stays NaN-free.  When the pixel at x%8 == 4 sees only its own seed column (:418-420)
+        // the candidates of column xb get the same treatment for that pixel only (sxq0).
+        float sxq[4], sxq0[4], ayy[4], sI[4], shi[4], slo[4];
         bool sv[4];
         int sidx[4];
+        bool allmd = true, allmd0 = true; // every valid candidate seed has mean_depth > 0 (:378), over 4 / over column xa only
+        const float fyq = (float)y * 0.25f;
 #pragma unroll
         for (int c = 0; c < 4; c++)
         {
             const int cx = (c >> 1) ? xb : xa, cy = (c & 1) ? yb : ya;
             sv[c] = ((c >> 1) ? vxb : vxa) && ((c & 1) ? vyb : vya);
             sidx[c] = cy * d.spw + cx;
-            const int li = sv[c] ? sidx[c] : 0; // invalid candidates read seed 0 and are masked out below
-            sd[c] = d.seed[so + li];
-            hl[c] = d.seed_hl[so + li];
+            const int li = sv[c] ? sidx[c] : 0; // invalid candidates read seed 0 and are pushed away below
+            const float4 s4 = d.seed[so + li];
+            const float2 hl = d.seed_hl[so + li];
+            sxq[c] = sv[c] ? s4.x * 0.25f : 1e18f;
+            sxq0[c] = ((c >> 1) && rx0 == 4) ? 1e18f : sxq[c];
+            const float ay = s4.y * 0.25f - fyq;
+            ayy[c] = ay * ay;
+            sI[c] = s4.z, shi[c] = hl.x, slo[c] = hl.y;
+            const bool mdpos = s4.w > 0.f || !sv[c];
+            allmd &= mdpos;
+            if (!(c >> 1)) allmd0 &= mdpos;
         }
-        const float fy = (float)y;
+        if (rx0 != 4) allmd0 = allmd;
         unsigned uncertain = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++)
         {
-            const float fx = (float)(x4 + i);
+            const float fxq = (float)(x4 + i) * 0.25f;
             const float pi = gi[i], pv = iv[i];
-            const bool hp = pv > 0.f;
-            float cn[4], cd[4];
-            bool vc[4];
-            bool all_has_depth = true;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-            { // x%8 == 4 sees only its own column (rx0==4, i==0 -> only xa), (:418-420)
-                vc[c] = sv[c] && ((c >> 1) ? !(rx0 == 4 && i == 0) : true);
-                const float ax = sd[c].x - fx, ay = sd[c].y - fy;
-                const float n = fmaf(ax, ax, ay * ay) * 0.0625f;
-                const float idf = sd[c].z - pi;
-                cn[c] = fmaf(idf * idf, 0.01f, n);
-                const float t = (hl[c].x - pv) + hl[c].y;
-                cd[c] = fmaf(t * t, 400.f, cn[c]);
-                all_has_depth &= (sd[c].w > 0.f && hp) || !vc[c];
-            }
-            float m1 = A_BIG, m2 = A_BIG;
-            int i1 = -1;
+            // all_has_depth (:443): every valid candidate has a depth and so has the pixel -> costs with the depth term, else without
+            const float w = (pv > 0.f && (i == 0 ? allmd0 : allmd)) ? 400.f : 0.f;
+            float cost[4];
 #pragma unroll
             for (int c = 0; c < 4; c++)
             {
-                const float cost = all_has_depth ? cd[c] : cn[c];
-                if (vc[c])
-                {
-                    if (cost < m1)
-                    {
-                        m2 = m1;
-                        m1 = cost;
-                        i1 = sidx[c];
-                    }
-                    else if (cost < m2)
-                        m2 = cost;
-                }
+                const float ax = (i == 0 ? sxq0[c] : sxq[c]) - fxq;
+                const float n = fmaf(ax, ax, ayy[c]);
+                const float idf = sI[c] - pi;
+                const float cn = fmaf(idf * idf, 0.01f, n);
+                const float t = (shi[c] - pv) + slo[c];
+                cost[c] = fmaf(t * t, w, cn);
             }
+            const float lo01 = fminf(cost[0], cost[1]), hi01 = fmaxf(cost[0], cost[1]);
+            const float lo23 = fminf(cost[2], cost[3]), hi23 = fmaxf(cost[2], cost[3]);
+            const float m1 = fminf(lo01, lo23);
+            const float m2 = fminf(fminf(fmaxf(lo01, lo23), fminf(hi01, hi23)), A_BIG); // second smallest, kept finite
+            win[i] = cost[0] == m1 ? sidx[0] : (cost[1] == m1 ? sidx[1] : (cost[2] == m1 ? sidx[2] : sidx[3]));
             const bool certain = (m2 - m1 > A_EPS * (m2 + m1) + A_ALPHA) && (m1 < 9e5f);
-            win[i] = i1;
             if (!certain) uncertain |= 1u << i;
         }
         if (uncertain)
-        { // exact path: the reference's expression, candidate order and strict '<' (first wins)
+        { // exact path: the reference's expression, candidate order and strict '<' (first wins).  Each lane walks its OWN
+          // flagged pixels, so a warp pays max-per-lane (usually one) exact evaluations, not one per pixel slot.
             SeedC sc[4];
 #pragma unroll
             for (int c = 0; c < 4; c++)
             {
-                sc[c].x = sd[c].x, sc[c].y = sd[c].y, sc[c].I = sd[c].z, sc[c].md = sd[c].w;
-                sc[c].inv = 1.0 / (double)sd[c].w; // only consumed when mean_depth > 0 (:378)
+                const int li = sv[c] ? sidx[c] : 0;
+                const float4 s4 = d.seed[so + li];
+                sc[c].x = s4.x, sc[c].y = s4.y, sc[c].I = s4.z, sc[c].md = s4.w;
+                sc[c].inv = d.inv_md[so + li]; // 1.0 / (double)mean_depth, only consumed when mean_depth > 0 (:378)
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
+            const float fy = (float)y;
+            while (uncertain)
             {
-                if (!((uncertain >> i) & 1u)) continue;
+                const int i = __ffs(uncertain) - 1;
+                uncertain &= uncertain - 1;
                 const float fx = (float)(x4 + i);
-                const float my_inv = iv[i];
+                const float my_i = pick4(gi[0], gi[1], gi[2], gi[3], i);
+                const float my_inv = pick4(iv[0], iv[1], iv[2], iv[3], i);
                 const double my_inv_d = (double)my_inv;
                 float min_d = 1e6f, min_nd = 1e6f;
                 int idx_d = -1, idx_nd = -1;
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmD
                 {
                     const bool valid = sv[c] && ((c >> 1) ? !(rx0 == 4 && i == 0) : true);
                     float cnd, cdd;
-                    const bool has = calc_cost(sc[c], gi[i], my_inv, my_inv_d, fx, fy, cnd, cdd);
+                    const bool has = calc_cost(sc[c], my_i, my_inv, my_inv_d, fx, fy, cnd, cdd);
                     cdd = valid ? cdd : __int_as_float(0x7f800000);
                     cnd = valid ? cnd : __int_as_float(0x7f800000);
                     all_has_depth &= has || !valid;
@@ -243,7 +249,11 @@ __global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmD
                     min_nd = bn ? cnd : min_nd;
                     idx_nd = bn ? sidx[c] : idx_nd;
                 }
-                win[i] = all_has_depth ? idx_d : idx_nd;
+                const int wv = all_has_depth ? idx_d : idx_nd;
+                win[0] = i == 0 ? wv : win[0];
+                win[1] = i == 1 ? wv : win[1];
+                win[2] = i == 2 ? wv : win[2];
+                win[3] = i == 3 ? wv : win[3];
             }
         }
 #pragma unroll
@@ -262,7 +272,9 @@ __global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmD
         return;
     }
 
-    // ---- iterations 2..: commit / defer (see k_assign)
+    // ---- iterations 2..: commit / defer (see k_assign).  A deferred pixel whose winner IS its current label is dropped:
+    // if the raster scan evaluates it (t[label] < idx) the label does not change and the stamp t[winner] = t[label] is
+    // already below idx, so it can change nothing -- the relaxation only ever needs the pixels that would switch seeds.
     int2 ent[4];
     int nent = 0;
     if (active)
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmD
                 }
                 if (d.tstable[so + win[i]] > pidx) atomicMin(&d.tstable[so + win[i]], pidx); // stable = false at time pidx (:445/:450)
             }
-            else
+            else if (win[i] != L[i])
             {
                 ent[nent++] = make_int2(pidx, win[i]);
             }
@@ -294,11 +306,11 @@ __global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmD
             *reinterpret_cast<int4 *>(d.labels + po) = make_int4(L[0], L[1], L[2], L[3]);
         }
     }
-    // warp-aggregated append of the deferred pixels
-    int total;
-    const int excl = warp_excl_scan(nent, lane, total);
-    if (total > 0)
+    // warp-aggregated append of the deferred pixels (rare: most warps have none)
+    if (__any_sync(FULL, nent > 0))
     {
+        int total;
+        const int excl = warp_excl_scan(nent, lane, total);
         int base = 0;
         if (lane == 31) base = atomicAdd(&d.nlist[b], total);
         base = __shfl_sync(FULL, base, 31);
@@ -320,42 +332,53 @@ __global__ void __launch_bounds__(256, 3) k_assign2(const __grid_constant__ DsmD
 }
 
 // -------------------------------------------------------------------------------------------
-// K2  slic_update — update_seeds_kernel (:468-562), gather and Huber-Newton in ONE kernel per seed tile
+// K2  slic_update — update_seeds_kernel (:468-562), as a tile gather and a per-seed solve
 //
-// A CTA owns DSM_TILE_SX x DSM_TILE_SY = 32 seeds.  One thread arms an mbarrier and issues three TMA tensor copies
-// (labels, depth, gray boxes of 76x41 / 80x41 elements at pixel (64 bx - 4, 32 by - 4); out-of-image parts are
-// zero-filled by the hardware and masked by coordinates below exactly like the reference's clamped loops).
-// Gather: a half-warp per seed, lane = window row.  A lane reads its row's 16 pixels with conflict-free
-// 16-byte shared loads, tests membership once per pixel, and the 16 lanes combine the exactly representable
-// integer sums (count, sum x, sum y, sum intensity: < 2^24, so the reference's float accumulation is exact and
-// order-free) with packed xor-butterflies.  Member depths > 0.1 are compacted IN RASTER ORDER (row-major = lane
-// order, then column order inside the lane) into a per-seed list in shared memory.
-// Newton: one thread per seed walks its list sequentially -- the float sums sum_depth (:511) and sum_a (:536-549)
-// feed the next pass's costs and are order-sensitive -- with list stride 229 words (conflict-free).
+// K2a k_gather (CTA = DSM_TILE_SX x DSM_TILE_SY = 32 seeds).  One thread arms an mbarrier and issues three TMA tensor
+//   copies (labels, depth boxes of 76x41 elements at pixel (64 bx - 4, 32 by - 4), gray box of 112x41 at (64 bx - 16,
+//   32 by - 4); out-of-image parts are zero-filled by the hardware and masked by coordinates below exactly like the
+//   reference's clamped loops).  A half-warp serves one seed, lane = window row: a lane reads its row's 16 pixels with
+//   conflict-free 16-byte shared loads and turns them into a 16-bit membership mask; count, sum x, sum y and sum
+//   intensity (exactly representable integers < 2^24, so the reference's float accumulation is exact and order-free)
+//   come from population counts and byte dot products of the mask and are combined over the 16 lanes by packed
+//   xor-butterflies.  Member depths > 0.1 are compacted IN RASTER ORDER (row-major = lane order, then column order
+//   inside the lane) into a per-seed list staged in shared memory and copied out as contiguous 16-byte runs:
+//   dlist[b][seed][DL_STRIDE].
+// K2b k_newton2 (thread per seed, every seed of the batch in flight): the float sums sum_depth (:511) and sum_a
+//   (:536-549) feed the next pass's costs and are order-sensitive, so one thread walks its seed's list
+//   sequentially, 8 entries (two 16-byte loads = one 32-byte sector) per step.  residual = fl(md - z) is monotone
+//   in z, so the list's extremes (found during the mean pass) decide for ALL entries whether they are inside the
+//   Huber range; in that -- by far most common -- case a Newton pass is a pure dependent chain
+//   sum_a = fmaf(2, md - z, sum_a) (2 r is exact: the same single rounding as `sum_a += 2 * residual`).
 // -------------------------------------------------------------------------------------------
-#define UL_STRIDE 229 // >= 15*15 possible members; odd, so 32 lanes reading the same position of 32 lists hit 32 banks
+#define DL_STRIDE 232 // floats per seed list: >= 15*15 possible members, multiple of 8 (32-byte sectors)
 #define TILE_PLANE_BYTES 12544 // 76 * 41 * 4 = 12464 rounded up to 128: TMA destinations are 128-byte aligned
-#define UPD_SMEM_LAB 0
-#define UPD_SMEM_DEP TILE_PLANE_BYTES
-#define UPD_SMEM_GRY (2 * TILE_PLANE_BYTES)
-#define UPD_SMEM_LIST (UPD_SMEM_GRY + DSM_TILE_GW * DSM_TILE_H)           // 28208: multiple of 16
-#define UPD_SMEM_SUM (UPD_SMEM_LIST + 32 * UL_STRIDE * 4)                 // int4[32]
-#define UPD_SMEM_ND (UPD_SMEM_SUM + 32 * 16)                              // int[32] list lengths, int[32] flags
-#define UPD_SMEM_BAR (UPD_SMEM_ND + 64 * 4)
-#define UPD_SMEM_BYTES (UPD_SMEM_BAR + 16)
+#define GAT_SMEM_LAB 0
+#define GAT_SMEM_DEP TILE_PLANE_BYTES
+#define GAT_SMEM_GRY (2 * TILE_PLANE_BYTES)
+#define GAT_SMEM_LIST (GAT_SMEM_GRY + DSM_TILE_GW * DSM_TILE_H) // float [16][DL_STRIDE]: the 16 seeds of one round
+#define GAT_SMEM_ND (GAT_SMEM_LIST + 16 * DL_STRIDE * 4)        // int [16] list lengths of the round
+#define GAT_SMEM_BAR (GAT_SMEM_ND + 16 * 4)
+#define GAT_SMEM_BYTES (GAT_SMEM_BAR + 16)
 #define TILE_TX_BYTES (2u * DSM_TILE_W * DSM_TILE_H * 4u + (unsigned)DSM_TILE_GW * DSM_TILE_H)
 
-__global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
+// sum over the set bits k of a 16-bit mask of k: sum_j 2^j popc(mask & {k : bit j of k set})
+__device__ __forceinline__ int mask_index_sum(unsigned m)
+{
+    return __popc(m & 0xaaaau) + 2 * __popc(m & 0xccccu) + 4 * __popc(m & 0xf0f0u) + 8 * __popc(m & 0xff00u);
+}
+// 4-bit mask -> 0xff per set bit
+__device__ __forceinline__ unsigned nibble_to_bytes(unsigned n) { return (((n & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu; }
+
+__global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int32_t *t_lab = reinterpret_cast<const int32_t *>(smem + UPD_SMEM_LAB);
-    const float *t_dep = reinterpret_cast<const float *>(smem + UPD_SMEM_DEP);
-    const uint8_t *t_gry = smem + UPD_SMEM_GRY;
-    float *lists = reinterpret_cast<float *>(smem + UPD_SMEM_LIST);
-    int4 *s_sum = reinterpret_cast<int4 *>(smem + UPD_SMEM_SUM);
-    int *s_nd = reinterpret_cast<int *>(smem + UPD_SMEM_ND);
-    int *s_act = s_nd + 32;
-    const unsigned bar = smem_u32(smem + UPD_SMEM_BAR);
+    const int32_t *t_lab = reinterpret_cast<const int32_t *>(smem + GAT_SMEM_LAB);
+    const float *t_dep = reinterpret_cast<const float *>(smem + GAT_SMEM_DEP);
+    const uint8_t *t_gry = smem + GAT_SMEM_GRY;
+    float *lists = reinterpret_cast<float *>(smem + GAT_SMEM_LIST);
+    int *s_nd = reinterpret_cast<int *>(smem + GAT_SMEM_ND);
+    const unsigned bar = smem_u32(smem + GAT_SMEM_BAR);
 
     const int b = d.frame0 + blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,9 +387,9 @@ __global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDe
     {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, TILE_TX_BYTES);
-        tma_load_3d(smem_u32(smem + UPD_SMEM_LAB), &mp.lab, X0, Y0, b, bar);
-        tma_load_3d(smem_u32(smem + UPD_SMEM_DEP), &mp.dep, X0, Y0, b, bar);
-        tma_load_3d(smem_u32(smem + UPD_SMEM_GRY), &mp.gry, X0, Y0, b, bar);
+        tma_load_3d(smem_u32(smem + GAT_SMEM_LAB), &mp.lab, X0, Y0, b, bar);
+        tma_load_3d(smem_u32(smem + GAT_SMEM_DEP), &mp.dep, X0, Y0, b, bar);
+        tma_load_3d(smem_u32(smem + GAT_SMEM_GRY), &mp.gry, X0 - DSM_TILE_GX, Y0, b, bar);
     }
     const int W = d.W, H = d.H;
     const size_t so = (size_t)b * d.S;
@@ -386,7 +409,8 @@ __global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDe
 #pragma unroll
     for (int rd = 0; rd < 2; rd++)
     {
-        const int sl = rd * 16 + warp * 2 + half;
+        const int q = warp * 2 + half; // seed slot of this round
+        const int sl = rd * 16 + q;
         const int tx = sl & 7, ty = sl >> 3;
         const int sp_x = blockIdx.x * DSM_TILE_SX + tx, sp_y = blockIdx.y * DSM_TILE_SY + ty;
         const int s = sp_y * d.spw + sp_x;
@@ -397,37 +421,34 @@ __global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDe
         const int ye = (y0 + 16) < H - 1 ? (y0 + 16) : H - 1;
         const int y = y0 + r;
         const bool rowin = act && y >= yb && y < ye;
-        const int kb = xb - x0, ke = xe - x0; // member columns of the window: kb <= k < ke
+        // member columns of the window: xb - x0 <= k < xe - x0; nothing if the row is outside
+        const unsigned kmask = rowin ? (((1u << (xe - x0)) - 1u) & ~((1u << (xb - x0)) - 1u)) : 0u;
         const int trow = ty * DSM_SP + r, tcol = tx * DSM_SP;
-        int lk[16], gk[16];
         float zk[16];
+        unsigned mm = 0, zm = 0; // bit k: label == s / depth > 0.1
         {
             const int4 *pl = reinterpret_cast<const int4 *>(t_lab + trow * DSM_TILE_W + tcol);
             const float4 *pz = reinterpret_cast<const float4 *>(t_dep + trow * DSM_TILE_W + tcol);
-            const uint2 *pg = reinterpret_cast<const uint2 *>(t_gry + trow * DSM_TILE_GW + tcol);
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int qd = 0; qd < 4; qd++)
             {
-                const int4 a = pl[q];
-                const float4 z = pz[q];
-                lk[4 * q] = a.x, lk[4 * q + 1] = a.y, lk[4 * q + 2] = a.z, lk[4 * q + 3] = a.w;
-                zk[4 * q] = z.x, zk[4 * q + 1] = z.y, zk[4 * q + 2] = z.z, zk[4 * q + 3] = z.w;
+                const int4 a = pl[qd];
+                const float4 z = pz[qd];
+                mm |= (a.x == s ? 1u : 0u) << (4 * qd) | (a.y == s ? 2u : 0u) << (4 * qd) | (a.z == s ? 4u : 0u) << (4 * qd) | (a.w == s ? 8u : 0u) << (4 * qd);
+                zk[4 * qd] = z.x, zk[4 * qd + 1] = z.y, zk[4 * qd + 2] = z.z, zk[4 * qd + 3] = z.w;
             }
-            const uint2 g0 = pg[0], g1 = pg[1];
-            const unsigned gw[4] = {g0.x, g0.y, g1.x, g1.y};
 #pragma unroll
-            for (int k = 0; k < 16; k++) gk[k] = (gw[k >> 2] >> (8 * (k & 3))) & 0xffu;
+            for (int k = 0; k < 16; k++) zm |= (zk[k] > F_0p1_LO ? 1u : 0u) << k; // (double)depth > 0.1 (:508)
         }
-        int cnt = 0, sdx = 0, si = 0;
-        unsigned dm = 0; // bit k: member with depth > 0.1
-#pragma unroll
-        for (int k = 0; k < 16; k++)
+        mm &= kmask;
+        const unsigned dm = mm & zm; // member with depth > 0.1
+        const int cnt = __popc(mm);
+        const int sdx = mask_index_sum(mm);
+        int si = 0;
         {
-            const bool mem = rowin && lk[k] == s && k >= kb && k < ke;
-            cnt += mem ? 1 : 0;
-            sdx += mem ? k : 0;
-            si += mem ? gk[k] : 0;
-            if (mem && zk[k] > F_0p1_LO) dm |= 1u << k; // (double)depth > 0.1 (:508)
+            const unsigned *pg = reinterpret_cast<const unsigned *>(t_gry + trow * DSM_TILE_GW + DSM_TILE_GX + tcol); // 4-byte aligned
+#pragma unroll
+            for (int qd = 0; qd < 4; qd++) si = (int)__dp4a(pg[qd] & nibble_to_bytes(mm >> (4 * qd)), 0x01010101u, (unsigned)si);
         }
         // packed 16-lane butterflies: count <= 225 (8 bits) | sum intensity <= 57375 (16 bits);
         // sum (x - x0) <= 3375 (12 bits) | sum (y - y0) <= 3375
@@ -447,26 +468,74 @@ __global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDe
             if (r >= o) incl += nb;
         }
         const int ndt = __shfl_sync(FULL, incl, 15, 16);
-        float *lp = lists + sl * UL_STRIDE + (incl - c);
+        if (rd) __syncthreads(); // the previous round's lists have been copied out
+        float *lp = lists + q * DL_STRIDE + (incl - c);
 #pragma unroll
         for (int k = 0; k < 16; k++)
             if ((dm >> k) & 1u) *lp++ = zk[k];
         if (r == 0)
         {
-            const int n = pa & 0xff;
-            s_sum[sl] = make_int4(n, n * x0 + (pb & 0xfff), n * y0 + (pb >> 12), pa >> 8);
-            s_nd[sl] = ndt;
-            s_act[sl] = act ? 1 : 0;
+            s_nd[q] = act ? ndt : 0;
+            if (act)
+            {
+                const int n = pa & 0xff;
+                d.usum[so + s] = make_int4(n, n * x0 + (pb & 0xfff), n * y0 + (pb >> 12), pa >> 8);
+                d.und[so + s] = ndt;
+            }
+        }
+        __syncthreads();
+        // copy-out: seed slot q2 of this round -> dlist[b][seed][0 .. nd), 16 bytes per thread and step
+        for (int i = threadIdx.x; i < 16 * (DL_STRIDE / 4); i += 256)
+        {
+            const int q2 = i / (DL_STRIDE / 4), j4 = i - q2 * (DL_STRIDE / 4);
+            if (4 * j4 < s_nd[q2])
+            {
+                const int sl2 = rd * 16 + q2;
+                const int s2 = (blockIdx.y * DSM_TILE_SY + (sl2 >> 3)) * d.spw + blockIdx.x * DSM_TILE_SX + (sl2 & 7);
+                reinterpret_cast<float4 *>(d.dlist + (so + s2) * DL_STRIDE)[j4] = reinterpret_cast<const float4 *>(lists + q2 * DL_STRIDE)[j4];
+            }
         }
     }
+}
+
+#define NW_CAP 11776 // floats of list staging per 128-seed CTA (46 KB, static shared memory limit 48 KB): 92 entries per seed on average, 225 possible
+__global__ void __launch_bounds__(128, 4) k_newton2(const __grid_constant__ DsmDev d)
+{
+    // The lists of the CTA's 128 seeds are contiguous runs in global memory; the CTA copies them into shared memory with
+    // coalesced 16-byte accesses (one list after the other, lengths rounded up to 4) and every thread then walks its own
+    // list there up to six times.  Lists that do not fit (rare: NW_CAP covers 92 entries per seed) stay in global memory.
+    __shared__ __align__(16) float buf[NW_CAP];
+    __shared__ int s_off[128], s_len[128], s_wsum[4];
+    const int b = d.frame0 + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x * 128 + tid;
+    const size_t so = (size_t)b * d.S;
+    const bool act = s < d.S && d.tstable[so + s] != DSM_STABLE; // stable seeds are untouched by update_seeds (:478-479)
+    const int nd = act ? d.und[so + s] : 0;
+    {
+        const int len4 = (nd + 3) & ~3;
+        int wtot;
+        const int wex = warp_excl_scan(len4, lane, wtot);
+        if (lane == 31) s_wsum[warp] = wtot;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; w++) base += s_wsum[w];
+        const int off = base + wex;
+        s_off[tid] = (off + len4 <= NW_CAP) ? off : -1;
+        s_len[tid] = nd;
+    }
     __syncthreads();
-    if (warp != 0) return;
-    // ---- Huber-Newton, one thread per seed of the tile (text of k_newton, lists in shared memory)
-    const int sl = lane;
-    if (!s_act[sl]) return; // stable (untouched by update_seeds) or outside the seed grid
-    const int sp_x = blockIdx.x * DSM_TILE_SX + (sl & 7), sp_y = blockIdx.y * DSM_TILE_SY + (sl >> 3);
-    const int s = sp_y * d.spw + sp_x;
-    const int4 su = s_sum[sl];
+    for (int q = warp; q < 128; q += 4)
+    {
+        const int off = s_off[q], len = s_len[q];
+        if (off < 0 || len == 0) continue; // warp-uniform
+        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + blockIdx.x * 128 + q) * DL_STRIDE);
+        float4 *dst = reinterpret_cast<float4 *>(buf + off);
+        for (int j4 = lane; 4 * j4 < len; j4 += 32) dst[j4] = src[j4];
+    }
+    __syncthreads();
+    if (!act) return;
+    const int4 su = d.usum[so + s];
     const int n = su.x;
     if (n == 0)
     { // unreachable for supported shapes (every seed keeps its centre pixel); recorded, never silently ignored
@@ -482,70 +551,60 @@ __global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDe
     // ::fabs(double): float differences, summed in double, rounded once (:527)
     const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
     const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
-    const int nd = s_nd[sl];
     float md = 0.0f;
     if (nd > 0)
     {
-        const float *dl = lists + sl * UL_STRIDE;
-        float sum_d = 0.0f;
+        const float *dl = s_off[tid] >= 0 ? buf + s_off[tid] : d.dlist + (so + s) * DL_STRIDE; // generic: shared or global
+        const float4 *dl4 = reinterpret_cast<const float4 *>(dl);
+        float sum_d = 0.0f, zmn = __int_as_float(0x7f800000), zmx = 0.f;
         {
             int k = 0;
             for (; k + 8 <= nd; k += 8)
             {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = dl[k + j];
+                const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
+                const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int j = 0; j < 8; j++) sum_d += v[j]; // raster order (:511)
+                zmn = fminf(zmn, fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7]))));
+                zmx = fmaxf(zmx, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
             }
-            for (; k < nd; k++) sum_d += dl[k];
+            for (; k < nd; k++)
+            {
+                const float v = dl[k];
+                sum_d += v;
+                zmn = fminf(zmn, v);
+                zmx = fmaxf(zmx, v);
+            }
         }
         md = sum_d / (float)nd;
         for (int it = 0; it < 5; it++)
         { // damped Huber-Newton (:534-554)
             float sa = 0.0f, sb = 0.0f;
-            int k = 0;
-            for (; k + 8 <= nd; k += 8)
-            {
-                float rr[8];
-                bool allin = true;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
+            if ((md - zmn) < F_0p4_HI && (md - zmx) > -F_0p4_HI)
+            { // every entry inside the Huber range ((double)r < 0.4 && (double)r > -0.4, :540): pure chain, sum_b = nd exact +2 steps
+                int k = 0;
+                for (; k + 8 <= nd; k += 8)
                 {
-                    rr[j] = md - dl[k + j];
-                    allin &= rr[j] < F_0p4_HI && rr[j] > -F_0p4_HI; // (double)r < 0.4 && (double)r > -0.4
+                    const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
+                    sa = fmaf(2.0f, md - a.x, sa), sa = fmaf(2.0f, md - a.y, sa), sa = fmaf(2.0f, md - a.z, sa), sa = fmaf(2.0f, md - a.w, sa);
+                    sa = fmaf(2.0f, md - c.x, sa), sa = fmaf(2.0f, md - c.y, sa), sa = fmaf(2.0f, md - c.z, sa), sa = fmaf(2.0f, md - c.w, sa);
                 }
-                if (allin)
-                { // common case: every residual inside the Huber range -> pure float chain
-#pragma unroll
-                    for (int j = 0; j < 8; j++) sa += 2 * rr[j];
-                    sb += 16; // eight exact +2 steps
-                }
-                else
-                {
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                    {
-                        if (rr[j] < F_0p4_HI && rr[j] > -F_0p4_HI)
-                        {
-                            sa += 2 * rr[j];
-                            sb += 2;
-                        }
-                        else
-                            sa = (float)((double)sa + (rr[j] > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
-                    }
-                }
+                for (; k < nd; k++) sa = fmaf(2.0f, md - dl[k], sa);
+                sb = (float)(2 * nd);
             }
-            for (; k < nd; k++)
+            else
             {
-                const float rr = md - dl[k];
-                if (rr < F_0p4_HI && rr > -F_0p4_HI)
+                for (int k = 0; k < nd; k++)
                 {
-                    sa += 2 * rr;
-                    sb += 2;
+                    const float rr = md - dl[k];
+                    if (rr < F_0p4_HI && rr > -F_0p4_HI)
+                    {
+                        sa += 2 * rr;
+                        sb += 2;
+                    }
+                    else
+                        sa = (float)((double)sa + (rr > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
                 }
-                else
-                    sa = (float)((double)sa + (rr > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
             }
             const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
             md = md + delta;
@@ -554,6 +613,7 @@ __global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDe
     }
     d.seed[so + s] = make_float4(mx, my, mi, md);
     d.seed_hl[so + s] = split_inverse(md);
+    d.inv_md[so + s] = 1.0 / (double)md; // exact-path operand of the assign pass, only consumed when md > 0 (:378)
     d.tstable[so + s] = newstable ? DSM_STABLE : -1;
 }
 
@@ -562,47 +622,56 @@ __global__ void __launch_bounds__(256, 3) k_update(const __grid_constant__ DsmDe
 // window scan of calculate_sp_depth_norms_kernel (:792-863) fused on the same TMA-staged seed tile.
 //
 // The reference computes a normal for EVERY pixel and then reads the ones of a superpixel's inliers.  Here the
-// window scan (half-warp per seed, lane = window row) first compacts the INLIER pixel positions of each seed into
-// shared memory; a second, dense phase (one warp per seed, lane per inlier) computes exactly those pixels'
-// normals from the depth tile -- each inlier belongs to one seed, so no normal is computed twice and none is
-// ever written to HBM (the 12 B/px `nrm` planes of the round-1 schedule are gone).  The same phase forms the
-// back-projected points, their mean, the centred points (get_huber_norm :111-126), and the first Gauss-Newton
-// pass's point sums: H = sum 2 q q^T (fp64, :141-155 with every residual inside the Huber range), max |r| and
-// max |q|^2.  If max |r| < 0.4 the solver (k_gn_solve) never needs the points; otherwise it reads the centred
-// points this kernel leaves in the [k][seed] list (staged through shared memory: full 32-byte sectors).
+// window scan (half-warp per seed, lane = window row, membership / valid-depth / inlier masks) first compacts the
+// INLIER pixel positions of each seed into shared memory; a second, dense phase (8 lanes per seed, 4 seeds per warp,
+// every lane walks every 8th inlier) computes exactly those pixels' normals from the depth tile -- each inlier
+// belongs to one seed, so no normal is computed twice and none is ever written to HBM (the 12 B/px `nrm` planes of
+// the round-1 schedule are gone).  The same phase forms the back-projected points, their mean, the centred points
+// (get_huber_norm :111-126, written as 32-byte runs of the per-seed lists qlist[b][seed][plane][PL_STRIDE]) and
+// everything the first Gauss-Newton pass needs from the points: H = sum 2 q q^T over all points, the same sums over
+// the points whose first residual is outside the Huber range (ho) with their clamped gradient (jo) (:133-171), the
+// smallest distance of any |residual| to the range boundary and max |q|^2.  With these k_gn_solve takes its first
+// step -- and, as long as the accumulated parameter change provably cannot move any residual across the boundary,
+// every further step -- without touching the points.
+// Pixel normal, fast path: n / |n| and the view angle with MUFU reciprocal square roots (a few ulp); the only place
+// where the exact value matters is the `|view| < 0.1` skip test (:706), so a pixel whose view angle is within
+// 1e-4 of +-0.1 is re-evaluated with the reference's IEEE divisions / square roots.
 // Not label-affecting: float sums are lane-partial + tree (order-free within 1e-4).
 // -------------------------------------------------------------------------------------------
-#define PF_CAP 228
+#define PL_STRIDE 232 // floats per plane of a seed's centred-point list (>= 225, multiple of 8)
+#define HREC 24       // doubles per seed: H (9), ho (10), jo (4), packed (margin, qmax2)
 #define PG_SMEM_LAB 0
 #define PG_SMEM_DEP TILE_PLANE_BYTES
-#define PG_SMEM_POS (2 * TILE_PLANE_BYTES)                       // u16 [32][PF_CAP + 4]
+#define PG_SMEM_POS (2 * TILE_PLANE_BYTES)                       // u16 [32][PG_POS_STRIDE]
 #define PG_POS_STRIDE 232
-#define PG_SMEM_STAGE (PG_SMEM_POS + 32 * PG_POS_STRIDE * 2)     // float [3][8][PF_CAP + 1]
-#define PG_ST_STRIDE 229
-#define PG_SMEM_KX (PG_SMEM_STAGE + 3 * 8 * PG_ST_STRIDE * 4)    // float [80] kx, float [48] ky
+#define PG_SMEM_KX (PG_SMEM_POS + 32 * PG_POS_STRIDE * 2)        // float [80] kx, float [48] ky
 #define PG_SMEM_REC (PG_SMEM_KX + 128 * 4)                       // float maxd[32], int nvalid[32], int ninl[32]
 #define PG_SMEM_BAR (PG_SMEM_REC + 96 * 4)
 #define PG_SMEM_BYTES (PG_SMEM_BAR + 16)
 #define PG_TX_BYTES (2u * DSM_TILE_W * DSM_TILE_H * 4u)
 
-__device__ __forceinline__ double warp_sum_d(double v)
+__device__ __forceinline__ float group8_sum_f(float v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double group8_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 
-__global__ void __launch_bounds__(256, 3) k_plane_gather(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
+__global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int32_t *t_lab = reinterpret_cast<const int32_t *>(smem + PG_SMEM_LAB);
     const float *t_dep = reinterpret_cast<const float *>(smem + PG_SMEM_DEP);
     uint16_t *s_pos = reinterpret_cast<uint16_t *>(smem + PG_SMEM_POS);
-    float *s_stage = reinterpret_cast<float *>(smem + PG_SMEM_STAGE);
     float *s_kx = reinterpret_cast<float *>(smem + PG_SMEM_KX), *s_ky = s_kx + 80;
     float *s_maxd = reinterpret_cast<float *>(smem + PG_SMEM_REC);
     int *s_nvalid = reinterpret_cast<int *>(s_maxd + 32), *s_ninl = s_nvalid + 32;
-    __shared__ int s_rows;
     const unsigned bar = smem_u32(smem + PG_SMEM_BAR);
 
     const int b = d.frame0 + blockIdx.z;
@@ -656,46 +725,49 @@ __global__ void __launch_bounds__(256, 3) k_plane_gather(const __grid_constant__
         const int y = y0 + r;
         const bool rowin = live && y >= 0 && y < H; // window bounded by the flat index only (:816)
         const int kb = x0 < 0 ? -x0 : 0, ke = (W - x0) < 16 ? (W - x0) : 16;
+        const unsigned kmask = rowin ? (((1u << ke) - 1u) & ~((1u << kb) - 1u)) : 0u;
         const int trow = ty * DSM_SP + r, tcol = tx * DSM_SP;
-        int lk[16];
-        float zk[16];
+        unsigned mm = 0, vm = 0, im = 0; // bit k: label == s / depth > 0.05 / |mean_depth - depth| < 0.4
         {
             const int4 *pl = reinterpret_cast<const int4 *>(t_lab + trow * DSM_TILE_W + tcol);
             const float4 *pz = reinterpret_cast<const float4 *>(t_dep + trow * DSM_TILE_W + tcol);
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int qd = 0; qd < 4; qd++)
             {
-                const int4 a = pl[q];
-                const float4 z = pz[q];
-                lk[4 * q] = a.x, lk[4 * q + 1] = a.y, lk[4 * q + 2] = a.z, lk[4 * q + 3] = a.w;
-                zk[4 * q] = z.x, zk[4 * q + 1] = z.y, zk[4 * q + 2] = z.z, zk[4 * q + 3] = z.w;
+                const int4 a = pl[qd];
+                const float4 z = pz[qd];
+                mm |= ((a.x == s ? 1u : 0u) | (a.y == s ? 2u : 0u) | (a.z == s ? 4u : 0u) | (a.w == s ? 8u : 0u)) << (4 * qd);
+                const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    vm |= (zz[j] > F_0p05_LO ? 1u : 0u) << (4 * qd + j); // (double)depth > 0.05 (:827)
+                    const float rr = sd.w - zz[j];
+                    im |= ((rr < F_0p4_HI && rr > -F_0p4_HI) ? 1u : 0u) << (4 * qd + j); // inlier (:849-860)
+                }
             }
         }
-        const float yd = (float)y - sd.y;
-        const float yd2 = yd * yd;
+        mm &= kmask;
+        vm &= mm;
+        im &= vm;
+        // max squared pixel distance of a member to the seed (:821-823): dist = fl(fl(xd^2) + fl(yd^2)) is monotone in |xd|,
+        // so within the row it is attained at the leftmost or the rightmost member
         float maxd = 0.f;
-        int nvalid = 0;
-        unsigned inl = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++)
+        if (mm)
         {
-            const bool mem = rowin && lk[k] == s && k >= kb && k < ke;
-            const float xd = (float)(x0 + k) - sd.x;
-            const float dist = xd * xd + yd2;
-            if (mem && dist > maxd) maxd = dist; // (:821-823)
-            const float mz = zk[k];
-            const bool valid = mem && mz > F_0p05_LO; // (double)depth > 0.05 (:827)
-            nvalid += valid ? 1 : 0;
-            const float rr = sd.w - mz;
-            if (valid && rr < F_0p4_HI && rr > -F_0p4_HI) inl |= 1u << k; // inlier (:849-860)
+            const float yd = (float)y - sd.y;
+            const float yd2 = yd * yd;
+            const float xl = (float)(x0 + __ffs(mm) - 1) - sd.x, xr = (float)(x0 + 31 - __clz(mm)) - sd.x;
+            maxd = fmaxf(xl * xl + yd2, xr * xr + yd2);
         }
+        int nvalid = __popc(vm);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1)
         {
             maxd = fmaxf(maxd, __shfl_xor_sync(FULL, maxd, o));
             nvalid += __shfl_xor_sync(FULL, nvalid, o);
         }
-        const int c = __popc(inl);
+        const int c = __popc(im);
         int incl = c;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1)
@@ -705,10 +777,10 @@ __global__ void __launch_bounds__(256, 3) k_plane_gather(const __grid_constant__
         }
         const int ninl = __shfl_sync(FULL, incl, 15, 16);
         uint16_t *pp = s_pos + sl * PG_POS_STRIDE + (incl - c);
-        const int pbase = trow * DSM_TILE_W + tcol;
+        const int pbase = (trow << 7) | tcol; // (tile row, tile column) packed: no division when unpacking
 #pragma unroll
         for (int k = 0; k < 16; k++)
-            if ((inl >> k) & 1u) *pp++ = (uint16_t)(pbase + k);
+            if ((im >> k) & 1u) *pp++ = (uint16_t)(pbase + k);
         if (r == 0)
         {
             s_maxd[sl] = maxd;
@@ -717,134 +789,164 @@ __global__ void __launch_bounds__(256, 3) k_plane_gather(const __grid_constant__
         }
     }
     __syncthreads();
-    // ---- phase 2: one warp per seed of a tile row, lane per inlier
-    for (int ty = 0; ty < DSM_TILE_SY; ty++)
+    // ---- phase 2: 8 lanes per seed, 4 seeds per warp; lane gl of a group walks the inliers gl, gl + 8, ...
+    const int gl = lane & 7;
+    const int sl = warp * 4 + (lane >> 3);
+    const int sp_x = blockIdx.x * DSM_TILE_SX + (sl & 7), sp_y = blockIdx.y * DSM_TILE_SY + (sl >> 3);
+    const bool live = sp_x < d.spw && sp_y < d.sph;
+    const int s = sp_y * d.spw + sp_x;
+    const int nvalid = s_nvalid[sl], ninl_raw = s_ninl[sl];
+    const float maxd = s_maxd[sl];
+    const bool ok = live && nvalid >= 16 && !((float)ninl_raw / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
+    const int ninl = ok ? ninl_raw : 0; // rejected seeds walk an empty list (the group stays convergent for the shuffles)
+    const uint16_t *pos = s_pos + sl * PG_POS_STRIDE;
+    float snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
+    for (int j = gl; j < ninl; j += 8)
     {
-        if (threadIdx.x == 0) s_rows = 0;
-        __syncthreads(); // previous row's copy-out has read the stage tile; s_rows reset
-        const int sl = ty * 8 + warp;
-        const int sp_x = blockIdx.x * DSM_TILE_SX + warp, sp_y = blockIdx.y * DSM_TILE_SY + ty;
-        const bool live = sp_x < d.spw && sp_y < d.sph;
-        const int s = sp_y * d.spw + sp_x;
-        const int nvalid = s_nvalid[sl], ninl = s_ninl[sl];
-        const float maxd = s_maxd[sl];
-        const bool ok = live && nvalid >= 16 && !((float)ninl / (float)nvalid < F_0p8_HI); // (:841), (double)ratio < 0.8 (:862)
-        if (ok) // warp-uniform
+        const int p = pos[j];
+        const int trow = p >> 7, tcol = p & 127;
+        const int x = X0 + tcol, y = Y0 + trow;
+        const float *pz = t_dep + trow * DSM_TILE_W + tcol;
+        const float mz = pz[0];
+        const float kxi = s_kx[tcol], ky0 = s_ky[trow];
+        const float mx = kxi * mz, my = ky0 * mz; // back_project in float (:94-96)
+        spx += mx;
+        spy += my;
+        spz += mz;
+        // pixel normal of (x, y), as calculate_pixels_norms_kernel (:664-712)
+        if (y >= 1 && y <= H - 2 && x >= 1 && x <= W - 2)
         {
-            const uint16_t *pos = s_pos + sl * PG_POS_STRIDE;
-            float snx = 0.f, sny = 0.f, snz = 0.f, spx = 0.f, spy = 0.f, spz = 0.f;
-            for (int j = lane; j < ninl; j += 32)
+            const float rz = pz[1], dz = pz[DSM_TILE_W];
+            if (!(mz < F_0p1_HI || rz < F_0p1_HI || dz < F_0p1_HI)) // (double)z < 0.1 (:688)
             {
-                const int p = pos[j];
-                const int trow = p / DSM_TILE_W, tcol = p - trow * DSM_TILE_W;
-                const int x = X0 + tcol, y = Y0 + trow;
-                const float mz = t_dep[p];
-                const float kxi = s_kx[tcol], ky0 = s_ky[trow];
-                spx += kxi * mz; // back_project in float (:94-96)
-                spy += ky0 * mz;
-                spz += mz;
-                // pixel normal of (x, y), as k_pixel_normals / calculate_pixels_norms_kernel (:664-712)
-                if (y >= 1 && y <= H - 2 && x >= 1 && x <= W - 2)
-                {
-                    const float rz = t_dep[p + 1], dz = t_dep[p + DSM_TILE_W];
-                    if (!(mz < F_0p1_HI || rz < F_0p1_HI || dz < F_0p1_HI)) // (double)z < 0.1 (:688)
-                    {
-                        const float kxr = s_kx[tcol + 1], ky1 = s_ky[trow + 1];
-                        const float mx = kxi * mz, my = ky0 * mz;
-                        const float rx = kxr * rz - mx, ry = ky0 * rz - my, rzz = rz - mz;
-                        const float dx = kxi * dz - mx, dy = ky1 * dz - my, dzz = dz - mz;
-                        float cxn = ry * dzz - rzz * dy;
-                        float cyn = rzz * dx - rx * dzz;
-                        float czn = rx * dy - ry * dx;
-                        const float len = sqrtf(cxn * cxn + cyn * cyn + czn * czn);
-                        cxn /= len;
-                        cyn /= len;
-                        czn /= len;
-                        const float view = (cxn * mx + cyn * my + czn * mz) / sqrtf(mx * mx + my * my + mz * mz);
-                        if (!(view > -F_0p1_HI && view < F_0p1_HI)) // |view| < 0.1 in double -> skipped (:706)
-                            snx += cxn, sny += cyn, snz += czn;
-                    }
+                const float kxr = s_kx[tcol + 1], ky1 = s_ky[trow + 1];
+                const float rx = kxr * rz - mx, ry = ky0 * rz - my, rzz = rz - mz;
+                const float dx = kxi * dz - mx, dy = ky1 * dz - my, dzz = dz - mz;
+                float cxn = ry * dzz - rzz * dy;
+                float cyn = rzz * dx - rx * dzz;
+                float czn = rx * dy - ry * dx;
+                const float l2 = cxn * cxn + cyn * cyn + czn * czn, p2 = mx * mx + my * my + mz * mz;
+                const float il = rsqrtf(l2);
+                float nx = cxn * il, ny = cyn * il, nz = czn * il;
+                float view = (nx * mx + ny * my + nz * mz) * rsqrtf(p2);
+                const float av = fabsf(view);
+                if (!(av > 0.1001f || av < 0.0999f))
+                { // within 1e-4 of the skip threshold (or NaN): the reference's own arithmetic decides
+                    const float len = sqrtf(l2);
+                    nx = cxn / len, ny = cyn / len, nz = czn / len;
+                    view = (nx * mx + ny * my + nz * mz) / sqrtf(p2);
                 }
+                if (!(view > -F_0p1_HI && view < F_0p1_HI)) // |view| < 0.1 in double -> skipped (:706)
+                    snx += nx, sny += ny, snz += nz;
             }
-            snx = warp_sum_f(snx), sny = warp_sum_f(sny), snz = warp_sum_f(snz);
-            spx = warp_sum_f(spx), spy = warp_sum_f(spy), spz = warp_sum_f(spz);
-            const float fn = (float)ninl;
-            const float mxs = spx / fn, mys = spy / fn, mzs = spz / fn; // (:117-119)
-            // initial normal of get_huber_norm = normalised sum of the inlier pixel normals (:864-871); 0/0 -> NaN, propagated (H6-iii)
-            const float len0 = sqrtf(snx * snx + sny * sny + snz * snz);
-            const float n0x = snx / len0, n0y = sny / len0, n0z = snz / len0;
-            double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // xx xy xz xw yy yz yw zz zw
-            float rmax = 0.f, qmax2 = 0.f;
-            bool rnan = false;
-            float *stx = s_stage + warp * PG_ST_STRIDE, *sty = stx + 8 * PG_ST_STRIDE, *stz = sty + 8 * PG_ST_STRIDE;
-            for (int j = lane; j < ninl; j += 32)
-            {
-                const int p = pos[j];
-                const int trow = p / DSM_TILE_W, tcol = p - trow * DSM_TILE_W;
-                const float mz = t_dep[p];
-                const float ax = s_kx[tcol] * mz - mxs, ay = s_ky[trow] * mz - mys, az = mz - mzs; // centred points (:121-126)
-                stx[j] = ax, sty[j] = ay, stz[j] = az;
-                const float rr = ax * n0x + ay * n0y + az * n0z + 0.f; // first-pass residual (:133), b = 0
-                rmax = fmaxf(rmax, fabsf(rr));
-                rnan |= !(rr == rr);
-                qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
-                h[0] += (double)(2 * ax * ax), h[1] += (double)(2 * ax * ay), h[2] += (double)(2 * ax * az), h[3] += (double)(2 * ax);
-                h[4] += (double)(2 * ay * ay), h[5] += (double)(2 * ay * az), h[6] += (double)(2 * ay);
-                h[7] += (double)(2 * az * az), h[8] += (double)(2 * az);
-            }
+        }
+    }
+    snx = group8_sum_f(snx), sny = group8_sum_f(sny), snz = group8_sum_f(snz);
+    spx = group8_sum_f(spx), spy = group8_sum_f(spy), spz = group8_sum_f(spz);
+    const float fn = (float)ninl;
+    const float mxs = spx / fn, mys = spy / fn, mzs = spz / fn; // (:117-119)
+    // initial normal of get_huber_norm = normalised sum of the inlier pixel normals (:864-871); 0/0 -> NaN, propagated (H6-iii)
+    const float len0 = sqrtf(snx * snx + sny * sny + snz * snz);
+    const float n0x = snx / len0, n0y = sny / len0, n0z = snz / len0;
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // xx xy xz xw yy yz yw zz zw over all points
+    float margin = __int_as_float(0x7f800000), qmax2 = 0.f;
+    bool rnan = false;
+    unsigned omask = 0; // bit i: this lane's i-th point (j = gl + 8 i, i <= 28) is outside the Huber range
+    float *qx = d.qlist + (so + s) * (3 * PL_STRIDE), *qy = qx + PL_STRIDE, *qz = qy + PL_STRIDE;
+    for (int j = gl, it = 0; j < ninl; j += 8, it++)
+    {
+        const int p = pos[j];
+        const int trow = p >> 7, tcol = p & 127;
+        const float mz = t_dep[trow * DSM_TILE_W + tcol];
+        const float ax = s_kx[tcol] * mz - mxs, ay = s_ky[trow] * mz - mys, az = mz - mzs; // centred points (:121-126)
+        qx[j] = ax, qy[j] = ay, qz[j] = az;
+        const float rr = ax * n0x + ay * n0y + az * n0z + 0.f; // first-pass residual (:133), b = 0
+        rnan |= !(rr == rr);
+        margin = fminf(margin, fabsf(fabsf(rr) - 0.4f));
+        qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
+        h[0] += (double)(2 * ax * ax), h[1] += (double)(2 * ax * ay), h[2] += (double)(2 * ax * az), h[3] += (double)(2 * ax);
+        h[4] += (double)(2 * ay * ay), h[5] += (double)(2 * ay * az), h[6] += (double)(2 * ay);
+        h[7] += (double)(2 * az * az), h[8] += (double)(2 * az);
+        if (!(rr < F_0p4_HI && rr > -F_0p4_HI)) omask |= 1u << it; // (:134)
+    }
 #pragma unroll
-            for (int i = 0; i < 9; i++) h[i] = warp_sum_d(h[i]);
-            rmax = warp_max_f(rmax);
-            qmax2 = warp_max_f(qmax2);
-            if (__any_sync(FULL, rnan)) rmax = __int_as_float(0x7f800000); // a NaN residual forces the solver to evaluate every pass
-            if (lane < 10)
-            {
-                double v = 0.0;
+    for (int i = 0; i < 9; i++) h[i] = group8_sum_d(h[i]);
 #pragma unroll
-                for (int i = 0; i < 9; i++)
-                    if (lane == i) v = h[i];
-                if (lane == 9) v = __hiloint2double(__float_as_int(qmax2), __float_as_int(rmax));
-                d.hrec[(so + s) * 10 + lane] = v;
-            }
-            if (lane == 0)
-            {
-                d.pfsum[(so + s) * 2] = make_float4(snx, sny, snz, maxd);
-                d.pfsum[(so + s) * 2 + 1] = make_float4(mxs, mys, mzs, __int_as_float(ninl));
-                atomicMax(&s_rows, ninl);
-            }
-        }
-        else if (live && lane == 0)
+    for (int o = 4; o > 0; o >>= 1)
+    {
+        margin = fminf(margin, __shfl_xor_sync(FULL, margin, o));
+        qmax2 = fmaxf(qmax2, __shfl_xor_sync(FULL, qmax2, o));
+        rnan |= __shfl_xor_sync(FULL, rnan ? 1 : 0, o) != 0;
+    }
+    if (rnan) margin = __int_as_float(0x7fc00000); // a NaN residual: no pass may ever be skipped
+    double *hr = d.hrec + (so + s) * HREC;
+    if (ok)
+    { // the group's lanes write the 9 sums and the packed (margin, qmax2)
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            if ((i & 7) == gl) hr[i] = h[i];
+        if (gl == 7) hr[23] = __hiloint2double(__float_as_int(qmax2), __float_as_int(margin));
+    }
+    // the out-of-range points (few per seed, none for most): the same ten sums (with ww) and the clamped gradient
+    // (:157-170), accumulated in a second sweep over just those points so that the 14 accumulators are not live above
+    double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, jo[4] = {0, 0, 0, 0};
+    if (__any_sync(FULL, omask != 0)) // warp-uniform
+    {
+        while (omask)
         {
-            d.pfsum[(so + s) * 2] = make_float4(0.f, 0.f, 0.f, maxd);
-            d.pfsum[(so + s) * 2 + 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-        }
-        __syncthreads();
-        // copy-out of the row's centred points as full 32-byte sectors of the [k][seed] lists
-        const int rows = s_rows;
-        const unsigned c = threadIdx.x & 7u;
-        if (blockIdx.x * DSM_TILE_SX + c < (unsigned)d.spw && sp_y < d.sph)
-        {
-            const size_t plane = (size_t)d.B * PF_CAP * d.Sp;
-            float *dx = d.qlist + ((size_t)b * PF_CAP * d.Sp + (size_t)sp_y * d.spw + blockIdx.x * DSM_TILE_SX + c);
-            float *dy = dx + plane, *dz = dy + plane;
-            const unsigned sp = (unsigned)d.Sp;
-            for (unsigned k = threadIdx.x >> 3; k < (unsigned)rows; k += 32u)
-            {
-                const unsigned t = c * PG_ST_STRIDE + k, o = k * sp;
-                dx[o] = s_stage[t];
-                dy[o] = s_stage[8 * PG_ST_STRIDE + t];
-                dz[o] = s_stage[16 * PG_ST_STRIDE + t];
+            const int it = __ffs(omask) - 1;
+            omask &= omask - 1;
+            const int p = pos[gl + 8 * it];
+            const int trow = p >> 7, tcol = p & 127;
+            const float mz = t_dep[trow * DSM_TILE_W + tcol];
+            const float ax = s_kx[tcol] * mz - mxs, ay = s_ky[trow] * mz - mys, az = mz - mzs;
+            const float rr = ax * n0x + ay * n0y + az * n0z + 0.f;
+            ho[0] += (double)(2 * ax * ax), ho[1] += (double)(2 * ax * ay), ho[2] += (double)(2 * ax * az), ho[3] += (double)(2 * ax);
+            ho[4] += (double)(2 * ay * ay), ho[5] += (double)(2 * ay * az), ho[6] += (double)(2 * ay);
+            ho[7] += (double)(2 * az * az), ho[8] += (double)(2 * az), ho[9] += 2;
+            if (rr >= F_0p4_HI)
+            { // (double)r >= 0.4 (:157-163)
+                jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay, jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+            }
+            else if (rr <= -F_0p4_HI)
+            { // (double)r <= -0.4 (:164-170)
+                jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay, jo[2] += -1 * HUBER_RANGE * (double)az,
+                    jo[3] += -1 * HUBER_RANGE;
             }
         }
+#pragma unroll
+        for (int i = 0; i < 10; i++) ho[i] = group8_sum_d(ho[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) jo[i] = group8_sum_d(jo[i]);
+    }
+    if (ok)
+    { // hr[18] = ho[9] (twice the number of out-of-range points) doubles as the "any" flag the solver tests
+        if (ho[9] != 0.0)
+        {
+#pragma unroll
+            for (int i = 0; i < 14; i++)
+                if ((i & 7) == gl) hr[9 + i] = i < 10 ? ho[i] : jo[i - 10];
+        }
+        else if (gl == 0)
+            hr[18] = 0.0;
+    }
+    if (live && gl == 0)
+    {
+        d.pfsum[(so + s) * 2] = ok ? make_float4(snx, sny, snz, maxd) : make_float4(0.f, 0.f, 0.f, maxd);
+        d.pfsum[(so + s) * 2 + 1] = ok ? make_float4(mxs, mys, mzs, __int_as_float(ninl)) : make_float4(0.f, 0.f, 0.f, __int_as_float(0));
     }
 }
 
 // -------------------------------------------------------------------------------------------
 // K4b  plane_solve — get_huber_norm (:104-188) + the projection (:884-912), one thread per seed.
-// Same algebra as k_gauss_newton (dsm_kernels.cu): H over all points once, passes only classify residuals, pass
-// skipping by the |r| bound.  The first pass's H, max |r| and max |q|^2 arrive from k_plane_gather; if that max |r|
-// is inside the Huber range (the common case) the solver is five register-only 4x4 solves and never touches the
-// point list; otherwise it evaluates the passes from the [k][seed] list exactly like k_gauss_newton.
+// Algebra as k_gauss_newton (dsm_kernels.cu): for the points whose residual is inside the Huber range,
+// sum 2 r q~ = (sum 2 q~ q~^T) theta, so with H over ALL points, H_R = H - ho and J = H_R theta + jo, where ho / jo are
+// the sums over the out-of-range points only.  A pass over the points is needed only to find out which points are
+// out of range.  Let m = min_i | |r_i| - 0.4 | at the last evaluated parameters; a step (dn, db) changes every
+// residual by at most |q|max |dn| + |db|, so while the accumulated bound stays below m (minus a slack far above the
+// float error of evaluating r) no point crosses the boundary: ho, jo are provably unchanged and the pass is skipped.
+// The first pass's sums arrive from k_plane_gather, so most seeds are five register-only 4x4 solves; the others read
+// the centred points from qlist[b][seed][plane][k] (16-byte loads) exactly like the reference's loop (:131-171).
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void solve4_spd_t(const double *h, const double *j, double *u)
 { // h: 10 unique entries xx xy xz xw yy yz yw zz zw ww of an SPD matrix; solves H u = j
@@ -887,34 +989,44 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
         const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
         float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
         const float mxs = P1.x, mys = P1.y, mzs = P1.z;
-        const size_t plane = (size_t)d.B * PF_CAP * d.Sp, st = (size_t)d.Sp;
-        const float *qx = d.qlist + (size_t)b * PF_CAP * d.Sp + s;
-        const float *qy = qx + plane, *qz = qy + plane;
-        double hall[10]; // xx xy xz xw yy yz yw zz zw ww over ALL points
-        const double *hr = d.hrec + (so + s) * 10;
+        const double *hr = d.hrec + (so + s) * HREC;
+        double hall[10], ho[10], jo[4];
 #pragma unroll
         for (int i = 0; i < 9; i++) hall[i] = hr[i];
         hall[9] = 2.0 * (double)n;
-        const double pk = hr[9];
-        float rmax = __int_as_float(__double2loint(pk)), qmax2 = __int_as_float(__double2hiint(pk));
-        // first pass already evaluated by k_plane_gather: every residual inside the Huber range?
-        bool need_pass = !(rmax < F_0p4_HI);
-        // (if not, the gather's H stays valid -- it is the sum over ALL points -- and only the classification is redone)
+#pragma unroll
+        for (int i = 0; i < 10; i++) ho[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) jo[i] = 0.0;
+        if (hr[18] != 0.0)
+        { // the first pass found points outside the Huber range
+#pragma unroll
+            for (int i = 0; i < 10; i++) ho[i] = hr[9 + i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) jo[i] = hr[19 + i];
+        }
+        const double pk = hr[23];
+        float margin = __int_as_float(__double2loint(pk));
+        const float qmax = sqrtf(__int_as_float(__double2hiint(pk)));
+        float moved = 0.f; // bound on the change of any residual since the classification behind ho / jo was made
         for (int gn = 0; gn < 5; gn++)
         {
-            double ho[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // same, over the points outside the Huber range
-            double jo[4] = {0, 0, 0, 0};
-            if (need_pass)
-            {
-                float rm = 0.f;
+            if (gn > 0 && !(moved + 2e-3f < margin)) // NaN-safe: a NaN margin keeps evaluating
+            { // some point may have crossed the Huber boundary: classify again (:131-171)
+                const float4 *qx = reinterpret_cast<const float4 *>(d.qlist + (so + s) * (3 * PL_STRIDE));
+                const float4 *qy = qx + PL_STRIDE / 4, *qz = qy + PL_STRIDE / 4;
+#pragma unroll
+                for (int i = 0; i < 10; i++) ho[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) jo[i] = 0.0;
+                float mg = __int_as_float(0x7f800000);
                 bool rnan = false;
                 auto point = [&](float ax, float ay, float az)
                 {
                     const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
-                    const bool inr = r < F_0p4_HI && r > -F_0p4_HI;  // (:134)
-                    rm = fmaxf(rm, fabsf(r));
                     rnan |= !(r == r);
-                    if (!inr)
+                    mg = fminf(mg, fabsf(fabsf(r) - 0.4f));
+                    if (!(r < F_0p4_HI && r > -F_0p4_HI)) // (:134)
                     {
                         ho[0] += (double)(2 * ax * ax), ho[1] += (double)(2 * ax * ay), ho[2] += (double)(2 * ax * az), ho[3] += (double)(2 * ax);
                         ho[4] += (double)(2 * ay * ay), ho[5] += (double)(2 * ay * az), ho[6] += (double)(2 * ay);
@@ -933,17 +1045,22 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
                 };
                 int k = 0;
                 for (; k + 4 <= n; k += 4)
-                { // four points in flight: 12 coalesced loads issued before the first is consumed
-                    const float a0 = qx[k * st], a1 = qx[(k + 1) * st], a2 = qx[(k + 2) * st], a3 = qx[(k + 3) * st];
-                    const float b0 = qy[k * st], b1 = qy[(k + 1) * st], b2 = qy[(k + 2) * st], b3 = qy[(k + 3) * st];
-                    const float c0 = qz[k * st], c1 = qz[(k + 1) * st], c2 = qz[(k + 2) * st], c3 = qz[(k + 3) * st];
-                    point(a0, b0, c0);
-                    point(a1, b1, c1);
-                    point(a2, b2, c2);
-                    point(a3, b3, c3);
+                {
+                    const float4 a = qx[k >> 2], bb = qy[k >> 2], c = qz[k >> 2];
+                    point(a.x, bb.x, c.x);
+                    point(a.y, bb.y, c.y);
+                    point(a.z, bb.z, c.z);
+                    point(a.w, bb.w, c.w);
                 }
-                for (; k < n; k++) point(qx[k * st], qy[k * st], qz[k * st]);
-                rmax = rnan ? __int_as_float(0x7f800000) : rm; // a NaN residual forces every later pass
+                if (k < n)
+                {
+                    const float4 a = qx[k >> 2], bb = qy[k >> 2], c = qz[k >> 2];
+                    point(a.x, bb.x, c.x);
+                    if (k + 1 < n) point(a.y, bb.y, c.y);
+                    if (k + 2 < n) point(a.z, bb.z, c.z);
+                }
+                margin = rnan ? __int_as_float(0x7fc00000) : mg;
+                moved = 0.f;
             }
             double hh[10], jj[4];
 #pragma unroll
@@ -961,11 +1078,8 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
             ny = (float)((double)ny - u[1]);
             nz = (float)((double)nz - u[2]);
             nb = (float)((double)nb - u[3]);
-            // can the next pass be skipped?  |r_i(new)| <= rmax + qmax |dn| + |db| (+ rounding slack)
             const float dx = nx - ox, dy = ny - oy, dz = nz - oz;
-            const float bound = rmax + sqrtf(qmax2) * sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + fabsf(nb - ob) + 1e-3f;
-            need_pass = !(bound < 0.39f); // NaN-safe: any NaN keeps evaluating
-            rmax = bound;
+            moved += qmax * sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + fabsf(nb - ob) + 1e-4f;
         }
         nb = nb - (nx * mxs + ny * mys + nz * mzs);
         const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
@@ -1005,7 +1119,7 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
 // -------------------------------------------------------------------------------------------
 int dsm_tile_setup()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, GAT_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_plane_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
     return e == cudaSuccess ? 0 : -1;
 }
@@ -1018,10 +1132,15 @@ void dsm_launch_assign2(const DsmDev &d, int nb, bool first, cudaStream_t s)
     else
         k_assign2<false><<<grid, block, 0, s>>>(d);
 }
-void dsm_launch_update(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s)
+void dsm_launch_gather(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s)
 {
     dim3 grid((d.spw + DSM_TILE_SX - 1) / DSM_TILE_SX, (d.sph + DSM_TILE_SY - 1) / DSM_TILE_SY, nb);
-    k_update<<<grid, 256, UPD_SMEM_BYTES, s>>>(d, m);
+    k_gather<<<grid, 256, GAT_SMEM_BYTES, s>>>(d, m);
+}
+void dsm_launch_newton2(const DsmDev &d, int nb, cudaStream_t s)
+{
+    dim3 grid((d.S + 127) / 128, nb);
+    k_newton2<<<grid, 128, 0, s>>>(d);
 }
 void dsm_launch_plane_gather(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s)
 {

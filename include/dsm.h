@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSM_VERSION 110 /* 0.1.10: + output formats, stream chunks, inactive store, debug variants */
+#define DSM_VERSION 200 /* 0.2.0: tile schedule (TMA-staged kernels), multi-GPU gather in the C ABI, runtime constant sets */
 
 /* ---- error codes ---- */
 #define DSM_OK 0
@@ -243,6 +243,31 @@ int dsm_inactive_transform(dsm_ctx *ctx, int keyframe_index, const float W_colma
 int dsm_inactive_export_cloud(dsm_ctx *ctx, dsm_point_t *out, int cap, int *n_out);
 int dsm_inactive_download(dsm_ctx *ctx, int keyframe_index, dsm_surfel_t *out, int cap, int *n_out);
 int dsm_inactive_size(dsm_ctx *ctx, int *n_surfels, int *n_segments);
+
+/* ---- multi-GPU: frames of a batch sharded across GPUs, ONE gather of the surfel deltas at the end ----
+ * One context per GPU (one process or thread each).  The reference has no counterpart (fuse_initialize_map is
+ * single-process, fusion_functions.cpp:30-83); what is gathered is what SurfelMap::fuse_map consumes after the call
+ * (surfel_map.cpp:1077-1109): every frame's new surfels and updated local surfels.
+ *   dsm_comm_unique_id   rank 0 creates the 128-byte NCCL id and hands it to the other ranks out of band
+ *   dsm_comm_init        collective: joins the communicator (ncclCommInitRank); NCCL is dlopen'ed ("libnccl.so.2": inside a
+ *                        PyTorch process the copy torch already loaded), DSM_E_NCCL if it is missing
+ *   dsm_gather_deltas    collective, after dsm_batch_run: packs ONLY the valid records of this rank's batch
+ *                          int32 'DSMD', n_frames, n_new_total, n_pool_total, n_new[n_frames], pool_ofs[n_frames+1], pad to 16 B,
+ *                          dsm_surfel_t new[n_new_total] (frame by frame, seed-index order), dsm_surfel_t pool[n_pool_total]
+ *                        and moves it to `root` (ncclAllGather of the byte counts + one grouped ncclSend/ncclRecv) on a side
+ *                        stream.  Waits for the batch's kernels (the counts must reach the host), returns before the
+ *                        transfer has finished; the next dsm_batch_run may be enqueued at once.
+ *   dsm_gather_wait      waits for the transfer
+ *   dsm_gathered_*       root only: the payload of every rank, on the device (zero copy) or copied to host memory */
+#define DSM_COMM_ID_BYTES 128
+int dsm_comm_unique_id(void *id_out128);
+int dsm_comm_init(dsm_ctx *ctx, const void *id128, int rank, int nranks);
+int dsm_comm_destroy(dsm_ctx *ctx);
+int dsm_gather_deltas(dsm_ctx *ctx, int root);
+int dsm_gather_wait(dsm_ctx *ctx);
+int dsm_gathered_device(dsm_ctx *ctx, void **dev_ptr, size_t *rank_offsets /* [nranks + 1] */);
+int dsm_gathered_rank_bytes(dsm_ctx *ctx, int rank, size_t *bytes);
+int dsm_gathered_download(dsm_ctx *ctx, int rank, void *host_out, size_t cap);
 
 /* ---- parity / debug readback (what the reference keeps private: fusion_functions.h:34-37) ---- */
 int dsm_get_labels(dsm_ctx *ctx, int frame, int32_t *labels_hw);   /* superpixel_index, [H][W] */

@@ -53,8 +53,8 @@ def test_stage_by_stage_vga(capi):
     ctx = capi.Context(cam, max_batch=1, max_local_surfels=16)
     pose = synth.identity_pose()
     ctx.batch_upload([0], gray[None], depth[None], pose[None], np.zeros(0, SURFEL_DTYPE), [0, 0])
-    # (kernels to run, oracle iterations, last-with-update); tile schedule: seed_init, then (assign, update) x 3
-    stages = [(2, 1, False), (3, 1, True), (4, 2, False), (5, 2, True), (6, 3, False), (7, 3, True)]
+    # (kernels to run, oracle iterations, last-with-update); tile schedule: seed_init, then (assign, gather, newton) x 3
+    stages = [(2, 1, False), (4, 1, True), (5, 2, False), (7, 2, True), (8, 3, False), (10, 3, True)]
     if int(os.environ.get("DSM_EXPERIMENTAL_VARIANTS", "0"), 0) & 256:  # round-1 schedule: assign, relax, gather, newton
         stages = [(2, 1, False), (4, 1, True), (6, 2, False), (8, 2, True), (10, 3, False), (12, 3, True)]
     for nk, iters, upd in stages:

@@ -1,9 +1,9 @@
-"""CPU test of the N>1 plumbing: world_size-2 gloo run of the shard + gather-of-deltas logic
-(densesurfelmapping_b200/gather.py) that bench.py uses over NCCL."""
+"""CPU tests of the N>1 plumbing: the wire format of the surfel-delta gather (restated in numpy, gather.py; the device
+packer of csrc/dsm_comm.cu must produce exactly these bytes, tests/test_gpu_comm.py) and a world_size-2 gloo run of
+the shard + variable-length gather logic."""
 import os
 
 import numpy as np
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -16,36 +16,35 @@ S, B = 12, 3
 def _fake_rank_data(rank):
     rng = np.random.RandomState(100 + rank)
     counts = rng.randint(0, S + 1, size=B).astype(np.int32)
-    new = np.zeros((B, S), SURFEL_DTYPE)
+    news = []
     for b in range(B):
+        a = np.zeros(counts[b], SURFEL_DTYPE)
         for f in ("px", "py", "pz", "weight"):
-            new[f][b, :counts[b]] = rng.rand(counts[b]).astype(np.float32)
-        new["update_times"][b, :counts[b]] = 1
-        new["last_update"][b, :counts[b]] = rank * 10 + b
-    npool = 5 + rank
-    pool = np.zeros(B * S, SURFEL_DTYPE)
-    pool["px"][:npool] = rng.rand(npool).astype(np.float32)
-    pool["update_times"][:npool] = rng.randint(0, 4, npool)
-    return counts, new, pool, npool
+            a[f] = rng.rand(counts[b]).astype(np.float32)
+        a["update_times"] = 1
+        a["last_update"] = rank * 10 + b
+        news.append(a)
+    per = rng.randint(0, 6, size=B)
+    ofs = np.concatenate([[0], np.cumsum(per)]).astype(np.int32)
+    pool = np.zeros(int(ofs[-1]), SURFEL_DTYPE)
+    pool["px"] = rng.rand(len(pool)).astype(np.float32)
+    pool["update_times"] = rng.randint(0, 4, len(pool))
+    return news, pool, ofs
 
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    counts, new, pool, npool = _fake_rank_data(rank)
-    t_new = torch.from_numpy(new.view(np.uint8).reshape(-1).view(np.float32).copy())
-    t_pool = torch.from_numpy(pool.view(np.uint8).reshape(-1).view(np.float32).copy())
-    res = gather.gather_deltas(t_new, torch.from_numpy(counts), t_pool, npool, dst=0)
+    news, pool, ofs = _fake_rank_data(rank)
+    res = gather.gather_payloads(gather.pack_payload(news, pool, ofs), dst=0)
     if rank == 0:
-        news, cnts, pools, pcnts = res
-        ok = True
+        ok = len(res) == world
         for r in range(world):
-            c, n, p, npl = _fake_rank_data(r)
-            got = gather.unpack_new(news[r], cnts[r], S)
-            ok &= all(got[b].tobytes() == n[b, :c[b]].tobytes() for b in range(B))
-            ok &= int(pcnts[r]) == npl
-            ok &= pools[r].numpy().view(np.uint8)[:npl * 44].tobytes() == p[:npl].tobytes()
-        q.put(ok)
+            n, p, o = _fake_rank_data(r)
+            gn, gp, go = gather.unpack_payload(res[r])
+            ok &= len(gn) == B and all(gn[b].tobytes() == n[b].tobytes() for b in range(B))
+            ok &= gp.tobytes() == p.tobytes() and (go == o).all()
+        q.put(bool(ok))
     else:
         assert res is None
     dist.barrier()
@@ -57,7 +56,20 @@ def test_shard_frames():
     assert sorted(sum((gather.shard_frames(256, r, 8) for r in range(8)), [])) == list(range(256))
 
 
-def test_gather_deltas_gloo_world2():
+def test_payload_round_trip_and_layout():
+    news, pool, ofs = _fake_rank_data(3)
+    buf = gather.pack_payload(news, pool, ofs)
+    hdr = buf[:16].view(np.int32)
+    assert hdr[0] == 0x444D5344 and hdr[1] == B and hdr[2] == sum(len(a) for a in news) and hdr[3] == len(pool)
+    assert buf.size == gather.header_bytes(B) + (hdr[2] + hdr[3]) * 44 and gather.header_bytes(B) % 16 == 0
+    gn, gp, go = gather.unpack_payload(buf)
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(gn, news)) and gp.tobytes() == pool.tobytes() and (go == ofs).all()
+    empty = gather.pack_payload([np.zeros(0, SURFEL_DTYPE)] * 2, np.zeros(0, SURFEL_DTYPE), [0, 0, 0])
+    gn, gp, go = gather.unpack_payload(empty)
+    assert [len(a) for a in gn] == [0, 0] and len(gp) == 0
+
+
+def test_gather_payloads_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000

@@ -5,8 +5,17 @@ set -u
 tag=${1:-check}
 out=gpurun_out/$tag
 mkdir -p "$out"
-echo "== default (tile) schedule" | tee "$out/summary.txt"
+echo "== kernel-by-kernel prefixes (tile schedule)" | tee "$out/summary.txt"
+DSM_GRAPHS=0 timeout 120 python tools/debug_one.py 640 480 2>&1 | tail -14 | tee -a "$out/summary.txt"
+if ! grep -q "label mismatches: 0" "$out/summary.txt"; then echo "tile schedule broken: stopping here" | tee -a "$out/summary.txt"; exit 1; fi
+echo "== default (tile) schedule" | tee -a "$out/summary.txt"
 timeout 420 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 | tee -a "$out/summary.txt"
+if [ "${QUICK:-0}" = "1" ]; then
+  echo "== bench (tile schedule)" | tee -a "$out/summary.txt"
+  timeout 420 python bench.py --steps 20 --warmup 5 --no-cpu > "$out/bench.json" 2> "$out/bench.err"
+  tail -c 2500 "$out/bench.json" | tee -a "$out/summary.txt"
+  exit 0
+fi
 echo "== round-1 schedule (DSM_EXPERIMENTAL_VARIANTS=256)" | tee -a "$out/summary.txt"
 DSM_EXPERIMENTAL_VARIANTS=256 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -5 | tee -a "$out/summary.txt"
 echo "== gated tests (DSM_TEST_UNVERIFIED=1)" | tee -a "$out/summary.txt"
