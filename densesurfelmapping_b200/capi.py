@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libdsm_b200.so")
 DSM_OK = 0
 ERRORS = {-1: "DSM_E_INVALID", -2: "DSM_E_SHAPE", -3: "DSM_E_NODEVICE", -4: "DSM_E_CUDA",
           -5: "DSM_E_NOMEM", -6: "DSM_E_CAPACITY", -7: "DSM_E_STATE", -8: "DSM_E_NCCL", -9: "DSM_E_IO"}
-NUM_KERNELS = 15
+NUM_KERNELS = 10
 
 # every symbol include/dsm.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
@@ -26,11 +26,11 @@ EXPORTS = [
     "dsm_fuse_batch", "dsm_fuse_batch_async", "dsm_batch_wait", "dsm_batch_restore_pool", "dsm_pool_upload", "dsm_fuse_frame_resident",
     "dsm_pool_transform", "dsm_pool_retire", "dsm_pool_append", "dsm_pool_size", "dsm_pool_download", "dsm_get_labels", "dsm_get_seeds",
     "dsm_debug_stop_after", "dsm_debug_invariant_violations", "dsm_profile_enable", "dsm_profile_reset", "dsm_profile_read", "dsm_kernel_name", "dsm_device_buffer",
-    "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices", "dsm_debug_set_variants", "dsm_fuse_stream_resident",
+    "dsm_pool_export_cloud", "dsm_pool_export_surfels", "dsm_write_pcd", "dsm_write_ply_mesh", "dsm_mesh_vertices", "dsm_fuse_stream_resident",
     "dsm_inactive_reserve", "dsm_inactive_retire", "dsm_inactive_reactivate", "dsm_inactive_transform", "dsm_inactive_export_cloud",
     "dsm_inactive_download", "dsm_inactive_size",
     "dsm_comm_unique_id", "dsm_comm_init", "dsm_comm_destroy", "dsm_gather_deltas", "dsm_gather_wait", "dsm_gathered_device",
-    "dsm_gathered_rank_bytes", "dsm_gathered_download",
+    "dsm_gathered_rank_bytes", "dsm_gathered_download", "dsm_set_constants",
 ]
 
 
@@ -39,6 +39,15 @@ class DsmParams(ctypes.Structure):
                 ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float), ("cy", ctypes.c_float),
                 ("fuse_far", ctypes.c_float), ("fuse_near", ctypes.c_float),
                 ("max_batch", ctypes.c_int32), ("max_local_surfels", ctypes.c_int32)]
+
+
+class DsmConstants(ctypes.Structure):
+    _fields_ = [("huber_range", ctypes.c_double), ("baseline", ctypes.c_double), ("disparity_error", ctypes.c_double),
+                ("min_tolerate_diff", ctypes.c_double)]
+
+
+CONSTANTS_DRIVE = (0.4, 0.5, 4.0, 0.1)    # fusion_functions.h:13-16
+CONSTANTS_RGBD = (0.05, 0.08, 1.0, 0.05)  # fusion_functions.h:18-21
 
 
 class DsmError(RuntimeError):
@@ -99,7 +108,6 @@ def load_library():
     L.dsm_get_seeds.argtypes = [vp, ci, vp]
     L.dsm_debug_stop_after.argtypes = [vp, ci]
     L.dsm_debug_invariant_violations.argtypes = [vp, ctypes.POINTER(ci)]
-    L.dsm_debug_set_variants.argtypes = [vp, ctypes.c_uint]
     L.dsm_profile_enable.argtypes = [vp, ctypes.c_uint32]
     L.dsm_profile_reset.argtypes = [vp]
     L.dsm_profile_read.argtypes = [vp, vp, vp]
@@ -109,6 +117,7 @@ def load_library():
     L.dsm_write_pcd.argtypes = [ctypes.c_char_p, vp, cs, ci]
     L.dsm_write_ply_mesh.argtypes = [ctypes.c_char_p, vp, cs]
     L.dsm_mesh_vertices.argtypes = [vp, cs, vp]
+    L.dsm_set_constants.argtypes = [vp, ctypes.POINTER(DsmConstants)]
     L.dsm_comm_unique_id.argtypes = [vp]
     L.dsm_comm_init.argtypes = [vp, vp, ci, ci]
     L.dsm_comm_destroy.argtypes = [vp]
@@ -138,6 +147,18 @@ def kernel_names():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def pose16(pose):
+    """Eigen::Matrix4f memory order (column-major float32[16]) of a pose.  A flat 16-vector is taken as already
+    column-major (what synth.pose_stream returns); a (4, 4) array is taken as the MATRIX T_world<-cam the way numpy
+    writes it (row i, column j = pose[i, j]) and is transposed into column-major memory -- it is not reinterpreted."""
+    a = np.asarray(pose, dtype=np.float32)
+    if a.shape == (4, 4):
+        return np.ascontiguousarray(a.T).reshape(16)
+    if a.size != 16:
+        raise ValueError("pose must be a (4, 4) matrix or a column-major 16-vector")
+    return np.ascontiguousarray(a).reshape(16)
 
 
 class Context:
@@ -175,7 +196,7 @@ class Context:
     def fuse_frame(self, ref_idx, gray, depth, pose, local):
         gray = np.ascontiguousarray(gray, dtype=np.uint8)
         depth = np.ascontiguousarray(depth, dtype=np.float32)
-        pose = np.ascontiguousarray(pose, dtype=np.float32).reshape(16)
+        pose = pose16(pose)
         local = np.array(local, dtype=SURFEL_DTYPE, copy=True)
         new = np.zeros(self.S, dtype=SURFEL_DTYPE)
         n = ctypes.c_int(0)
@@ -218,6 +239,11 @@ class Context:
         self.batch_run()
         return self.batch_download()
 
+    def set_constants(self, constants):
+        """(huber_range, baseline, disparity_error, min_tolerate_diff): CONSTANTS_DRIVE (default) or CONSTANTS_RGBD."""
+        k = DsmConstants(*constants)
+        self._ck(self.lib.dsm_set_constants(self.h, ctypes.byref(k)))
+
     # ---- multi-GPU gather of the surfel deltas (csrc/dsm_comm.cu) ----
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         assert len(unique_id) == 128
@@ -247,7 +273,7 @@ class Context:
     def fuse_frame_resident(self, ref_idx, gray, depth, pose, want_count=False):
         gray = np.ascontiguousarray(gray, dtype=np.uint8)
         depth = np.ascontiguousarray(depth, dtype=np.float32)
-        pose = np.ascontiguousarray(pose, dtype=np.float32).reshape(16)
+        pose = pose16(pose)
         n = ctypes.c_int(0)
         self._ck(self.lib.dsm_fuse_frame_resident(self.h, int(ref_idx), _ptr(gray), gray.strides[0], _ptr(depth), depth.strides[0],
                                                   _ptr(pose), ctypes.byref(n) if want_count else None))
@@ -266,7 +292,7 @@ class Context:
         return cnt if want_counts else None
 
     def pool_transform(self, W_colmajor):
-        w = np.ascontiguousarray(W_colmajor, dtype=np.float32).reshape(16)
+        w = pose16(W_colmajor)
         self._ck(self.lib.dsm_pool_transform(self.h, _ptr(w)))
 
     def pool_retire(self, keyframe_index, cap=None):
@@ -321,7 +347,7 @@ class Context:
         return n.value
 
     def inactive_transform(self, keyframe_index, W_colmajor):
-        w = np.ascontiguousarray(W_colmajor, dtype=np.float32).reshape(16)
+        w = pose16(W_colmajor)
         self._ck(self.lib.dsm_inactive_transform(self.h, int(keyframe_index), _ptr(w)))
 
     def inactive_size(self):
@@ -356,9 +382,6 @@ class Context:
 
     def debug_stop_after(self, n):
         self._ck(self.lib.dsm_debug_stop_after(self.h, int(n)))
-
-    def debug_set_variants(self, mask):
-        self._ck(self.lib.dsm_debug_set_variants(self.h, int(mask)))
 
     def invariant_violations(self):
         c = ctypes.c_int(0)

@@ -11,10 +11,8 @@
 #include <new>
 #include <vector>
 
-static const char *kKernelNames[DSM_NUM_KERNELS] = {
-    "seed_init", "slic_assign_first", "slic_assign", "stable_relax", "slic_gather_depths", "slic_newton",
-    "plane_gather_points", "surfel_fuse", "surfel_init", "repack", "pixel_normals", "plane_gauss_newton",
-    "slic_gather", "plane_gather", "plane_solve"};
+static const char *kKernelNames[DSM_NUM_KERNELS] = {"seed_init", "slic_assign_first", "slic_assign", "slic_gather", "slic_newton",
+                                                     "plane_gather", "plane_solve", "surfel_fuse", "surfel_init", "repack"};
 
 extern "C" int dsm_version(void) { return DSM_VERSION; }
 
@@ -96,7 +94,6 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(ctx->ipose);
     cudaFree(ctx->refidx);
     cudaFree(ctx->seed_export);
-    cudaFree(d.nrm);
     cudaFree(ctx->kx);
     cudaFree(ctx->ky);
     cudaFree(ctx->gray_packed);
@@ -118,12 +115,6 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
-    for (int i = 0; i < 5; i++)
-    {
-        if (ctx->s_fork[i]) cudaStreamSynchronize(ctx->s_fork[i]), cudaStreamDestroy(ctx->s_fork[i]);
-        if (ctx->ev_fork_a[i]) cudaEventDestroy(ctx->ev_fork_a[i]);
-        if (ctx->ev_fork_b[i]) cudaEventDestroy(ctx->ev_fork_b[i]);
-    }
     cudaFreeHost(ctx->h_pose);
     cudaFreeHost(ctx->h_ofs);
     cudaFreeHost(ctx->h_ref);
@@ -131,12 +122,26 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     delete ctx;
 }
 
-static int ensure_fork_streams(dsm_ctx *ctx);
-
 // TMA descriptors for the tile kernels: each per-pixel array as a [B][H][Wp] tensor, box = one 8x4-seed tile plus
 // halo (DSM_TILE_W x DSM_TILE_H elements; out-of-image parts of a box are zero-filled by the copy engine).
 // cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so the library keeps linking
 // against cudart only.
+// smallest float >= c: (double)x < c  <=>  x < ceil_float(c) for every float x
+static float ceil_float(double c)
+{
+    float f = (float)c;
+    if ((double)f < c) f = nextafterf(f, INFINITY);
+    return f;
+}
+static void apply_constants(DsmDev &d, const dsm_constants &k)
+{
+    d.huber = k.huber_range;
+    d.huber_hi = ceil_float(k.huber_range);
+    d.baseline = k.baseline;
+    d.disparity_error = k.disparity_error;
+    d.min_tolerate_diff = k.min_tolerate_diff;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -214,7 +219,6 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->s_h2d = ctx->s_d2h = nullptr;
     for (int i = 0; i < 4; i++) ctx->s_comp[i] = nullptr;
     ctx->ev_start = nullptr;
-    for (int i = 0; i < 5; i++) ctx->s_fork[i] = nullptr, ctx->ev_fork_a[i] = ctx->ev_fork_b[i] = nullptr;
     for (int i = 0; i < 8; i++) ctx->ev_h2d[i] = ctx->ev_done[i] = nullptr;
     ctx->gray_packed = nullptr;
     ctx->res_upper = 0;
@@ -245,6 +249,10 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     d.fx = params->fx, d.fy = params->fy, d.cx = params->cx, d.cy = params->cy;
     d.fuse_far = params->fuse_far, d.fuse_near = params->fuse_near;
     d.camera_f = (float)((fabs((double)params->fx) + fabs((double)params->fy)) / 2.0); // (:250)
+    {
+        const dsm_constants drive = DSM_CONSTANTS_DRIVE;
+        apply_constants(d, drive);
+    }
     d.px_stride = px;
     const size_t npool = (size_t)(params->max_local_surfels > 0 ? params->max_local_surfels : 1);
     cudaError_t e = cudaSuccess;
@@ -263,9 +271,9 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.tstable, (size_t)B * S);
     ALLOC(d.usum, (size_t)B * S);
     ALLOC(d.und, (size_t)B * S);
-    ALLOC(d.dlist, (size_t)B * 232 * ((S + 31) / 32 * 32)); // tile schedule: [B][S][232]; round-1 schedule: [B][228][Sp]
+    ALLOC(d.dlist, (size_t)B * S * 232);
     ALLOC(d.errflag, (size_t)B);
-    ALLOC(d.qlist, (size_t)3 * B * 232 * ((S + 31) / 32 * 32)); // tile schedule: [B][S][3][232]; round-1 schedule: [3][B][228][Sp]
+    ALLOC(d.qlist, (size_t)B * S * 3 * 232);
     ALLOC(d.pfsum, (size_t)B * S * 2);
     ALLOC(d.plane, (size_t)B * S * 3);
     ALLOC(d.fused, (size_t)B * S);
@@ -280,7 +288,6 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(ctx->ipose, (size_t)B * 16);
     ALLOC(ctx->refidx, (size_t)B);
     ALLOC(ctx->seed_export, (size_t)S);
-    ALLOC(d.nrm, 3 * (B * px) + 64);
     ALLOC(ctx->kx, (size_t)Wp + 16);
     ALLOC(ctx->ky, (size_t)H + 16);
     ALLOC(ctx->gray_packed, (size_t)B * H * W + 64);
@@ -291,7 +298,6 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(ctx->wmat, 16);
     ALLOC(ctx->res_ofs, 2);
 #undef ALLOC
-    d.nrm_plane = B * px;
     d.frame0 = 0;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
@@ -327,14 +333,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     d.kx = ctx->kx;
     d.ky = ctx->ky;
     d.max_pool_per_frame = 0;
-    d.variants = 0;
     if (make_tile_maps(ctx) != DSM_OK || dsm_tile_setup() != 0)
-    {
-        dsm_destroy(ctx);
-        return DSM_E_CUDA;
-    }
-    if (const char *ev = getenv("DSM_EXPERIMENTAL_VARIANTS")) d.variants = (int)strtol(ev, nullptr, 0); // see dsm_debug_set_variants
-    if ((d.variants & DSM_VARIANT_NORMALS_FORK) && ensure_fork_streams(ctx) != DSM_OK)
     {
         dsm_destroy(ctx);
         return DSM_E_CUDA;
@@ -533,18 +532,6 @@ extern "C" int dsm_batch_restore_pool(dsm_ctx *ctx)
     return DSM_OK;
 }
 
-// side streams / events of the forked pixel-normal pass; created outside any stream capture
-static int ensure_fork_streams(dsm_ctx *ctx)
-{
-    for (int i = 0; i < 5; i++)
-    {
-        if (!ctx->s_fork[i]) CK(cudaStreamCreateWithFlags(&ctx->s_fork[i], cudaStreamNonBlocking));
-        if (!ctx->ev_fork_a[i]) CK(cudaEventCreateWithFlags(&ctx->ev_fork_a[i], cudaEventDisableTiming));
-        if (!ctx->ev_fork_b[i]) CK(cudaEventCreateWithFlags(&ctx->ev_fork_b[i], cudaEventDisableTiming));
-    }
-    return DSM_OK;
-}
-
 // The per-frame schedule: generate_super_pixels (:960-975) then fuse (:58-71) then initialise (:79),
 // enqueued for the frame slots [f0, f0 + nf).
 // phase bit 0: the pose- and pool-independent part (superpixels, pixel normals, plane fit); bit 1: fuse + initialise.
@@ -561,66 +548,17 @@ static int launch_schedule(dsm_ctx *ctx, int f0, int nf, int max_pool_per_frame,
         ProfScope p(ctx, ID, st);       \
         CALL;                           \
     }
-    // EXPERIMENTAL (variant bit 5): the pixel-normal pass depends on the depth image only, so it is
-    // forked onto a side stream at the start of the schedule and joined before the plane-fit gather; it then fills
-    // the SMs that the one-CTA-per-frame kernels (relax, seed init) and the latency-bound per-seed kernels leave idle.
-    int fk = -1;
-    if ((d.variants & DSM_VARIANT_NORMALS_FORK) && (phase & 1) && ctx->stop_after <= 0)
-    {
-        fk = 4;
-        for (int i = 0; i < 4; i++)
-            if (st == ctx->s_comp[i]) fk = i;
-        if (!ctx->s_fork[fk] || !ctx->ev_fork_a[fk] || !ctx->ev_fork_b[fk]) fk = -1; // created by ensure_fork_streams()
-    }
-    if (fk >= 0)
-    {
-        CK(cudaEventRecord(ctx->ev_fork_a[fk], st));
-        CK(cudaStreamWaitEvent(ctx->s_fork[fk], ctx->ev_fork_a[fk], 0));
-        {
-            ProfScope p(ctx, DSM_K_PIXEL_NORMALS, ctx->s_fork[fk]);
-            dsm_launch_pixel_normals(d, nb, ctx->s_fork[fk]);
-        }
-        CK(cudaEventRecord(ctx->ev_fork_b[fk], ctx->s_fork[fk]));
-    }
-    if ((phase & 1) && !(d.variants & DSM_VARIANT_LEGACY))
-    { // tile schedule (dsm_tile.cu): 12 launches for generate_super_pixels (:960-975)
+    if (phase & 1)
+    { // generate_super_pixels (:960-975): seed init, 3 x (assign [+ stable relaxation], gather, Newton), plane fit
         STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
         for (int it = 0; it < 3; it++) // ITERATION_NUM (fusion_functions.h:8)
         {
-            STEP(it == 0 ? DSM_K_ASSIGN_FIRST : DSM_K_ASSIGN, dsm_launch_assign2(d, nb, it == 0, st)); // relax folded in
-            STEP(DSM_K_UPDATE, dsm_launch_gather(d, ctx->maps, nb, st));
+            STEP(it == 0 ? DSM_K_ASSIGN_FIRST : DSM_K_ASSIGN, dsm_launch_assign2(d, nb, it == 0, st));
+            STEP(DSM_K_GATHER, dsm_launch_gather(d, ctx->maps, nb, st));
             STEP(DSM_K_NEWTON, dsm_launch_newton2(d, nb, st));
         }
         STEP(DSM_K_PLANE_GATHER, dsm_launch_plane_gather(d, ctx->maps, nb, st));
         STEP(DSM_K_PLANE_SOLVE, dsm_launch_gn_solve(d, nb, st));
-    }
-    else if (phase & 1)
-    {
-    STEP(DSM_K_SEED_INIT, dsm_launch_seed_init(d, nb, st));
-    for (int it = 0; it < 3; it++) // ITERATION_NUM (fusion_functions.h:8)
-    {
-        if (it == 0)
-        {
-            STEP(DSM_K_ASSIGN_FIRST, dsm_launch_assign(d, nb, true, st));
-        }
-        else
-        {
-            STEP(DSM_K_ASSIGN, dsm_launch_assign(d, nb, false, st));
-            STEP(DSM_K_RELAX, dsm_launch_relax(d, nb, st));
-        }
-        STEP(DSM_K_GATHER_DEPTHS, dsm_launch_gather_depths(d, nb, st));
-        STEP(DSM_K_NEWTON, dsm_launch_newton(d, nb, st));
-    }
-    if (fk >= 0)
-    {
-        CK(cudaStreamWaitEvent(st, ctx->ev_fork_b[fk], 0));
-    }
-    else
-    {
-        STEP(DSM_K_PIXEL_NORMALS, dsm_launch_pixel_normals(d, nb, st));
-    }
-    STEP(DSM_K_GATHER_POINTS, dsm_launch_gather_points(d, nb, st));
-    STEP(DSM_K_GAUSS_NEWTON, dsm_launch_gauss_newton(d, nb, st));
     }
     if (phase & 2)
     {
@@ -710,23 +648,23 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
     return DSM_OK;
 }
 
+extern "C" int dsm_set_constants(dsm_ctx *ctx, const dsm_constants *k)
+{
+    if (!ctx || !k) return DSM_E_INVALID;
+    if (!(k->huber_range > 0.0) || !(k->baseline > 0.0) || !(k->disparity_error > 0.0) || !(k->min_tolerate_diff >= 0.0)) return DSM_E_INVALID;
+    if (ctx->in_flight) return DSM_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.exec); // captured schedules embed the kernel parameters
+    ctx->graphs.clear();
+    apply_constants(ctx->d, *k);
+    return DSM_OK;
+}
+
 extern "C" int dsm_debug_stop_after(dsm_ctx *ctx, int n)
 {
     if (!ctx) return DSM_E_INVALID;
     ctx->stop_after = n;
-    return DSM_OK;
-}
-
-extern "C" int dsm_debug_set_variants(dsm_ctx *ctx, unsigned mask)
-{
-    if (!ctx) return DSM_E_INVALID;
-    if (ctx->in_flight) return DSM_E_STATE;
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.exec); // captured schedules embed the kernel choice
-    ctx->graphs.clear();
-    ctx->d.variants = (int)mask;
-    if (mask & DSM_VARIANT_NORMALS_FORK) return ensure_fork_streams(ctx);
     return DSM_OK;
 }
 
@@ -1442,7 +1380,7 @@ extern "C" int dsm_get_seeds(dsm_ctx *ctx, int frame, dsm_seed_t *seeds)
     if (!ctx || !seeds || frame < 0 || frame >= ctx->p.max_batch) return DSM_E_INVALID;
     if (!ctx->ran) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    const int plane_done = (ctx->d.variants & DSM_VARIANT_LEGACY) ? 15 : 12; // kernels of the schedule up to and including the plane fit
+    const int plane_done = 12; // kernels of the schedule up to and including the plane fit
     dsm_launch_seeds_export(ctx->d, frame, ctx->seed_export, (ctx->stop_after > 0 && ctx->stop_after < plane_done) ? 1 : 0, ctx->stream);
     CK(cudaMemcpyAsync(seeds, ctx->seed_export, (size_t)ctx->S * sizeof(dsm_seed_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -70,8 +70,6 @@ struct dsm_ctx
     };
     std::vector<InactSeg> inact_segs;
     cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
-    cudaStream_t s_fork[5];              // experimental (variant bit 5): side stream per compute stream for the forked pixel-normal pass
-    cudaEvent_t ev_fork_a[5], ev_fork_b[5];
     // pinned host staging for the small per-batch tables
     float *h_pose; // [B][32]: pose then inverse
     int32_t *h_ofs;

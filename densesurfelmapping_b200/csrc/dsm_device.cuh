@@ -2,22 +2,25 @@
 //
 // HBM layout per context (B = max_batch frames, P = H*Wp pitched pixels, S = seeds per frame):
 //   gray    u8  [B][H][Wp]      Wp = W rounded up to 16 so every row starts 16-byte aligned
-//   depth   f32 [B][H][Wp]      (vector loads, 1-D bulk copies)
+//   depth   f32 [B][H][Wp]      (vector loads, TMA boxes)
+//   invd    f32 [B][H][Wp]      (float)(1.0 / (double)depth) for depth > 0.01, else 0 (:404-405): what the assign passes read
 //   labels  i32 [B][H][Wp]      superpixel_index of the reference (fusion_functions.h:37)
 //   seed    float4 [B][S]       (x, y, mean_intensity, mean_depth)  -- the clustering state
-//   inv_md  f64 [B][S]          1.0 / mean_depth, hoisted out of calculate_cost (:380)
+//   seed_hl float2 [B][S]       1.0 / (double)mean_depth as hi + lo floats (fp32 cost filter of the assign pass)
+//   inv_md  f64 [B][S]          1.0 / (double)mean_depth (exact path of the assign pass, :380)
 //   tstable i32 [B][S]          stable flag + raster time stamp: INT_MAX = stable,
 //                               -1 = unstable, k >= 0 = un-stabled when raster scan reached k
 //   usum    int4 [B][S], und i32 [B][S]   update_seeds integer sums / depth-list lengths
-//   dlist   f32 [B][228][S]     member depths in raster order (K2a -> K2b), [k][seed]
+//   dlist   f32 [B][S][232]     member depths in raster order (k_gather -> k_newton2), one contiguous list per seed
+//   done    i32 [B]             frame-completion tickets of the assign pass
 //   errflag i32 [B]             invariant violations (must stay 0)
-//   nrm     f32 [3][B][H][Wp]   pixel normals (K3 -> K4), 12 B/px instead of the reference's 36 B/px
 //   kx, ky  f32 [Wp+16], [H+16] back-projection factors, computed once per context
-//   qlist   f32 [3][B][228][S]  centred plane-fit inlier points (K4a -> K4b), [k][seed]
+//   qlist   f32 [B][S][3][232]  centred plane-fit inlier points (k_plane_gather -> k_gn_solve fallback passes)
+//   hrec    f64 [B][24][S]      first Gauss-Newton pass sums of the plane fit, field-major
 //   pfsum   float4 [B][S][2]    per-seed plane-fit summary
 //   plane   float4 [B][S][3]    (n.xyz, view_cos) (posi.xyz, mean_depth) (size, I, x, y)
 //   fused   i32 [B][S]          Superpixel_seed::fused
-//   list    int2 [B][P]         pixels owned by stable seeds: (pitched raster index, winner)
+//   list    int2 [B][P]         deferred pixels of the stable relaxation: (pitched raster index, winner)
 //   nlist   i32 [B]
 //   pool    dsm_surfel_t [max_local]   AoS, ABI layout (44 B) so upload/download are plain copies
 //   poolofs i32 [B+1]
@@ -39,6 +42,10 @@ struct DsmDev
     int frame0; // first frame slot this launch works on (chunked copy/compute overlap)
     int Sp; // S rounded up to 32: row stride of the [k][seed] scratch lists
     float fx, fy, cx, cy, fuse_far, fuse_near, camera_f;
+    // algorithm constants (dsm_set_constants; fusion_functions.h:12-21).  huber_hi = smallest float >= huber: for every float x,
+    // (double)x < huber  <=>  x < huber_hi  and  (double)x >= huber  <=>  x >= huber_hi (the float-vs-double-literal compares)
+    double huber, baseline, disparity_error, min_tolerate_diff;
+    float huber_hi;
     // per-frame strides in elements
     size_t px_stride; // H*Wp
     // buffers
@@ -50,14 +57,12 @@ struct DsmDev
     int32_t *tstable;
     int4 *usum;         // update_seeds integer sums per seed: (count, sum x, sum y, sum intensity)
     int32_t *und;       // number of member depths > 0.1
-    float *dlist;       // [B][DL_CAP][S] member depths in raster order, [k][seed] so thread-per-seed reads coalesce
+    float *dlist;       // [B][S][232] member depths in raster order, one contiguous list per seed
     int32_t *errflag;   // [B] count of "impossible" events (non-stable seed without members)
     float4 *plane;
-    float *nrm;         // pixel normals, 3 planes of B*px_stride floats (x | y | z)
-    size_t nrm_plane;   // B * px_stride
     const float *kx;    // [Wp+16]: ((float)u - cx) / fx, the per-column factor of back_project (:94)
     const float *ky;    // [H+16]:  ((float)v - cy) / fy
-    float *qlist;       // plane-fit scratch: 3 planes [B][PF_CAP][S] of centred inlier points
+    float *qlist;       // [B][S][3][232] centred plane-fit inlier points
     float4 *pfsum;      // [B][S][2]: (sum n.xyz, max_dist) (mean.xyz, inlier count or 0 if rejected)
     int32_t *fused;
     int2 *list;
@@ -74,21 +79,8 @@ struct DsmDev
     float *invd;        // [B][H][Wp] (float)(1.0 / (double)depth) for depth > 0.01, else 0 (:404-405), written by the first assign pass
     float2 *seed_hl;    // [B][S] 1.0 / (double)mean_depth split into two floats (hi, lo) for the filtered assign pass
     int32_t *done;      // [B] frame-completion tickets of the assign pass (the last CTA of a frame runs the stable relaxation)
-    double *hrec;       // [B][S][24] plane fit, first residual pass: H = sum 2 q q^T (9), the same over out-of-range points (10), their clamped gradient (4), packed (margin, qmax2)
-    int variants;           // DSM_VARIANT_* bits: experimental kernel variants (0 = the measured default path)
+    double *hrec;       // [B][24][S] plane fit, first residual pass: H = sum 2 q q^T (9), the same over out-of-range points (10), their clamped gradient (4), packed (margin, qmax2)
 };
-
-// experimental kernel variants (dsm_debug_set_variants).  All are bit-identical to the default
-// kernels by construction (same arithmetic, same order; only the data movement differs).
-#define DSM_VARIANT_NEWTON_STAGED 1u  // k_newton_staged: list staged once into shared memory with cp.async
-#define DSM_VARIANT_GATHER_TILED 2u   // k_gather_depths_tiled: window tiles by 1-D bulk copies (TMA) into shared memory
-#define DSM_VARIANT_POINTS_TILED 4u   // k_gather_points_tiled: same for the plane-fit gather
-#define DSM_VARIANT_INIT_MULTIBLOCK 16u // k_init_surfels_mb: several CTAs per frame, offsets by re-evaluating the emit predicate
-#define DSM_VARIANT_NORMALS_FORK 32u   // host schedule: the pixel-normal pass runs on a side stream concurrently with the clustering
-#define DSM_VARIANT_SEED_INIT_WIDE 64u  // k_seed_init_wide: hole search with the whole window in flight
-#define DSM_VARIANT_ASSIGN_FEWER_CVT 128u // k_assign_x: two of the seven float<->double conversions per candidate done on the fp64 pipe
-#define DSM_VARIANT_LEGACY 256u       // round-1 schedule (17 launches, kernels of dsm_kernels.cu) instead of the tile schedule
-#define DSM_VARIANT_GN_STAGED 8u      // k_gauss_newton_staged: point list streamed through shared memory (cp.async, double-buffered)
 
 // TMA descriptors (cuTensorMapEncodeTiled) of the three per-pixel arrays as [B][H][Wp] tensors; box = one seed tile plus halo
 struct DsmMaps
@@ -111,30 +103,18 @@ enum DsmKernelId
     DSM_K_SEED_INIT = 0,
     DSM_K_ASSIGN_FIRST = 1,
     DSM_K_ASSIGN = 2,
-    DSM_K_RELAX = 3,
-    DSM_K_GATHER_DEPTHS = 4,
-    DSM_K_NEWTON = 5,
-    DSM_K_GATHER_POINTS = 6,
+    DSM_K_GATHER = 3,       // window gather of update_seeds_kernel
+    DSM_K_NEWTON = 4,       // Huber-Newton solve of update_seeds_kernel
+    DSM_K_PLANE_GATHER = 5, // pixel normals + plane-fit gather
+    DSM_K_PLANE_SOLVE = 6,  // plane-fit solver
     DSM_K_FUSE = 7,
     DSM_K_INIT_SURFELS = 8,
     DSM_K_REPACK = 9,
-    DSM_K_PIXEL_NORMALS = 10,
-    DSM_K_GAUSS_NEWTON = 11,
-    DSM_K_UPDATE = 12,       // tile schedule: window gather (the Huber-Newton solve reports as slic_newton)
-    DSM_K_PLANE_GATHER = 13, // tile schedule: pixel normals + plane-fit gather
-    DSM_K_PLANE_SOLVE = 14,  // tile schedule: plane-fit solver
 };
 
 // launchers (dsm_kernels.cu); nb = frames in this batch
 void dsm_launch_repack(const DsmDev &d, int nb, const uint8_t *gray_packed, const float *depth_packed, cudaStream_t s);
 void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_assign(const DsmDev &d, int nb, bool first, cudaStream_t s);
-void dsm_launch_relax(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_gather_depths(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_newton(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_pixel_normals(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_gather_points(const DsmDev &d, int nb, cudaStream_t s);
-void dsm_launch_gauss_newton(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, int raw_md, cudaStream_t s);

@@ -15,6 +15,7 @@
 //    conflict-free LDS.128), compact into shared memory and run the order-sensitive per-seed math from there.
 // All citations ":NNN" refer to /root/reference/surfel_fusion/src/fusion_functions.cpp.
 #include "dsm_exact.cuh"
+#include <cuda_pipeline.h>
 
 // -------------------------------------------------------------------------------------------
 // mbarrier / TMA helpers (raw PTX; one elected thread arms the barrier and issues the tensor copies)
@@ -484,16 +485,18 @@ __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDe
             }
         }
         __syncthreads();
-        // copy-out: seed slot q2 of this round -> dlist[b][seed][0 .. nd), 16 bytes per thread and step
-        for (int i = threadIdx.x; i < 16 * (DL_STRIDE / 4); i += 256)
+        // copy-out: warp w moves the lists of seed slots w and w + 8 of this round -> dlist[b][seed][0 .. nd), 16 bytes per lane
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++)
         {
-            const int q2 = i / (DL_STRIDE / 4), j4 = i - q2 * (DL_STRIDE / 4);
-            if (4 * j4 < s_nd[q2])
-            {
-                const int sl2 = rd * 16 + q2;
-                const int s2 = (blockIdx.y * DSM_TILE_SY + (sl2 >> 3)) * d.spw + blockIdx.x * DSM_TILE_SX + (sl2 & 7);
-                reinterpret_cast<float4 *>(d.dlist + (so + s2) * DL_STRIDE)[j4] = reinterpret_cast<const float4 *>(lists + q2 * DL_STRIDE)[j4];
-            }
+            const int q2 = warp + 8 * h2, n2 = s_nd[q2];
+            if (n2 == 0) continue; // warp-uniform
+            const int sl2 = rd * 16 + q2;
+            const int s2 = (blockIdx.y * DSM_TILE_SY + (sl2 >> 3)) * d.spw + blockIdx.x * DSM_TILE_SX + (sl2 & 7);
+            float4 *dst = reinterpret_cast<float4 *>(d.dlist + (so + s2) * DL_STRIDE);
+            const float4 *src = reinterpret_cast<const float4 *>(lists + q2 * DL_STRIDE);
+            if (4 * lane < n2) dst[lane] = src[lane];
+            if (4 * (lane + 32) < n2) dst[lane + 32] = src[lane + 32];
         }
     }
 }
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDe
 __global__ void __launch_bounds__(128, 4) k_newton2(const __grid_constant__ DsmDev d)
 {
     // The lists of the CTA's 128 seeds are contiguous runs in global memory; the CTA copies them into shared memory with
-    // coalesced 16-byte accesses (one list after the other, lengths rounded up to 4) and every thread then walks its own
+    // coalesced 16-byte asynchronous copies (cp.async; one list after the other, lengths rounded up to 4) and every thread then walks its own
     // list there up to six times.  Lists that do not fit (rare: NW_CAP covers 92 entries per seed) stay in global memory.
     __shared__ __align__(16) float buf[NW_CAP];
     __shared__ int s_off[128], s_len[128], s_wsum[4];
@@ -531,8 +534,10 @@ __global__ void __launch_bounds__(128, 4) k_newton2(const __grid_constant__ DsmD
         if (off < 0 || len == 0) continue; // warp-uniform
         const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + blockIdx.x * 128 + q) * DL_STRIDE);
         float4 *dst = reinterpret_cast<float4 *>(buf + off);
-        for (int j4 = lane; 4 * j4 < len; j4 += 32) dst[j4] = src[j4];
+        for (int j4 = lane; 4 * j4 < len; j4 += 32) __pipeline_memcpy_async(dst + j4, src + j4, 16); // LDGSTS: no register staging, no wait
     }
+    __pipeline_commit();
+    __pipeline_wait_prior(0); // every copy of the CTA was in flight at once: one memory round trip for all 128 lists
     __syncthreads();
     if (!act) return;
     const int4 su = d.usum[so + s];
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(128, 4) k_newton2(const __grid_constant__ DsmD
         for (int it = 0; it < 5; it++)
         { // damped Huber-Newton (:534-554)
             float sa = 0.0f, sb = 0.0f;
-            if ((md - zmn) < F_0p4_HI && (md - zmx) > -F_0p4_HI)
+            if ((md - zmn) < d.huber_hi && (md - zmx) > -d.huber_hi)
             { // every entry inside the Huber range ((double)r < 0.4 && (double)r > -0.4, :540): pure chain, sum_b = nd exact +2 steps
                 int k = 0;
                 for (; k + 8 <= nd; k += 8)
@@ -593,17 +598,47 @@ __global__ void __launch_bounds__(128, 4) k_newton2(const __grid_constant__ DsmD
                 sb = (float)(2 * nd);
             }
             else
-            {
-                for (int k = 0; k < nd; k++)
+            { // some entry is outside the range: 8 entries per step; a step whose 8 residuals are all inside is the same
+              // chain plus eight exact +2 steps of sum_b, only the (few) other steps classify entry by entry (:540-547)
+                int k = 0;
+                for (; k + 8 <= nd; k += 8)
+                {
+                    const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
+                    const float rr[8] = {md - a.x, md - a.y, md - a.z, md - a.w, md - c.x, md - c.y, md - c.z, md - c.w};
+                    float rmx = rr[0], rmn = rr[0];
+#pragma unroll
+                    for (int j = 1; j < 8; j++) rmx = fmaxf(rmx, rr[j]), rmn = fminf(rmn, rr[j]);
+                    if (rmx < d.huber_hi && rmn > -d.huber_hi)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sa = fmaf(2.0f, rr[j], sa);
+                        sb += 16;
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            if (rr[j] < d.huber_hi && rr[j] > -d.huber_hi)
+                            {
+                                sa = fmaf(2.0f, rr[j], sa);
+                                sb += 2;
+                            }
+                            else
+                                sa = (float)((double)sa + (rr[j] > 0 ? d.huber : -1 * d.huber));
+                        }
+                    }
+                }
+                for (; k < nd; k++)
                 {
                     const float rr = md - dl[k];
-                    if (rr < F_0p4_HI && rr > -F_0p4_HI)
+                    if (rr < d.huber_hi && rr > -d.huber_hi)
                     {
-                        sa += 2 * rr;
+                        sa = fmaf(2.0f, rr, sa);
                         sb += 2;
                     }
                     else
-                        sa = (float)((double)sa + (rr > 0 ? HUBER_RANGE : -1 * HUBER_RANGE));
+                        sa = (float)((double)sa + (rr > 0 ? d.huber : -1 * d.huber));
                 }
             }
             const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
@@ -743,7 +778,7 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
                 {
                     vm |= (zz[j] > F_0p05_LO ? 1u : 0u) << (4 * qd + j); // (double)depth > 0.05 (:827)
                     const float rr = sd.w - zz[j];
-                    im |= ((rr < F_0p4_HI && rr > -F_0p4_HI) ? 1u : 0u) << (4 * qd + j); // inlier (:849-860)
+                    im |= ((rr < d.huber_hi && rr > -d.huber_hi) ? 1u : 0u) << (4 * qd + j); // inlier (:849-860)
                 }
             }
         }
@@ -862,12 +897,12 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
         qx[j] = ax, qy[j] = ay, qz[j] = az;
         const float rr = ax * n0x + ay * n0y + az * n0z + 0.f; // first-pass residual (:133), b = 0
         rnan |= !(rr == rr);
-        margin = fminf(margin, fabsf(fabsf(rr) - 0.4f));
+        margin = fminf(margin, fabsf(fabsf(rr) - d.huber_hi));
         qmax2 = fmaxf(qmax2, ax * ax + ay * ay + az * az);
         h[0] += (double)(2 * ax * ax), h[1] += (double)(2 * ax * ay), h[2] += (double)(2 * ax * az), h[3] += (double)(2 * ax);
         h[4] += (double)(2 * ay * ay), h[5] += (double)(2 * ay * az), h[6] += (double)(2 * ay);
         h[7] += (double)(2 * az * az), h[8] += (double)(2 * az);
-        if (!(rr < F_0p4_HI && rr > -F_0p4_HI)) omask |= 1u << it; // (:134)
+        if (!(rr < d.huber_hi && rr > -d.huber_hi)) omask |= 1u << it; // (:134)
     }
 #pragma unroll
     for (int i = 0; i < 9; i++) h[i] = group8_sum_d(h[i]);
@@ -879,13 +914,14 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
         rnan |= __shfl_xor_sync(FULL, rnan ? 1 : 0, o) != 0;
     }
     if (rnan) margin = __int_as_float(0x7fc00000); // a NaN residual: no pass may ever be skipped
-    double *hr = d.hrec + (so + s) * HREC;
+    double *hr = d.hrec + (size_t)b * HREC * d.S + s; // [b][field][seed]: the solver's thread-per-seed reads coalesce
+    const size_t hs = (size_t)d.S;
     if (ok)
     { // the group's lanes write the 9 sums and the packed (margin, qmax2)
 #pragma unroll
         for (int i = 0; i < 9; i++)
-            if ((i & 7) == gl) hr[i] = h[i];
-        if (gl == 7) hr[23] = __hiloint2double(__float_as_int(qmax2), __float_as_int(margin));
+            if ((i & 7) == gl) hr[i * hs] = h[i];
+        if (gl == 7) hr[23 * hs] = __hiloint2double(__float_as_int(qmax2), __float_as_int(margin));
     }
     // the out-of-range points (few per seed, none for most): the same ten sums (with ww) and the clamped gradient
     // (:157-170), accumulated in a second sweep over just those points so that the 14 accumulators are not live above
@@ -904,14 +940,14 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
             ho[0] += (double)(2 * ax * ax), ho[1] += (double)(2 * ax * ay), ho[2] += (double)(2 * ax * az), ho[3] += (double)(2 * ax);
             ho[4] += (double)(2 * ay * ay), ho[5] += (double)(2 * ay * az), ho[6] += (double)(2 * ay);
             ho[7] += (double)(2 * az * az), ho[8] += (double)(2 * az), ho[9] += 2;
-            if (rr >= F_0p4_HI)
+            if (rr >= d.huber_hi)
             { // (double)r >= 0.4 (:157-163)
-                jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay, jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                jo[0] += d.huber * (double)ax, jo[1] += d.huber * (double)ay, jo[2] += d.huber * (double)az, jo[3] += d.huber;
             }
-            else if (rr <= -F_0p4_HI)
+            else if (rr <= -d.huber_hi)
             { // (double)r <= -0.4 (:164-170)
-                jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay, jo[2] += -1 * HUBER_RANGE * (double)az,
-                    jo[3] += -1 * HUBER_RANGE;
+                jo[0] += -1 * d.huber * (double)ax, jo[1] += -1 * d.huber * (double)ay, jo[2] += -1 * d.huber * (double)az,
+                    jo[3] += -1 * d.huber;
             }
         }
 #pragma unroll
@@ -925,10 +961,10 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
         {
 #pragma unroll
             for (int i = 0; i < 14; i++)
-                if ((i & 7) == gl) hr[9 + i] = i < 10 ? ho[i] : jo[i - 10];
+                if ((i & 7) == gl) hr[(9 + i) * hs] = i < 10 ? ho[i] : jo[i - 10];
         }
         else if (gl == 0)
-            hr[18] = 0.0;
+            hr[18 * hs] = 0.0;
     }
     if (live && gl == 0)
     {
@@ -948,13 +984,13 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
 // The first pass's sums arrive from k_plane_gather, so most seeds are five register-only 4x4 solves; the others read
 // the centred points from qlist[b][seed][plane][k] (16-byte loads) exactly like the reference's loop (:131-171).
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void solve4_spd_t(const double *h, const double *j, double *u)
-{ // h: 10 unique entries xx xy xz xw yy yz yw zz zw ww of an SPD matrix; solves H u = j
-    const double a00 = h[0], a01 = h[1], a02 = h[2], a03 = h[3];
+__device__ __forceinline__ void solve4_spd_t(const double *h, double lambda, const double *j, double *u)
+{ // h: 10 unique entries xx xy xz xw yy yz yw zz zw ww of an SPD matrix; solves (H + lambda I) u = j
+    const double a00 = h[0] + lambda, a01 = h[1], a02 = h[2], a03 = h[3];
     const double i0 = 1.0 / a00;
     const double l10 = a01 * i0, l20 = a02 * i0, l30 = a03 * i0;
-    const double a11 = h[4] - l10 * a01, a12 = h[5] - l10 * a02, a13 = h[6] - l10 * a03;
-    const double a22p = h[7] - l20 * a02, a23p = h[8] - l20 * a03, a33p = h[9] - l30 * a03;
+    const double a11 = (h[4] + lambda) - l10 * a01, a12 = h[5] - l10 * a02, a13 = h[6] - l10 * a03;
+    const double a22p = (h[7] + lambda) - l20 * a02, a23p = h[8] - l20 * a03, a33p = (h[9] + lambda) - l30 * a03;
     const double i1 = 1.0 / a11;
     const double l21 = a12 * i1, l31 = a13 * i1;
     const double a22 = a22p - l21 * a12, a23 = a23p - l21 * a13, a33q = a33p - l31 * a13;
@@ -971,7 +1007,7 @@ __device__ __forceinline__ void solve4_spd_t(const double *h, const double *j, d
     u[0] = y0 * i0 - l10 * u[1] - l20 * u[2] - l30 * u[3];
 }
 
-__global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(128, 5) k_gn_solve(const __grid_constant__ DsmDev d)
 {
     const int b = d.frame0 + blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -989,26 +1025,25 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
         const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
         float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
         const float mxs = P1.x, mys = P1.y, mzs = P1.z;
-        const double *hr = d.hrec + (so + s) * HREC;
-        double hall[10], ho[10], jo[4];
+        const double *hr = d.hrec + (size_t)b * HREC * d.S + s; // [b][field][seed]
+        const size_t hs = (size_t)d.S;
+        // hh0 = H over the in-range points = H_all - ho; jo = clamped gradient of the out-of-range points.  H_all itself is
+        // only needed again when the points have to be classified anew (rare), so it is not kept in registers.
+        double hh0[10], jo[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 9; i++) hall[i] = hr[i];
-        hall[9] = 2.0 * (double)n;
-#pragma unroll
-        for (int i = 0; i < 10; i++) ho[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) jo[i] = 0.0;
-        if (hr[18] != 0.0)
+        for (int i = 0; i < 9; i++) hh0[i] = hr[i * hs];
+        hh0[9] = 2.0 * (double)n;
+        if (hr[18 * hs] != 0.0)
         { // the first pass found points outside the Huber range
 #pragma unroll
-            for (int i = 0; i < 10; i++) ho[i] = hr[9 + i];
+            for (int i = 0; i < 10; i++) hh0[i] -= hr[(9 + i) * hs];
 #pragma unroll
-            for (int i = 0; i < 4; i++) jo[i] = hr[19 + i];
+            for (int i = 0; i < 4; i++) jo[i] = hr[(19 + i) * hs];
         }
-        const double pk = hr[23];
+        const double pk = hr[23 * hs];
         float margin = __int_as_float(__double2loint(pk));
         const float qmax = sqrtf(__int_as_float(__double2hiint(pk)));
-        float moved = 0.f; // bound on the change of any residual since the classification behind ho / jo was made
+        float moved = 0.f; // bound on the change of any residual since the classification behind hh0 / jo was made
         for (int gn = 0; gn < 5; gn++)
         {
             if (gn > 0 && !(moved + 2e-3f < margin)) // NaN-safe: a NaN margin keeps evaluating
@@ -1016,7 +1051,8 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
                 const float4 *qx = reinterpret_cast<const float4 *>(d.qlist + (so + s) * (3 * PL_STRIDE));
                 const float4 *qy = qx + PL_STRIDE / 4, *qz = qy + PL_STRIDE / 4;
 #pragma unroll
-                for (int i = 0; i < 10; i++) ho[i] = 0.0;
+                for (int i = 0; i < 9; i++) hh0[i] = hr[i * hs];
+                hh0[9] = 2.0 * (double)n;
 #pragma unroll
                 for (int i = 0; i < 4; i++) jo[i] = 0.0;
                 float mg = __int_as_float(0x7f800000);
@@ -1025,21 +1061,21 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
                 {
                     const float r = ax * nx + ay * ny + az * nz + nb; // (:133)
                     rnan |= !(r == r);
-                    mg = fminf(mg, fabsf(fabsf(r) - 0.4f));
-                    if (!(r < F_0p4_HI && r > -F_0p4_HI)) // (:134)
+                    mg = fminf(mg, fabsf(fabsf(r) - d.huber_hi));
+                    if (!(r < d.huber_hi && r > -d.huber_hi)) // (:134)
                     {
-                        ho[0] += (double)(2 * ax * ax), ho[1] += (double)(2 * ax * ay), ho[2] += (double)(2 * ax * az), ho[3] += (double)(2 * ax);
-                        ho[4] += (double)(2 * ay * ay), ho[5] += (double)(2 * ay * az), ho[6] += (double)(2 * ay);
-                        ho[7] += (double)(2 * az * az), ho[8] += (double)(2 * az), ho[9] += 2;
-                        if (r >= F_0p4_HI)
-                        { // (double)r >= 0.4 (:157-163)
-                            jo[0] += HUBER_RANGE * (double)ax, jo[1] += HUBER_RANGE * (double)ay;
-                            jo[2] += HUBER_RANGE * (double)az, jo[3] += HUBER_RANGE;
+                        hh0[0] -= (double)(2 * ax * ax), hh0[1] -= (double)(2 * ax * ay), hh0[2] -= (double)(2 * ax * az), hh0[3] -= (double)(2 * ax);
+                        hh0[4] -= (double)(2 * ay * ay), hh0[5] -= (double)(2 * ay * az), hh0[6] -= (double)(2 * ay);
+                        hh0[7] -= (double)(2 * az * az), hh0[8] -= (double)(2 * az), hh0[9] -= 2;
+                        if (r >= d.huber_hi)
+                        { // (double)r >= HUBER_RANGE (:157-163)
+                            jo[0] += d.huber * (double)ax, jo[1] += d.huber * (double)ay;
+                            jo[2] += d.huber * (double)az, jo[3] += d.huber;
                         }
-                        else if (r <= -F_0p4_HI)
-                        { // (double)r <= -0.4 (:164-170)
-                            jo[0] += -1 * HUBER_RANGE * (double)ax, jo[1] += -1 * HUBER_RANGE * (double)ay;
-                            jo[2] += -1 * HUBER_RANGE * (double)az, jo[3] += -1 * HUBER_RANGE;
+                        else if (r <= -d.huber_hi)
+                        { // (double)r <= -HUBER_RANGE (:164-170)
+                            jo[0] += -1 * d.huber * (double)ax, jo[1] += -1 * d.huber * (double)ay;
+                            jo[2] += -1 * d.huber * (double)az, jo[3] += -1 * d.huber;
                         }
                     }
                 };
@@ -1062,17 +1098,14 @@ __global__ void __launch_bounds__(128) k_gn_solve(const __grid_constant__ DsmDev
                 margin = rnan ? __int_as_float(0x7fc00000) : mg;
                 moved = 0.f;
             }
-            double hh[10], jj[4];
-#pragma unroll
-            for (int i = 0; i < 10; i++) hh[i] = hall[i] - ho[i];
+            double jj[4];
             const double tx = (double)nx, ty = (double)ny, tz = (double)nz, tb = (double)nb;
-            jj[0] = ((hh[0] * tx + hh[1] * ty) + hh[2] * tz) + hh[3] * tb + jo[0];
-            jj[1] = ((hh[1] * tx + hh[4] * ty) + hh[5] * tz) + hh[6] * tb + jo[1];
-            jj[2] = ((hh[2] * tx + hh[5] * ty) + hh[7] * tz) + hh[8] * tb + jo[2];
-            jj[3] = ((hh[3] * tx + hh[6] * ty) + hh[8] * tz) + hh[9] * tb + jo[3];
-            hh[0] += 5, hh[4] += 5, hh[7] += 5, hh[9] += 5; // LM damping (:172-175)
+            jj[0] = ((hh0[0] * tx + hh0[1] * ty) + hh0[2] * tz) + hh0[3] * tb + jo[0];
+            jj[1] = ((hh0[1] * tx + hh0[4] * ty) + hh0[5] * tz) + hh0[6] * tb + jo[1];
+            jj[2] = ((hh0[2] * tx + hh0[5] * ty) + hh0[7] * tz) + hh0[8] * tb + jo[2];
+            jj[3] = ((hh0[3] * tx + hh0[6] * ty) + hh0[8] * tz) + hh0[9] * tb + jo[3];
             double u[4];
-            solve4_spd_t(hh, jj, u);
+            solve4_spd_t(hh0, 5.0, jj, u); // LM damping: + 5 on the diagonal (:172-175)
             const float ox = nx, oy = ny, oz = nz, ob = nb;
             nx = (float)((double)nx - u[0]);
             ny = (float)((double)ny - u[1]);

@@ -78,9 +78,9 @@ typedef struct dsm_seed_t
 /* ---- context parameters ---- */
 /* The first eight fields are the arguments of FusionFunctions::initialize
  * (fusion_functions.h:84-87, fusion_functions.cpp:7-28).  The rest size the GPU-resident
- * buffers.  The algorithm constants are the reference's "drive" set
- * (fusion_functions.h:7-16: SP_SIZE 8, ITERATION_NUM 3, HUBER_RANGE 0.4, BASELINE 0.5,
- * DISPARITY_ERROR 4.0, MIN_TOLERATE_DIFF 0.1, MAX_ANGLE_COS 0.1) compiled into the kernels. */
+ * buffers.  SP_SIZE 8, ITERATION_NUM 3 and MAX_ANGLE_COS 0.1 (fusion_functions.h:8-11) are compiled into the kernels;
+ * the four constants the reference ships in two sets ("drive" / "RGBD", fusion_functions.h:12-21) are run-time
+ * values: a new context holds the drive set, dsm_set_constants() switches. */
 typedef struct dsm_params
 {
     int32_t width, height;
@@ -104,6 +104,18 @@ const char *dsm_last_error(const dsm_ctx *ctx);
 int dsm_create(const dsm_params *params, int device, void *cuda_stream, dsm_ctx **out);
 void dsm_destroy(dsm_ctx *ctx);
 int dsm_num_seeds(const dsm_ctx *ctx); /* S = (W/8)*(H/8) */
+
+/* The constants the reference selects at compile time by (un)commenting one of two #define blocks (fusion_functions.h:12-21):
+ * HUBER_RANGE (Huber-Newton mean depth :540-547, plane-fit inliers :850 and robust weights :134-169), and BASELINE,
+ * DISPARITY_ERROR, MIN_TOLERATE_DIFF (depth tolerance of the surfel association :252-253).  Applies to every later call on
+ * the context; a fresh context holds DSM_CONSTANTS_DRIVE. */
+typedef struct dsm_constants
+{
+    double huber_range, baseline, disparity_error, min_tolerate_diff;
+} dsm_constants;
+#define DSM_CONSTANTS_DRIVE {0.4, 0.5, 4.0, 0.1}   /* fusion_functions.h:13-16, the set the reference ships enabled (KITTI) */
+#define DSM_CONSTANTS_RGBD {0.05, 0.08, 1.0, 0.05} /* fusion_functions.h:18-21, the commented RGB-D / VINS set */
+int dsm_set_constants(dsm_ctx *ctx, const dsm_constants *constants);
 
 /* ---- reference-identical single-frame call ----
  * Replaces FusionFunctions::fuse_initialize_map (fusion_functions.cpp:30-83) with the same
@@ -280,17 +292,10 @@ int dsm_debug_stop_after(dsm_ctx *ctx, int n_kernels);
  * without members); the parity tests assert it is 0. */
 int dsm_debug_invariant_violations(dsm_ctx *ctx, int *count);
 
-/* debug / experiments: select experimental kernel variants (bit mask, 0 = the measured default path; bits in
- * csrc/dsm_device.cuh, DSM_VARIANT_*).  Every variant computes bit-identical results by construction; they exist so
- * that a data-movement change can be A/B-timed and parity-checked on the same build (the environment variable
- * DSM_EXPERIMENTAL_VARIANTS sets the initial mask of every context, so the whole test suite and bench.py can run
- * under a variant unchanged).  Drops the context's captured CUDA graphs. */
-int dsm_debug_set_variants(dsm_ctx *ctx, unsigned mask);
-
 /* ---- measurement hooks ----
  * Per-kernel CUDA-event timing on the context's stream.  mask selects kernels (bit k = kernel
  * id k, see dsm_kernel_name); 0 disables.  Accumulates until dsm_profile_reset(). */
-#define DSM_NUM_KERNELS 15
+#define DSM_NUM_KERNELS 10
 int dsm_profile_enable(dsm_ctx *ctx, uint32_t kernel_mask);
 int dsm_profile_reset(dsm_ctx *ctx);
 /* resolves pending events (synchronises); ms_total/launches are [DSM_NUM_KERNELS] */

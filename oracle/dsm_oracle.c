@@ -37,10 +37,14 @@
 #define ITERATION_NUM 3      /* fusion_functions.h:8  */
 #define THREAD_NUM 10        /* fusion_functions.h:9  */
 #define MAX_ANGLE_COS 0.1    /* fusion_functions.h:11 */
-#define HUBER_RANGE 0.4      /* fusion_functions.h:13 */
-#define BASELINE 0.5         /* fusion_functions.h:14 */
-#define DISPARITY_ERROR 4.0  /* fusion_functions.h:15 */
-#define MIN_TOLERATE_DIFF 0.1 /* fusion_functions.h:16 */
+/* The reference selects these four at compile time by (un)commenting one of two #define blocks (fusion_functions.h:12-21);
+ * here they are process-wide variables so that one library serves both sets: "drive" (the default, :13-16) and "RGBD" (:18-21).
+ * dsmor_set_constants switches (pyoracle sets them before every call of a wrapper object). */
+static double g_huber_range = 0.4, g_baseline = 0.5, g_disparity_error = 4.0, g_min_tolerate_diff = 0.1;
+#define HUBER_RANGE g_huber_range
+#define BASELINE g_baseline
+#define DISPARITY_ERROR g_disparity_error
+#define MIN_TOLERATE_DIFF g_min_tolerate_diff
 
 /* elements.h:5-20 (60 bytes) */
 typedef struct
@@ -86,6 +90,14 @@ typedef struct
 } ctx_t;
 
 /* ---- initialize (:7-28) ---- */
+void dsmor_set_constants(double huber_range, double baseline, double disparity_error, double min_tolerate_diff)
+{
+    g_huber_range = huber_range;
+    g_baseline = baseline;
+    g_disparity_error = disparity_error;
+    g_min_tolerate_diff = min_tolerate_diff;
+}
+
 void *dsmor_create(int w, int h, float fx, float fy, float cx, float cy, float far_d, float near_d)
 {
     if (w % SP_SIZE > 4 || h % SP_SIZE > 4 || w < 3 * SP_SIZE || h < 3 * SP_SIZE)

@@ -119,17 +119,45 @@ class RefSerial(_Base):
     libname = "libdsm_ref_serial.so"
 
 
+class RefSerialRGBD(_Base):
+    """The serial reference compiled with its second constant set (fusion_functions.h:17-21; oracle/ref_driver.cpp, DSM_REF_RGBD)."""
+    prefix = "dsmref_"
+    libname = "libdsm_ref_serial_rgbd.so"
+
+
 class RefMT(_Base):
     prefix = "dsmref_"
     libname = "libdsm_ref_mt.so"
+
+
+CONSTANTS_DRIVE = (0.4, 0.5, 4.0, 0.1)    # fusion_functions.h:13-16
+CONSTANTS_RGBD = (0.05, 0.08, 1.0, 0.05)  # fusion_functions.h:18-21
 
 
 class Restatement(_Base):
     prefix = "dsmor_"
     libname = "libdsm_oracle.so"
 
+    def __init__(self, cam, constants=CONSTANTS_DRIVE):
+        super().__init__(cam)
+        self.constants = tuple(float(c) for c in constants)
+        self.lib.dsmor_set_constants.argtypes = [ctypes.c_double] * 4
+        self.lib.dsmor_set_constants.restype = None
+
+    def _select(self):
+        self.lib.dsmor_set_constants(*self.constants)  # process-wide in the C file: set before every call of this object
+
+    def fuse(self, *a, **k):
+        self._select()
+        return super().fuse(*a, **k)
+
+    def superpixels(self, *a, **k):
+        self._select()
+        return super().superpixels(*a, **k)
+
     def debug_iters(self, gray, depth, iters, last_with_update=True):
         """seed init + `iters` assign passes (last update_seeds optional); returns (labels, seeds)."""
+        self._select()
         gray = np.ascontiguousarray(gray, dtype=np.uint8)
         depth = np.ascontiguousarray(depth, dtype=np.float32)
         self.lib.dsmor_debug_iters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]

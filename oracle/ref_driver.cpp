@@ -55,6 +55,20 @@ static inline int dsm_ref_noprintf(const char *, ...) { return 0; }
 #define printf dsm_ref_noprintf
 
 #define private public
+#ifdef DSM_REF_RGBD
+// The reference's second constant set ("for RGBD", fusion_functions.h:17-21) ships commented out.  This variant compiles the
+// same unmodified source with exactly those four values: the header is included first (its #pragma once makes the
+// source's own #include a no-op), the four macros are redefined, then the source follows.
+#include "fusion_functions.h"
+#undef HUBER_RANGE
+#undef BASELINE
+#undef DISPARITY_ERROR
+#undef MIN_TOLERATE_DIFF
+#define HUBER_RANGE 0.05
+#define BASELINE 0.08
+#define DISPARITY_ERROR 1.0
+#define MIN_TOLERATE_DIFF 0.05
+#endif
 #include DSM_REF_SOURCE // "/root/reference/surfel_fusion/src/fusion_functions.cpp"
 #undef private
 #undef printf

@@ -3,10 +3,8 @@
 Markers / switches:
   -m "not gpu"             CPU suite: oracle vs golden vectors, ABI surface, host logic, gloo gather, file writers
   -m gpu                   parity suite proper, through the C ABI on a B200
-  DSM_TEST_VARIANTS=1      also run tests/test_gpu_variants.py (experimental kernel variants)
-  DSM_TEST_UNVERIFIED=1    also run the GPU tests of code written after round 1's GPU budget was spent
-                           (chunked stream, C++ resident-pool helper)
-  DSM_EXPERIMENTAL_VARIANTS=<mask>   library switch: run ANY test / bench.py with the given variant mask as default
+No test is gated by an environment variable; the only hardware-conditional skip is the two-rank NCCL test, which
+needs two GPUs (tests/test_gpu_comm.py, run with `gpurun --gpus 2`).
 """
 import os
 import sys

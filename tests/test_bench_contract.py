@@ -12,12 +12,11 @@ def test_every_scheduled_kernel_has_a_byte_model():
     import bench
     from densesurfelmapping_b200 import capi
     P, S = 1226 * 370, 7038
-    scheduled = ["seed_init", "slic_assign_first", "slic_assign", "slic_gather_depths", "slic_newton", "pixel_normals",
-                 "plane_gather_points", "plane_gauss_newton", "surfel_fuse", "surfel_init"]
     names = capi.kernel_names()
-    for k in scheduled:
-        assert k in names, k
-        assert bench.kernel_alg_bytes(k, P, S, 6000, 2600) > 0, k
+    assert len(names) == capi.NUM_KERNELS
+    for k in names:
+        if k != "repack":  # input staging of the host-buffer entry points, not part of the resident step
+            assert bench.kernel_alg_bytes(k, P, S, 6000, 2600) > 0, k
     # compulsory bytes of the whole path per frame
     assert abs((9 * P + 60 * S) - 4_504_860) < 10
 

@@ -101,8 +101,6 @@ def test_resident_helper_compiles_and_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("DSM_TEST_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: set DSM_TEST_UNVERIFIED=1 to run")
 def test_resident_helper_flow_matches_oracle(tmp_path):
     import pyoracle
     from test_gpu_resident import match_as_sets

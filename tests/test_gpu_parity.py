@@ -55,8 +55,6 @@ def test_stage_by_stage_vga(capi):
     ctx.batch_upload([0], gray[None], depth[None], pose[None], np.zeros(0, SURFEL_DTYPE), [0, 0])
     # (kernels to run, oracle iterations, last-with-update); tile schedule: seed_init, then (assign, gather, newton) x 3
     stages = [(2, 1, False), (4, 1, True), (5, 2, False), (7, 2, True), (8, 3, False), (10, 3, True)]
-    if int(os.environ.get("DSM_EXPERIMENTAL_VARIANTS", "0"), 0) & 256:  # round-1 schedule: assign, relax, gather, newton
-        stages = [(2, 1, False), (4, 1, True), (6, 2, False), (8, 2, True), (10, 3, False), (12, 3, True)]
     for nk, iters, upd in stages:
         ctx.debug_stop_after(nk)
         ctx.batch_run()
@@ -280,4 +278,34 @@ def test_random_small_images(capi):
         assert nbad == 0, f"image {seed}: {nbad} label mismatches"
         check_seeds(ctx.seeds(), orc.seeds())
         check_surfels(ng, no, f"image {seed} new")
+    ctx.close()
+
+
+def test_rgbd_constant_set_hd(capi):
+    """BASELINE configs[4] flavour: 1280x720 with the reference's second constant set (fusion_functions.h:17-21,
+    selected at run time with dsm_set_constants) against the reference source compiled with those #defines."""
+    import pyoracle
+    cam = synth.Camera(1280, 720, 720.0, 720.0, 639.5, 359.5, 0.3, 8.0)
+    have_ref = os.path.exists(os.path.join(pyoracle.REFDIR, "libdsm_ref_serial_rgbd.so"))
+    orc = pyoracle.RefSerialRGBD(cam) if have_ref else pyoracle.Restatement(cam, pyoracle.CONSTANTS_RGBD)
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=1 << 17)
+    ctx.set_constants(capi.CONSTANTS_RGBD)
+    pool_o = pool_g = np.zeros(0, SURFEL_DTYPE)
+    for t in range(2):
+        pose = synth.pose_stream(t)
+        gray, depth = synth.make_frame(cam, 700 + t, pose)
+        depth = (depth * np.float32(0.2)).astype(np.float32)  # indoor range: the RGBD set assumes metres of a room
+        lo, no = orc.fuse(t, gray, depth, pose, pool_o)
+        lg, ng = ctx.fuse_frame(t, gray, depth, pose, pool_g)
+        assert (ctx.labels() == orc.labels()).all()
+        check_seeds(ctx.seeds(), orc.seeds())
+        check_surfels(lg, lo, "local")
+        check_surfels(ng, no, "new")
+        assert ctx.invariant_violations() == 0
+        pool_o = compact_like_caller(lo, no)
+        pool_g = compact_like_caller(lg, ng)
+    ctx.set_constants(capi.CONSTANTS_DRIVE)  # and back: the drive set must give something else on this data
+    _, nd = ctx.fuse_frame(5, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+    _, nr = orc.fuse(5, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+    assert len(nd) != len(nr) or not np.array_equal(nd["pz"], nr["pz"])
     ctx.close()

@@ -125,8 +125,6 @@ def test_pool_retire_and_append_move_add_surfels():
     ctx.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DSM_TEST_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: set DSM_TEST_UNVERIFIED=1 to run")
 @pytest.mark.parametrize("chunk", [1, 3, 4])
 def test_stream_chunks_equal_frame_by_frame(chunk):
     """dsm_fuse_stream_resident (n frames per call) must leave exactly the pool that n calls of
@@ -164,8 +162,6 @@ def test_stream_chunks_equal_frame_by_frame(chunk):
     b.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DSM_TEST_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: set DSM_TEST_UNVERIFIED=1 to run")
 def test_inactive_store_round_trip():
     """Device-resident attached_surfels: retire two keyframes into the store, warp one of them, publish the inactive
     cloud, bring one back -- against the restated (and reference-pinned, tests/test_refmap.py) SurfelMap members."""

@@ -108,6 +108,32 @@ def test_restatement_equals_reference_serial_small():
         pool = np.concatenate([lr[lr["update_times"] > 0] if len(lr) else lr, nr])
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(pyoracle.REFDIR, "libdsm_ref_serial_rgbd.so")), reason="oracle/_ref/libdsm_ref_serial_rgbd.so not built")
+def test_restatement_equals_reference_serial_with_the_rgbd_constant_set():
+    """The reference's second constant set (fusion_functions.h:17-21, HUBER_RANGE 0.05 ...): the restatement with
+    run-time constants against the reference source compiled with those #defines, on an indoor-range stream; and the
+    two sets must really differ on that data (otherwise the test would not notice a dropped constant)."""
+    cam = synth.Camera(324, 242, 260.0, 260.0, 161.5, 120.5, 0.3, 5.0)
+    rs, ro = pyoracle.RefSerialRGBD(cam), pyoracle.Restatement(cam, pyoracle.CONSTANTS_RGBD)
+    rd = pyoracle.Restatement(cam)  # drive set on the same frames
+    pool, pool_d, differs = np.zeros(0, SURFEL_DTYPE), np.zeros(0, SURFEL_DTYPE), False
+    for t in range(3):
+        pose = synth.pose_stream(t)
+        g, d = synth.make_frame(cam, 60 + t, pose)
+        d = (d * np.float32(0.15)).astype(np.float32)  # metres of an indoor scene
+        lr, nr = rs.fuse(t, g, d, pose, pool)
+        lo, no = ro.fuse(t, g, d, pose, pool)
+        assert (rs.labels() == ro.labels()).all()
+        assert_records_equal(ro.seeds(), rs.seeds(), "seeds")
+        assert_records_equal(lo, lr, "local")
+        assert_records_equal(no, nr, "new")
+        ld, nd = rd.fuse(t, g, d, pose, pool_d)
+        differs |= (rd.labels() != ro.labels()).any() or len(nd) != len(no) or canon(nd) != canon(no)
+        pool = np.concatenate([lr[lr["update_times"] > 0] if len(lr) else lr, nr])
+        pool_d = np.concatenate([ld[ld["update_times"] > 0] if len(ld) else ld, nd])
+    assert differs
+
+
 def test_every_seed_keeps_its_centre_pixel():
     """Why the update_seeds early `return` (fusion_functions.cpp:516-517) can never fire for a valid
     shape: the pixel at (8sx+4, 8sy+4) has exactly one candidate seed, so every seed always owns it."""

@@ -10,7 +10,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python tools/prof_step.py 32 3 > "$out/launches.log" 2>&1
 # full set: skip the setup batch (pool seeding: one schedule) and the first step, capture the second step's kernels
 nk=${2:-12}
-timeout 600 ncu --set full --clock-control none --import-source on --launch-skip $((2 * nk + 2)) --launch-count $nk -f -o "$out/full" \
+timeout 600 ncu --set full --clock-control none --import-source on --launch-skip ${3:-29} --launch-count $nk -f -o "$out/full" \
     python tools/prof_step.py 32 3 > "$out/full.log" 2>&1
 ls -la "$out"
 tail -3 "$out/full.log"
