@@ -728,7 +728,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "kernel_ms_per_step": kernel_ms, "kernel_ms_per_launch": per_launch_ms,
             "parity": parity,
         }
-        if world == 1:
+        if world == 1 and os.environ.get("DSM_BENCH_NO_EXTRAS") != "1":
             line["extras"] = run_extras(cam, local_rank, stream)
         if world == 1 and not args.no_cpu:
             pools_cpu = [pool_np[offsets[b]:offsets[b + 1]] for b in range(B)]

@@ -332,7 +332,7 @@ class Context:
         self._ck(fn(self.h, int(min_update_times), _ptr(out), cap, ctypes.byref(n)))
         return out[:min(n.value, cap)].copy()
 
-    # ---- inactive store (experimental) ----
+    # ---- inactive store ----
     def inactive_reserve(self, n):
         self._ck(self.lib.dsm_inactive_reserve(self.h, int(n)))
 

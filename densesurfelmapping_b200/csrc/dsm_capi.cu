@@ -73,6 +73,8 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(d.invd);
     cudaFree(d.seed_hl);
     cudaFree(d.done);
+    cudaFree(d.hardq);
+    cudaFree(d.nhard);
     cudaFree(d.hrec);
     cudaFree(d.tstable);
     cudaFree(d.usum);
@@ -267,6 +269,8 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.invd, B * px + 64);
     ALLOC(d.seed_hl, (size_t)B * S);
     ALLOC(d.done, (size_t)B);
+    ALLOC(d.hardq, (size_t)B * S);
+    ALLOC(d.nhard, (size_t)B);
     ALLOC(d.hrec, (size_t)B * S * 24);
     ALLOC(d.tstable, (size_t)B * S);
     ALLOC(d.usum, (size_t)B * S);
@@ -642,8 +646,21 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
     if (!ctx) return DSM_E_INVALID;
     if (!ctx->uploaded) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    int rc = enqueue_schedule(ctx, 0, ctx->nb, ctx->d.max_pool_per_frame, ctx->stream);
-    if (rc != DSM_OK) return rc;
+    // DSM_RUN_CHUNK=n (experiment): run the batch n frames at a time through the whole schedule, so that a sub-batch's
+    // images, labels and lists stay L2-resident between its kernels (DRAM traffic) at the price of more, smaller launches
+    int chunk = ctx->nb;
+    if (const char *e = getenv("DSM_RUN_CHUNK"))
+    {
+        const int v = atoi(e);
+        if (v >= 1 && v < ctx->nb) chunk = v;
+    }
+    if (ctx->stop_after > 0) chunk = ctx->nb; // the debug kernel budget counts launches of the whole batch
+    for (int f0 = 0; f0 < ctx->nb; f0 += chunk)
+    {
+        const int nf = ctx->nb - f0 < chunk ? ctx->nb - f0 : chunk;
+        int rc = enqueue_schedule(ctx, f0, nf, ctx->d.max_pool_per_frame, ctx->stream);
+        if (rc != DSM_OK) return rc;
+    }
     ctx->ran = true;
     return DSM_OK;
 }

@@ -78,6 +78,8 @@ struct DsmDev
     // tile path (dsm_tile.cu)
     float *invd;        // [B][H][Wp] (float)(1.0 / (double)depth) for depth > 0.01, else 0 (:404-405), written by the first assign pass
     float2 *seed_hl;    // [B][S] 1.0 / (double)mean_depth split into two floats (hi, lo) for the filtered assign pass
+    int32_t *hardq;     // [B][S] seeds whose Huber-Newton needs the entry-by-entry classification (k_newton2 -> k_newton_hard)
+    int32_t *nhard;     // [B] queue lengths
     int32_t *done;      // [B] frame-completion tickets of the assign pass (the last CTA of a frame runs the stable relaxation)
     double *hrec;       // [B][24][S] plane fit, first residual pass: H = sum 2 q q^T (9), the same over out-of-range points (10), their clamped gradient (4), packed (margin, qmax2)
 };

@@ -321,9 +321,12 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
     // frame-completion ticket: the CTA that takes the last ticket of frame b sees every other CTA's labels, list
     // entries and time stamps (release: fence before the ticket; acquire: fence after it) and resolves the frame
     const int tid = threadIdx.y * 64 + threadIdx.x;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&d.done[b], 1) == (int)(gridDim.x * gridDim.y) - 1) ? 1 : 0;
+    __syncthreads(); // the CTA's writes happen-before thread 0's fence (fences are cumulative): one fence per CTA, as in a grid barrier
+    if (tid == 0)
+    {
+        __threadfence();
+        s_last = (atomicAdd(&d.done[b], 1) == (int)(gridDim.x * gridDim.y) - 1) ? 1 : 0;
+    }
     __syncthreads();
     if (s_last)
     {
@@ -392,6 +395,7 @@ __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDe
         tma_load_3d(smem_u32(smem + GAT_SMEM_DEP), &mp.dep, X0, Y0, b, bar);
         tma_load_3d(smem_u32(smem + GAT_SMEM_GRY), &mp.gry, X0 - DSM_TILE_GX, Y0, b, bar);
     }
+    if (threadIdx.x == 1 && blockIdx.x == 0 && blockIdx.y == 0) d.nhard[b] = 0; // this pass's queue of hard Newton seeds
     const int W = d.W, H = d.H;
     const size_t so = (size_t)b * d.S;
     const int half = lane >> 4, r = lane & 15;
@@ -501,17 +505,18 @@ __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDe
     }
 }
 
-#define NW_CAP 11776 // floats of list staging per 128-seed CTA (46 KB, static shared memory limit 48 KB): 92 entries per seed on average, 225 possible
-__global__ void __launch_bounds__(128, 4) k_newton2(const __grid_constant__ DsmDev d)
+#define NW_T 64       // seeds (threads) per CTA of the two Newton kernels
+#define NW_CAP 5632   // floats of list staging per CTA (22 KB): 88 entries per seed on average, 225 possible; 8 CTAs per SM
+__global__ void __launch_bounds__(NW_T, 8) k_newton2(const __grid_constant__ DsmDev d)
 {
-    // The lists of the CTA's 128 seeds are contiguous runs in global memory; the CTA copies them into shared memory with
+    // The lists of the CTA's NW_T seeds are contiguous runs in global memory; the CTA copies them into shared memory with
     // coalesced 16-byte asynchronous copies (cp.async; one list after the other, lengths rounded up to 4) and every thread then walks its own
-    // list there up to six times.  Lists that do not fit (rare: NW_CAP covers 92 entries per seed) stay in global memory.
+    // list there up to six times.  Lists that do not fit (rare: NW_CAP covers 88 entries per seed) stay in global memory.
     __shared__ __align__(16) float buf[NW_CAP];
-    __shared__ int s_off[128], s_len[128], s_wsum[4];
+    __shared__ int s_off[NW_T], s_len[NW_T], s_wsum[NW_T / 32];
     const int b = d.frame0 + blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int s = blockIdx.x * 128 + tid;
+    const int s = blockIdx.x * NW_T + tid;
     const size_t so = (size_t)b * d.S;
     const bool act = s < d.S && d.tstable[so + s] != DSM_STABLE; // stable seeds are untouched by update_seeds (:478-479)
     const int nd = act ? d.und[so + s] : 0;
@@ -528,128 +533,205 @@ __global__ void __launch_bounds__(128, 4) k_newton2(const __grid_constant__ DsmD
         s_len[tid] = nd;
     }
     __syncthreads();
-    for (int q = warp; q < 128; q += 4)
+    for (int q = warp; q < NW_T; q += NW_T / 32)
     {
         const int off = s_off[q], len = s_len[q];
         if (off < 0 || len == 0) continue; // warp-uniform
-        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + blockIdx.x * 128 + q) * DL_STRIDE);
+        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + blockIdx.x * NW_T + q) * DL_STRIDE);
         float4 *dst = reinterpret_cast<float4 *>(buf + off);
         for (int j4 = lane; 4 * j4 < len; j4 += 32) __pipeline_memcpy_async(dst + j4, src + j4, 16); // LDGSTS: no register staging, no wait
     }
     __pipeline_commit();
-    __pipeline_wait_prior(0); // every copy of the CTA was in flight at once: one memory round trip for all 128 lists
+    __pipeline_wait_prior(0); // every copy of the CTA was in flight at once: one memory round trip for all the lists
+    __syncthreads();
+    // Every seed runs its mean pass and its Newton passes as long as every entry is inside the Huber range (a pure
+    // dependent chain).  A seed that meets an out-of-range entry is appended to the frame's queue of hard seeds with its
+    // state; k_newton_hard continues those, one thread each at full occupancy, so that the entry-by-entry
+    // classification loop is never executed by a warp in which one lane needs it and 31 wait.
+    if (act)
+    {
+        const int4 su = d.usum[so + s];
+        const int n = su.x;
+        if (n == 0)
+        { // unreachable for supported shapes (every seed keeps its centre pixel); recorded, never silently ignored
+            atomicAdd(&d.errflag[b], 1);
+            d.tstable[so + s] = -1;
+        }
+        else
+        {
+            const float fn = (float)n; // sums below are < 2^24 so the reference's float accumulation is exact
+            const float mi = (float)su.w / fn;
+            const float mx = (float)su.y / fn;
+            const float my = (float)su.z / fn;
+            const float4 pre = d.seed[so + s];
+            // ::fabs(double): float differences, summed in double, rounded once (:527)
+            const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
+            const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
+            float md = 0.0f;
+            bool queued = false;
+            if (nd > 0)
+            {
+                const float *dl = s_off[tid] >= 0 ? buf + s_off[tid] : d.dlist + (so + s) * DL_STRIDE; // generic: shared or global
+                const float4 *dl4 = reinterpret_cast<const float4 *>(dl);
+                float sum_d = 0.0f, zmn = __int_as_float(0x7f800000), zmx = 0.f;
+                {
+                    int k = 0;
+                    for (; k + 8 <= nd; k += 8)
+                    {
+                        const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
+                        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sum_d += v[j]; // raster order (:511)
+                        zmn = fminf(zmn, fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7]))));
+                        zmx = fmaxf(zmx, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+                    }
+                    for (; k < nd; k++)
+                    {
+                        const float v = dl[k];
+                        sum_d += v;
+                        zmn = fminf(zmn, v);
+                        zmx = fmaxf(zmx, v);
+                    }
+                }
+                md = sum_d / (float)nd;
+                for (int it = 0; it < 5; it++)
+                { // damped Huber-Newton (:534-554)
+                    // residual = fl(md - z) is monotone in z: the list's extremes decide for ALL entries whether they are inside
+                    // the Huber range ((double)r < HUBER_RANGE && (double)r > -HUBER_RANGE, :540)
+                    if (!((md - zmn) < d.huber_hi && (md - zmx) > -d.huber_hi))
+                    {
+                        queued = true;
+                        d.pfsum[(so + s) * 2] = make_float4(md, __int_as_float(it), zmn, zmx); // the plane-fit scratch is free during the clustering
+                        break;
+                    }
+                    // every entry in range: sum_a += 2 * residual (2 r is exact, one rounding per add = fmaf(2, r, sum_a)),
+                    // sum_b = nd exact additions of 2
+                    float sa = 0.0f;
+                    int k = 0;
+                    for (; k + 8 <= nd; k += 8)
+                    {
+                        const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
+                        sa = fmaf(2.0f, md - a.x, sa), sa = fmaf(2.0f, md - a.y, sa), sa = fmaf(2.0f, md - a.z, sa), sa = fmaf(2.0f, md - a.w, sa);
+                        sa = fmaf(2.0f, md - c.x, sa), sa = fmaf(2.0f, md - c.y, sa), sa = fmaf(2.0f, md - c.z, sa), sa = fmaf(2.0f, md - c.w, sa);
+                    }
+                    for (; k < nd; k++) sa = fmaf(2.0f, md - dl[k], sa);
+                    const float delta = (float)((double)(-sa) / ((double)(float)(2 * nd) + 10.0));
+                    md = md + delta;
+                    if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
+                }
+            }
+            if (queued)
+            {
+                d.pfsum[(so + s) * 2 + 1] = make_float4(mx, my, mi, newstable ? 1.f : 0.f);
+                d.hardq[so + atomicAdd(&d.nhard[b], 1)] = s;
+            }
+            else
+            {
+                d.seed[so + s] = make_float4(mx, my, mi, md);
+                d.seed_hl[so + s] = split_inverse(md);
+                d.inv_md[so + s] = 1.0 / (double)md; // exact-path operand of the assign pass, only consumed when md > 0 (:378)
+                d.tstable[so + s] = newstable ? DSM_STABLE : -1;
+            }
+        }
+    }
+}
+
+// K2c k_newton_hard (thread per queued seed): the Newton passes of the seeds that have entries outside the Huber range
+// (:540-547), continued from the state k_newton2 left.  Eight entries per step: their residuals and in-range flags are
+// independent and computed first; what remains serial is the reference's running sum -- fmaf(2, r, sum_a) for an entry
+// in range, (float)((double)sum_a + -+HUBER_RANGE) for one outside (:547).
+__global__ void __launch_bounds__(NW_T, 8) k_newton_hard(const __grid_constant__ DsmDev d)
+{
+    __shared__ __align__(16) float buf[NW_CAP];
+    __shared__ int s_off[NW_T], s_len[NW_T], s_seed[NW_T], s_wsum[NW_T / 32];
+    const int b = d.frame0 + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nq = d.nhard[b];
+    if (blockIdx.x * NW_T >= nq) return; // whole CTA beyond the queue
+    const int q = blockIdx.x * NW_T + tid;
+    const size_t so = (size_t)b * d.S;
+    const bool act = q < nq;
+    const int s = act ? d.hardq[so + q] : 0;
+    const int nd = act ? d.und[so + s] : 0;
+    { // stage the CTA's lists into shared memory exactly like k_newton2 (coalesced cp.async, all in flight at once)
+        const int len4 = (nd + 3) & ~3;
+        int wtot;
+        const int wex = warp_excl_scan(len4, lane, wtot);
+        if (lane == 31) s_wsum[warp] = wtot;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; w++) base += s_wsum[w];
+        const int off = base + wex;
+        s_off[tid] = (off + len4 <= NW_CAP) ? off : -1;
+        s_len[tid] = nd;
+        s_seed[tid] = s;
+    }
+    __syncthreads();
+    for (int q2 = warp; q2 < NW_T; q2 += NW_T / 32)
+    {
+        const int off = s_off[q2], len = s_len[q2];
+        if (off < 0 || len == 0) continue; // warp-uniform
+        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + s_seed[q2]) * DL_STRIDE);
+        float4 *dst = reinterpret_cast<float4 *>(buf + off);
+        for (int j4 = lane; 4 * j4 < len; j4 += 32) __pipeline_memcpy_async(dst + j4, src + j4, 16);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
     __syncthreads();
     if (!act) return;
-    const int4 su = d.usum[so + s];
-    const int n = su.x;
-    if (n == 0)
-    { // unreachable for supported shapes (every seed keeps its centre pixel); recorded, never silently ignored
-        atomicAdd(&d.errflag[b], 1);
-        d.tstable[so + s] = -1;
-        return;
-    }
-    const float fn = (float)n; // sums below are < 2^24 so the reference's float accumulation is exact
-    const float mi = (float)su.w / fn;
-    const float mx = (float)su.y / fn;
-    const float my = (float)su.z / fn;
-    const float4 pre = d.seed[so + s];
-    // ::fabs(double): float differences, summed in double, rounded once (:527)
-    const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
-    const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
-    float md = 0.0f;
-    if (nd > 0)
+    const float4 st = d.pfsum[(so + s) * 2], mn = d.pfsum[(so + s) * 2 + 1];
+    const float *dl = s_off[tid] >= 0 ? buf + s_off[tid] : d.dlist + (so + s) * DL_STRIDE; // generic: shared or global
+    const float4 *dl4 = reinterpret_cast<const float4 *>(dl);
+    float md = st.x;
+    const float zmn = st.z, zmx = st.w;
+    const double hp = d.huber, hm = -1 * d.huber;
+    for (int it = __float_as_int(st.y); it < 5; it++)
     {
-        const float *dl = s_off[tid] >= 0 ? buf + s_off[tid] : d.dlist + (so + s) * DL_STRIDE; // generic: shared or global
-        const float4 *dl4 = reinterpret_cast<const float4 *>(dl);
-        float sum_d = 0.0f, zmn = __int_as_float(0x7f800000), zmx = 0.f;
-        {
+        float sa = 0.0f, sb = 0.0f;
+        if ((md - zmn) < d.huber_hi && (md - zmx) > -d.huber_hi)
+        { // back inside the range with every entry: the pure chain
             int k = 0;
             for (; k + 8 <= nd; k += 8)
             {
                 const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
-                const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                sa = fmaf(2.0f, md - a.x, sa), sa = fmaf(2.0f, md - a.y, sa), sa = fmaf(2.0f, md - a.z, sa), sa = fmaf(2.0f, md - a.w, sa);
+                sa = fmaf(2.0f, md - c.x, sa), sa = fmaf(2.0f, md - c.y, sa), sa = fmaf(2.0f, md - c.z, sa), sa = fmaf(2.0f, md - c.w, sa);
+            }
+            for (; k < nd; k++) sa = fmaf(2.0f, md - dl[k], sa);
+            sb = (float)(2 * nd);
+        }
+        else
+        {
+            int k = 0, nin = 0;
+            for (; k + 8 <= nd; k += 8)
+            {
+                const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
+                const float rr[8] = {md - a.x, md - a.y, md - a.z, md - a.w, md - c.x, md - c.y, md - c.z, md - c.w};
+                unsigned in = 0;
 #pragma unroll
-                for (int j = 0; j < 8; j++) sum_d += v[j]; // raster order (:511)
-                zmn = fminf(zmn, fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7]))));
-                zmx = fmaxf(zmx, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+                for (int j = 0; j < 8; j++) in |= ((rr[j] < d.huber_hi && rr[j] > -d.huber_hi) ? 1u : 0u) << j;
+                nin += __popc(in);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    sa = ((in >> j) & 1u) ? fmaf(2.0f, rr[j], sa) : (float)((double)sa + (rr[j] > 0 ? hp : hm));
             }
             for (; k < nd; k++)
             {
-                const float v = dl[k];
-                sum_d += v;
-                zmn = fminf(zmn, v);
-                zmx = fmaxf(zmx, v);
+                const float rr = md - dl[k];
+                const bool in = rr < d.huber_hi && rr > -d.huber_hi;
+                nin += in ? 1 : 0;
+                sa = in ? fmaf(2.0f, rr, sa) : (float)((double)sa + (rr > 0 ? hp : hm));
             }
+            sb = (float)(2 * nin); // nin exact additions of 2
         }
-        md = sum_d / (float)nd;
-        for (int it = 0; it < 5; it++)
-        { // damped Huber-Newton (:534-554)
-            float sa = 0.0f, sb = 0.0f;
-            if ((md - zmn) < d.huber_hi && (md - zmx) > -d.huber_hi)
-            { // every entry inside the Huber range ((double)r < 0.4 && (double)r > -0.4, :540): pure chain, sum_b = nd exact +2 steps
-                int k = 0;
-                for (; k + 8 <= nd; k += 8)
-                {
-                    const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
-                    sa = fmaf(2.0f, md - a.x, sa), sa = fmaf(2.0f, md - a.y, sa), sa = fmaf(2.0f, md - a.z, sa), sa = fmaf(2.0f, md - a.w, sa);
-                    sa = fmaf(2.0f, md - c.x, sa), sa = fmaf(2.0f, md - c.y, sa), sa = fmaf(2.0f, md - c.z, sa), sa = fmaf(2.0f, md - c.w, sa);
-                }
-                for (; k < nd; k++) sa = fmaf(2.0f, md - dl[k], sa);
-                sb = (float)(2 * nd);
-            }
-            else
-            { // some entry is outside the range: 8 entries per step; a step whose 8 residuals are all inside is the same
-              // chain plus eight exact +2 steps of sum_b, only the (few) other steps classify entry by entry (:540-547)
-                int k = 0;
-                for (; k + 8 <= nd; k += 8)
-                {
-                    const float4 a = dl4[k >> 2], c = dl4[(k >> 2) + 1];
-                    const float rr[8] = {md - a.x, md - a.y, md - a.z, md - a.w, md - c.x, md - c.y, md - c.z, md - c.w};
-                    float rmx = rr[0], rmn = rr[0];
-#pragma unroll
-                    for (int j = 1; j < 8; j++) rmx = fmaxf(rmx, rr[j]), rmn = fminf(rmn, rr[j]);
-                    if (rmx < d.huber_hi && rmn > -d.huber_hi)
-                    {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) sa = fmaf(2.0f, rr[j], sa);
-                        sb += 16;
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int j = 0; j < 8; j++)
-                        {
-                            if (rr[j] < d.huber_hi && rr[j] > -d.huber_hi)
-                            {
-                                sa = fmaf(2.0f, rr[j], sa);
-                                sb += 2;
-                            }
-                            else
-                                sa = (float)((double)sa + (rr[j] > 0 ? d.huber : -1 * d.huber));
-                        }
-                    }
-                }
-                for (; k < nd; k++)
-                {
-                    const float rr = md - dl[k];
-                    if (rr < d.huber_hi && rr > -d.huber_hi)
-                    {
-                        sa = fmaf(2.0f, rr, sa);
-                        sb += 2;
-                    }
-                    else
-                        sa = (float)((double)sa + (rr > 0 ? d.huber : -1 * d.huber));
-                }
-            }
-            const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
-            md = md + delta;
-            if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
-        }
+        const float delta = (float)((double)(-sa) / ((double)sb + 10.0));
+        md = md + delta;
+        if (delta < F_0p01_HI && delta > -F_0p01_HI) break; // |delta| < 0.01 in double (:552)
     }
-    d.seed[so + s] = make_float4(mx, my, mi, md);
+    d.seed[so + s] = make_float4(mn.x, mn.y, mn.z, md);
     d.seed_hl[so + s] = split_inverse(md);
-    d.inv_md[so + s] = 1.0 / (double)md; // exact-path operand of the assign pass, only consumed when md > 0 (:378)
-    d.tstable[so + s] = newstable ? DSM_STABLE : -1;
+    d.inv_md[so + s] = 1.0 / (double)md;
+    d.tstable[so + s] = mn.w != 0.f ? DSM_STABLE : -1;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1007,49 +1089,166 @@ __device__ __forceinline__ void solve4_spd_t(const double *h, double lambda, con
     u[0] = y0 * i0 - l10 * u[1] - l20 * u[2] - l30 * u[3];
 }
 
-__global__ void __launch_bounds__(128, 5) k_gn_solve(const __grid_constant__ DsmDev d)
+// centre of the superpixel projected onto the fitted plane, view angle, size (:872-912): the seed's final record
+__device__ __forceinline__ void finish_plane(const DsmDev &d, size_t o, const float4 &sd, const float4 &P0, const float4 &P1, float nx, float ny,
+                                             float nz, float nb)
 {
-    const int b = d.frame0 + blockIdx.y;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= d.S) return;
-    const size_t so = (size_t)b * d.S;
-    const float4 sd = d.seed[so + s];
-    const float4 P0 = d.pfsum[(so + s) * 2], P1 = d.pfsum[(so + s) * 2 + 1];
-    const int n = __float_as_int(P1.w);
-    // default record: plane fit rejected -> zero normal / position / view_cos / size (H6-i), Huber mean depth kept
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 r1 = make_float4(0.f, 0.f, 0.f, sd.w);
-    float4 r2 = make_float4(0.f, sd.z, sd.x, sd.y);
-    if (n > 0)
+    nb = nb - (nx * P1.x + ny * P1.y + nz * P1.z);
+    const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
+    nx /= nl;
+    ny /= nl;
+    nz /= nl;
+    nb /= nl;
+    const float axf = (sd.x - d.cx) / d.fx * sd.w;
+    const float ayf = (sd.y - d.cy) / d.fy * sd.w;
+    double ax = (double)axf, ay = (double)ayf, az = (double)sd.w;
+    const float kk = (float)(-1 * (ax * (double)nx + ay * (double)ny + az * (double)nz) - (double)nb);
+    ax += (double)(kk * nx);
+    ay += (double)(kk * ny);
+    az += (double)(kk * nz);
+    const float mean_depth = (float)az;
+    float view_cos = (float)(-1.0 * ((double)nx * ax + (double)ny * ay + (double)nz * az) / sqrt(ax * ax + ay * ay + az * az));
+    if (view_cos < 0)
     {
-        const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
-        float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
-        const float mxs = P1.x, mys = P1.y, mzs = P1.z;
-        const double *hr = d.hrec + (size_t)b * HREC * d.S + s; // [b][field][seed]
-        const size_t hs = (size_t)d.S;
-        // hh0 = H over the in-range points = H_all - ho; jo = clamped gradient of the out-of-range points.  H_all itself is
-        // only needed again when the points have to be classified anew (rare), so it is not kept in registers.
-        double hh0[10], jo[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 9; i++) hh0[i] = hr[i * hs];
-        hh0[9] = 2.0 * (double)n;
-        if (hr[18 * hs] != 0.0)
-        { // the first pass found points outside the Huber range
-#pragma unroll
-            for (int i = 0; i < 10; i++) hh0[i] -= hr[(9 + i) * hs];
-#pragma unroll
-            for (int i = 0; i < 4; i++) jo[i] = hr[(19 + i) * hs];
+        view_cos = -view_cos;
+        nx = -nx;
+        ny = -ny;
+        nz = -nz;
+    }
+    float4 *pl = d.plane + o * 3;
+    pl[0] = make_float4(nx, ny, nz, view_cos);
+    pl[1] = make_float4((float)ax, (float)ay, (float)az, mean_depth);
+    pl[2] = make_float4(sqrtf(P0.w), sd.z, sd.x, sd.y);
+}
+
+// one damped Gauss-Newton step (:172-181) from hh0 = H over the in-range points and jo = clamped gradient of the others;
+// returns the bound on how far the step can move any residual: |q|max |dn| + |db| (+ rounding slack)
+__device__ __forceinline__ float gn_step(const double *hh0, const double *jo, float qmax, float &nx, float &ny, float &nz, float &nb)
+{
+    double jj[4];
+    const double tx = (double)nx, ty = (double)ny, tz = (double)nz, tb = (double)nb;
+    jj[0] = ((hh0[0] * tx + hh0[1] * ty) + hh0[2] * tz) + hh0[3] * tb + jo[0];
+    jj[1] = ((hh0[1] * tx + hh0[4] * ty) + hh0[5] * tz) + hh0[6] * tb + jo[1];
+    jj[2] = ((hh0[2] * tx + hh0[5] * ty) + hh0[7] * tz) + hh0[8] * tb + jo[2];
+    jj[3] = ((hh0[3] * tx + hh0[6] * ty) + hh0[8] * tz) + hh0[9] * tb + jo[3];
+    double u[4];
+    solve4_spd_t(hh0, 5.0, jj, u); // LM damping: + 5 on the diagonal (:172-175)
+    const float ox = nx, oy = ny, oz = nz, ob = nb;
+    nx = (float)((double)nx - u[0]);
+    ny = (float)((double)ny - u[1]);
+    nz = (float)((double)nz - u[2]);
+    nb = (float)((double)nb - u[3]);
+    const float dx = nx - ox, dy = ny - oy, dz = nz - oz;
+    return qmax * sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + fabsf(nb - ob) + 1e-4f;
+}
+
+#define GS_CAP 9216 // floats of point staging per 128-seed CTA (36 KB): three planes of the queued seeds' centred points
+__global__ void __launch_bounds__(128, 4) k_gn_solve(const __grid_constant__ DsmDev d)
+{
+    // Phase A: every seed iterates from the sums of k_plane_gather for as long as no residual can have crossed the Huber
+    // boundary -- most seeds finish all five steps here without ever touching their points.  A seed that has to classify
+    // its points again is queued.  Phase B: the queued seeds' point lists (contiguous runs in global memory) are staged
+    // into shared memory with cp.async and the seeds continue, packed densely into the CTA's first warps.
+    __shared__ __align__(16) float pts[GS_CAP];
+    __shared__ float4 s_theta[128]; // queued seed: plane parameters so far
+    __shared__ int s_queue[128], s_gn[128], s_poff[128], s_nq, s_used;
+    const int b = d.frame0 + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x * 128 + tid;
+    const size_t so = (size_t)b * d.S;
+    const size_t hs = (size_t)d.S;
+    if (tid == 0) s_nq = 0, s_used = 0;
+    __syncthreads();
+    if (s < d.S)
+    {
+        const float4 sd = d.seed[so + s];
+        const float4 P0 = d.pfsum[(so + s) * 2], P1 = d.pfsum[(so + s) * 2 + 1];
+        const int n = __float_as_int(P1.w);
+        if (n <= 0)
+        { // plane fit rejected -> zero normal / position / view_cos / size (H6-i), Huber mean depth kept
+            float4 *pl = d.plane + (so + s) * 3;
+            pl[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pl[1] = make_float4(0.f, 0.f, 0.f, sd.w);
+            pl[2] = make_float4(0.f, sd.z, sd.x, sd.y);
         }
-        const double pk = hr[23 * hs];
-        float margin = __int_as_float(__double2loint(pk));
-        const float qmax = sqrtf(__int_as_float(__double2hiint(pk)));
-        float moved = 0.f; // bound on the change of any residual since the classification behind hh0 / jo was made
-        for (int gn = 0; gn < 5; gn++)
+        else
         {
-            if (gn > 0 && !(moved + 2e-3f < margin)) // NaN-safe: a NaN margin keeps evaluating
-            { // some point may have crossed the Huber boundary: classify again (:131-171)
-                const float4 *qx = reinterpret_cast<const float4 *>(d.qlist + (so + s) * (3 * PL_STRIDE));
-                const float4 *qy = qx + PL_STRIDE / 4, *qz = qy + PL_STRIDE / 4;
+            const float len0 = sqrtf(P0.x * P0.x + P0.y * P0.y + P0.z * P0.z);
+            float nx = P0.x / len0, ny = P0.y / len0, nz = P0.z / len0, nb = 0.f; // len0 == 0 -> NaN, propagated (H6-iii)
+            const double *hr = d.hrec + (size_t)b * HREC * d.S + s; // [b][field][seed]
+            // hh0 = H over the in-range points = H_all - ho; jo = clamped gradient of the out-of-range points
+            double hh0[10], jo[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 9; i++) hh0[i] = hr[i * hs];
+            hh0[9] = 2.0 * (double)n;
+            if (hr[18 * hs] != 0.0)
+            { // the first pass found points outside the Huber range
+#pragma unroll
+                for (int i = 0; i < 10; i++) hh0[i] -= hr[(9 + i) * hs];
+#pragma unroll
+                for (int i = 0; i < 4; i++) jo[i] = hr[(19 + i) * hs];
+            }
+            const double pk = hr[23 * hs];
+            const float margin = __int_as_float(__double2loint(pk));
+            const float qmax = sqrtf(__int_as_float(__double2hiint(pk)));
+            float moved = 0.f; // bound on the change of any residual since the classification behind hh0 / jo was made
+            int gn = 0;
+            for (; gn < 5; gn++)
+            {
+                if (gn > 0 && !(moved + 2e-3f < margin)) break; // NaN-safe: a NaN margin queues the seed
+                moved += gn_step(hh0, jo, qmax, nx, ny, nz, nb);
+            }
+            if (gn == 5)
+                finish_plane(d, so + s, sd, P0, P1, nx, ny, nz, nb);
+            else
+            { // some point may have crossed the Huber boundary: continue in phase B
+                const int q = atomicAdd(&s_nq, 1);
+                const int len4 = (n + 3) & ~3;
+                const int off = atomicAdd(&s_used, 3 * len4);
+                s_queue[q] = tid;
+                s_gn[tid] = gn;
+                s_poff[tid] = (off + 3 * len4 <= GS_CAP) ? off : -1;
+                s_theta[tid] = make_float4(nx, ny, nz, nb);
+            }
+        }
+    }
+    __syncthreads();
+    const int nq = s_nq;
+    if (nq == 0) return;
+    for (int q = warp; q < nq; q += 4)
+    { // stage the three planes of a queued seed's centred points: coalesced 16-byte cp.async, all in flight at once
+        const int t2 = s_queue[q], off = s_poff[t2];
+        if (off < 0) continue; // does not fit: that seed reads global memory
+        const size_t o2 = so + blockIdx.x * 128 + t2;
+        const int n2 = __float_as_int(d.pfsum[o2 * 2 + 1].w), l4 = ((n2 + 3) & ~3) >> 2;
+        const float4 *src = reinterpret_cast<const float4 *>(d.qlist + o2 * (3 * PL_STRIDE));
+        float4 *dst = reinterpret_cast<float4 *>(pts + off);
+        for (int pln = 0; pln < 3; pln++)
+            for (int j4 = lane; j4 < l4; j4 += 32) __pipeline_memcpy_async(dst + pln * l4 + j4, src + pln * (PL_STRIDE / 4) + j4, 16);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    for (int q = tid; q < nq; q += 128)
+    {
+        const int t2 = s_queue[q];
+        const size_t o2 = so + blockIdx.x * 128 + t2;
+        const float4 sd = d.seed[o2];
+        const float4 P0 = d.pfsum[o2 * 2], P1 = d.pfsum[o2 * 2 + 1];
+        const int n = __float_as_int(P1.w), l4 = ((n + 3) & ~3) >> 2;
+        const double *hr = d.hrec + (size_t)b * HREC * d.S + (blockIdx.x * 128 + t2);
+        const float qmax = sqrtf(__int_as_float(__double2hiint(hr[23 * hs])));
+        const float4 th = s_theta[t2];
+        float nx = th.x, ny = th.y, nz = th.z, nb = th.w;
+        const int off = s_poff[t2];
+        const float4 *qx = off >= 0 ? reinterpret_cast<const float4 *>(pts + off) : reinterpret_cast<const float4 *>(d.qlist + o2 * (3 * PL_STRIDE));
+        const int pstride = off >= 0 ? l4 : PL_STRIDE / 4; // float4 units between the planes
+        float margin = 0.f, moved = 0.f;
+        double hh0[10], jo[4];
+        for (int gn = s_gn[t2]; gn < 5; gn++)
+        {
+            if (!(moved + 2e-3f < margin))
+            { // classify the points again (:131-171)
 #pragma unroll
                 for (int i = 0; i < 9; i++) hh0[i] = hr[i * hs];
                 hh0[9] = 2.0 * (double)n;
@@ -1082,7 +1281,7 @@ __global__ void __launch_bounds__(128, 5) k_gn_solve(const __grid_constant__ Dsm
                 int k = 0;
                 for (; k + 4 <= n; k += 4)
                 {
-                    const float4 a = qx[k >> 2], bb = qy[k >> 2], c = qz[k >> 2];
+                    const float4 a = qx[k >> 2], bb = qx[pstride + (k >> 2)], c = qx[2 * pstride + (k >> 2)];
                     point(a.x, bb.x, c.x);
                     point(a.y, bb.y, c.y);
                     point(a.z, bb.z, c.z);
@@ -1090,7 +1289,7 @@ __global__ void __launch_bounds__(128, 5) k_gn_solve(const __grid_constant__ Dsm
                 }
                 if (k < n)
                 {
-                    const float4 a = qx[k >> 2], bb = qy[k >> 2], c = qz[k >> 2];
+                    const float4 a = qx[k >> 2], bb = qx[pstride + (k >> 2)], c = qx[2 * pstride + (k >> 2)];
                     point(a.x, bb.x, c.x);
                     if (k + 1 < n) point(a.y, bb.y, c.y);
                     if (k + 2 < n) point(a.z, bb.z, c.z);
@@ -1098,53 +1297,10 @@ __global__ void __launch_bounds__(128, 5) k_gn_solve(const __grid_constant__ Dsm
                 margin = rnan ? __int_as_float(0x7fc00000) : mg;
                 moved = 0.f;
             }
-            double jj[4];
-            const double tx = (double)nx, ty = (double)ny, tz = (double)nz, tb = (double)nb;
-            jj[0] = ((hh0[0] * tx + hh0[1] * ty) + hh0[2] * tz) + hh0[3] * tb + jo[0];
-            jj[1] = ((hh0[1] * tx + hh0[4] * ty) + hh0[5] * tz) + hh0[6] * tb + jo[1];
-            jj[2] = ((hh0[2] * tx + hh0[5] * ty) + hh0[7] * tz) + hh0[8] * tb + jo[2];
-            jj[3] = ((hh0[3] * tx + hh0[6] * ty) + hh0[8] * tz) + hh0[9] * tb + jo[3];
-            double u[4];
-            solve4_spd_t(hh0, 5.0, jj, u); // LM damping: + 5 on the diagonal (:172-175)
-            const float ox = nx, oy = ny, oz = nz, ob = nb;
-            nx = (float)((double)nx - u[0]);
-            ny = (float)((double)ny - u[1]);
-            nz = (float)((double)nz - u[2]);
-            nb = (float)((double)nb - u[3]);
-            const float dx = nx - ox, dy = ny - oy, dz = nz - oz;
-            moved += qmax * sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + fabsf(nb - ob) + 1e-4f;
+            moved += gn_step(hh0, jo, qmax, nx, ny, nz, nb);
         }
-        nb = nb - (nx * mxs + ny * mys + nz * mzs);
-        const float nl = sqrtf(nx * nx + ny * ny + nz * nz);
-        nx /= nl;
-        ny /= nl;
-        nz /= nl;
-        nb /= nl;
-        // centre of the superpixel projected onto the fitted plane (:884-895)
-        const float axf = (sd.x - d.cx) / d.fx * sd.w;
-        const float ayf = (sd.y - d.cy) / d.fy * sd.w;
-        double ax = (double)axf, ay = (double)ayf, az = (double)sd.w;
-        const float kk = (float)(-1 * (ax * (double)nx + ay * (double)ny + az * (double)nz) - (double)nb);
-        ax += (double)(kk * nx);
-        ay += (double)(kk * ny);
-        az += (double)(kk * nz);
-        const float mean_depth = (float)az;
-        float view_cos = (float)(-1.0 * ((double)nx * ax + (double)ny * ay + (double)nz * az) / sqrt(ax * ax + ay * ay + az * az));
-        if (view_cos < 0)
-        {
-            view_cos = -view_cos;
-            nx = -nx;
-            ny = -ny;
-            nz = -nz;
-        }
-        r0 = make_float4(nx, ny, nz, view_cos);
-        r1 = make_float4((float)ax, (float)ay, (float)az, mean_depth);
-        r2.x = sqrtf(P0.w);
+        finish_plane(d, o2, sd, P0, P1, nx, ny, nz, nb);
     }
-    float4 *pl = d.plane + (so + s) * 3;
-    pl[0] = r0;
-    pl[1] = r1;
-    pl[2] = r2;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1172,8 +1328,9 @@ void dsm_launch_gather(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s
 }
 void dsm_launch_newton2(const DsmDev &d, int nb, cudaStream_t s)
 {
-    dim3 grid((d.S + 127) / 128, nb);
-    k_newton2<<<grid, 128, 0, s>>>(d);
+    dim3 grid((d.S + NW_T - 1) / NW_T, nb);
+    k_newton2<<<grid, NW_T, 0, s>>>(d);
+    k_newton_hard<<<grid, NW_T, 0, s>>>(d); // surplus CTAs exit at once: the queue length is on the device
 }
 void dsm_launch_plane_gather(const DsmDev &d, const DsmMaps &m, int nb, cudaStream_t s)
 {

@@ -17,6 +17,13 @@
  * by the caller (the reference is single-threaded at this call site too: ros_node.cpp:38-41).
  * Element layouts are byte-identical to the reference PODs (elements.h:5-31).
  *
+ * Numerical contract: superpixel labels and the clustering state (seed x, y, intensity, Huber mean depth, stable flag)
+ * are bit-identical to the serialised reference; the plane fit and everything downstream of it (seed normal / position /
+ * view_cos / size, surfel geometry) agree within 1e-4 (norm-based) but are NOT bit-identical: their float / fp64 sums are
+ * accumulated lane-partially and tree-reduced instead of sequentially (fusion_functions.cpp:117-119, :849-860).  A frame's
+ * results do not depend on the batch size, on chunking or on which entry point delivered it: every entry point runs the
+ * same kernels.
+ *
  * INTEGRATION.md shows the reference-side binding (a FusionFunctions-compatible C++ adapter,
  * include/dsm_fusion_functions.hpp, plus the ctypes stub used by the tests).
  */
@@ -181,7 +188,9 @@ int dsm_batch_restore_pool(dsm_ctx *ctx);
  *   dsm_pool_retire            the removal half of SurfelMap::move_add_surfels (surfel_map.cpp:1479-1497):
  *                              the live surfels whose last_update == keyframe_index are copied out in
  *                              pool order (they become that pose's attached_surfels) and flagged dead
- *                              (update_times = 0; the next fuse post-step drops them).  Synchronises.
+ *                              (update_times = 0; the next fuse post-step drops them).  Counts first: if more than
+ *                              `cap` surfels match, nothing is flagged, *n_out is the number needed and the call
+ *                              returns DSM_E_CAPACITY.  Synchronises.
  *   dsm_pool_append            the insertion half (surfel_map.cpp:1583-1587): surfels of poses that
  *                              re-enter the drift-free set are appended to the pool.  Synchronises.
  *   dsm_pool_size / dsm_pool_download   read back (synchronise). */
@@ -190,13 +199,11 @@ int dsm_fuse_frame_resident(dsm_ctx *ctx, int reference_frame_index,
                             const uint8_t *gray, size_t gray_pitch, const float *depth, size_t depth_pitch,
                             const float pose_colmajor[16], int *n_new);
 /* n consecutive frames of the SAME stream in one call (tightly packed [n][H][W] images, [n][16] poses): results are
- * those of n calls of dsm_fuse_frame_resident (labels bit-identical; surfels bit-identical while n * seeds <= 20000,
- * beyond that the plane fit switches to its large-batch kernel whose fp64 sums run in another order, ~1e-16
- * relative), but the pose- and pool-independent stages (superpixels, normals, plane fit) of all n frames run as one
+ * those of n calls of dsm_fuse_frame_resident (same kernels, same order on the pool), but the pose- and pool-independent stages (superpixels, normals, plane fit) of all n frames run as one
  * batch; only fuse / initialise / compaction run frame by frame.  Trades
  * n-1 frames of latency for throughput (offline sequences, or a node that lags behind its camera).  n <= max_batch;
  * with 2n <= max_batch the copy of one run overlaps the kernels of the previous one.  n_new (optional, [n]) = new
- * surfels per frame; passing it synchronises.  EXPERIMENTAL: added after round 1's GPU budget was spent. */
+ * surfels per frame; passing it synchronises. */
 int dsm_fuse_stream_resident(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_index,
                              const uint8_t *gray, const float *depth, const float *poses_colmajor, int32_t *n_new);
 int dsm_pool_transform(dsm_ctx *ctx, const float W_colmajor[16]);
@@ -234,7 +241,7 @@ int dsm_write_pcd(const char *path, const dsm_point_t *points, size_t n, int bin
 int dsm_write_ply_mesh(const char *path, const dsm_surfel_t *surfels, size_t n);
 int dsm_mesh_vertices(const dsm_surfel_t *surfels, size_t n, float *vertices36);
 
-/* ---- inactive store (EXPERIMENTAL: written after round 1's GPU budget was spent) ----
+/* ---- inactive store ----
  * What SurfelMap keeps per pose outside the drift-free window -- PoseElement::attached_surfels and the mirror
  * inactive_pointcloud (surfel_map.h:36-46) -- resident on the device next to the local pool, so that
  * move_add_surfels and the loop-closure warp of the inactive surfels never cross PCIe.  Host orchestration over the

@@ -171,7 +171,7 @@ class ResidentSurfelPool
         return report("save_mesh");
     }
 
-    // ---- device-resident attached_surfels / inactive_pointcloud (EXPERIMENTAL, see include/dsm.h "inactive store") ----
+    // ---- device-resident attached_surfels / inactive_pointcloud (see include/dsm.h "inactive store") ----
     // Call reserve_inactive() once after initialize(); then the removal / insertion halves of move_add_surfels and the
     // per-pose inactive warp never move surfels across PCIe.
     int reserve_inactive(int max_inactive_surfels)

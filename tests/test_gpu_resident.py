@@ -125,11 +125,53 @@ def test_pool_retire_and_append_move_add_surfels():
     ctx.close()
 
 
+def test_pool_retire_with_a_too_small_buffer_leaves_the_pool_untouched():
+    """dsm_pool_retire counts first: when the retired surfels do not fit the caller's buffer nothing is flagged dead,
+    the call fails with DSM_E_CAPACITY and reports the needed size."""
+    import ctypes
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    pose = synth.pose_stream(0)
+    gray, depth = synth.make_frame(cam, 510, pose)
+    _, pool = oracle_for(cam).fuse(4, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))
+    assert len(pool) > 10
+    ctx = capi.Context(cam, max_batch=1, max_local_surfels=len(pool) + 64)
+    ctx.pool_upload(pool)
+    out, n = np.zeros(4, SURFEL_DTYPE), ctypes.c_int(0)
+    rc = ctx.lib.dsm_pool_retire(ctx.h, 4, out.ctypes.data, 4, ctypes.byref(n))
+    assert rc == -6 and n.value == len(pool)            # DSM_E_CAPACITY, *n_out = what a second call needs
+    assert ctx.pool_download().tobytes() == pool.tobytes()  # nothing was retired
+    assert ctx.pool_retire(4).tobytes() == pool.tobytes()   # with room: all of them, in pool order
+    assert (ctx.pool_download()["update_times"] == 0).all()
+    ctx.close()
+
+
+def test_host_pointer_calls_invalidate_the_resident_pool():
+    """dsm_fuse_frame / dsm_fuse_batch copy the caller's surfels into the buffer that holds the resident pool: afterwards the
+    resident entry points must refuse (DSM_E_STATE) instead of running on overwritten data."""
+    from densesurfelmapping_b200 import capi
+    cam = synth.VGA
+    pose = synth.pose_stream(0)
+    gray, depth = synth.make_frame(cam, 511, pose)
+    ctx = capi.Context(cam, max_batch=2, max_local_surfels=1 << 16)
+    ctx.pool_upload(np.zeros(0, SURFEL_DTYPE))
+    ctx.fuse_frame_resident(0, gray, depth, pose)
+    assert ctx.pool_size() > 0
+    _, new = ctx.fuse_frame(0, gray, depth, pose, np.zeros(0, SURFEL_DTYPE))   # host-pointer call on the same context
+    assert len(new) > 0
+    for call in (ctx.pool_size, ctx.pool_download, lambda: ctx.fuse_frame_resident(1, gray, depth, pose), lambda: ctx.pool_retire(0)):
+        with pytest.raises(capi.DsmError) as e:
+            call()
+        assert e.value.code == -7  # DSM_E_STATE
+    ctx.pool_upload(new)           # a fresh upload makes the resident mode usable again
+    assert ctx.pool_size() == len(new)
+    ctx.close()
+
+
 @pytest.mark.parametrize("chunk", [1, 3, 4])
 def test_stream_chunks_equal_frame_by_frame(chunk):
     """dsm_fuse_stream_resident (n frames per call) must leave exactly the pool that n calls of
-    dsm_fuse_frame_resident leave: same kernels, same order on the pool, only batched differently
-    (chunk * 4800 seeds <= 20000, so every chunk size here uses the same plane-fit kernel as a single frame)."""
+    dsm_fuse_frame_resident leave: same kernels, same order on the pool, only batched differently."""
     from densesurfelmapping_b200 import capi
     cam = synth.VGA
     T = 8
