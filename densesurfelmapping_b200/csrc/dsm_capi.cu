@@ -71,6 +71,7 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     cudaFree(d.seed);
     cudaFree(d.inv_md);
     cudaFree(d.invd);
+    cudaFree(d.code);
     cudaFree(d.seed_hl);
     cudaFree(d.done);
     cudaFree(d.hardq);
@@ -165,7 +166,7 @@ static int make_tile_maps(dsm_ctx *ctx)
         void *base;
         CUtensorMapDataType type;
         unsigned esize, boxw;
-    } specs[3] = {{&ctx->maps.lab, d.labels, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, DSM_TILE_W},
+    } specs[3] = {{&ctx->maps.cod, d.code, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, DSM_TILE_GW},
                   {&ctx->maps.dep, ctx->depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, DSM_TILE_W},
                   {&ctx->maps.gry, ctx->gray, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, DSM_TILE_GW}};
     for (auto &sp : specs)
@@ -267,6 +268,7 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ALLOC(d.seed, (size_t)B * S);
     ALLOC(d.inv_md, (size_t)B * S);
     ALLOC(d.invd, B * px + 64);
+    ALLOC(d.code, B * px + 64);
     ALLOC(d.seed_hl, (size_t)B * S);
     ALLOC(d.done, (size_t)B);
     ALLOC(d.hardq, (size_t)B * S);
@@ -646,21 +648,11 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
     if (!ctx) return DSM_E_INVALID;
     if (!ctx->uploaded) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    // DSM_RUN_CHUNK=n (experiment): run the batch n frames at a time through the whole schedule, so that a sub-batch's
-    // images, labels and lists stay L2-resident between its kernels (DRAM traffic) at the price of more, smaller launches
-    int chunk = ctx->nb;
-    if (const char *e = getenv("DSM_RUN_CHUNK"))
-    {
-        const int v = atoi(e);
-        if (v >= 1 && v < ctx->nb) chunk = v;
-    }
-    if (ctx->stop_after > 0) chunk = ctx->nb; // the debug kernel budget counts launches of the whole batch
-    for (int f0 = 0; f0 < ctx->nb; f0 += chunk)
-    {
-        const int nf = ctx->nb - f0 < chunk ? ctx->nb - f0 : chunk;
-        int rc = enqueue_schedule(ctx, f0, nf, ctx->d.max_pool_per_frame, ctx->stream);
-        if (rc != DSM_OK) return rc;
-    }
+    // (Running the batch in L2-sized sub-batches was measured and is slower: 8 / 16 frames per pass through the schedule
+    // take 1.70 / 1.29 ms per 32 frames against 1.08 ms for the whole batch -- the kernels are issue- or latency-bound,
+    // not DRAM-bound, and smaller launches fill the GPU worse.  profiles/README.md, history.)
+    int rc = enqueue_schedule(ctx, 0, ctx->nb, ctx->d.max_pool_per_frame, ctx->stream);
+    if (rc != DSM_OK) return rc;
     ctx->ran = true;
     return DSM_OK;
 }

@@ -5,6 +5,8 @@
 //   depth   f32 [B][H][Wp]      (vector loads, TMA boxes)
 //   invd    f32 [B][H][Wp]      (float)(1.0 / (double)depth) for depth > 0.01, else 0 (:404-405): what the assign passes read
 //   labels  i32 [B][H][Wp]      superpixel_index of the reference (fusion_functions.h:37)
+//   code    u8  [B][H][Wp]      the same label as the index of the winning candidate among the pixel's 2x2 candidate seeds:
+//                               what the window gathers test (1 B/px, a byte compare against a position-only pattern)
 //   seed    float4 [B][S]       (x, y, mean_intensity, mean_depth)  -- the clustering state
 //   seed_hl float2 [B][S]       1.0 / (double)mean_depth as hi + lo floats (fp32 cost filter of the assign pass)
 //   inv_md  f64 [B][S]          1.0 / (double)mean_depth (exact path of the assign pass, :380)
@@ -76,6 +78,7 @@ struct DsmDev
     const int32_t *refidx;
     int max_pool_per_frame; // largest per-frame pool slice in this batch (grid sizing)
     // tile path (dsm_tile.cu)
+    uint8_t *code;      // [B][H][Wp] label of every pixel as the index (0..3) of the winning candidate among its 2x2 candidate seeds (mirror of labels)
     float *invd;        // [B][H][Wp] (float)(1.0 / (double)depth) for depth > 0.01, else 0 (:404-405), written by the first assign pass
     float2 *seed_hl;    // [B][S] 1.0 / (double)mean_depth split into two floats (hi, lo) for the filtered assign pass
     int32_t *hardq;     // [B][S] seeds whose Huber-Newton needs the entry-by-entry classification (k_newton2 -> k_newton_hard)
@@ -87,7 +90,7 @@ struct DsmDev
 // TMA descriptors (cuTensorMapEncodeTiled) of the three per-pixel arrays as [B][H][Wp] tensors; box = one seed tile plus halo
 struct DsmMaps
 {
-    CUtensorMap lab, dep, gry;
+    CUtensorMap cod, dep, gry; // label codes (u8), depth (f32), gray (u8)
 };
 // seed tile of the tile kernels: 8 x 4 superpixels = 64 x 32 pixels, plus a 4-pixel halo (the 16 x 16 windows of
 // update_seeds_kernel :481-489 and calculate_sp_depth_norms_kernel :806-811 overlap their neighbours by 8)

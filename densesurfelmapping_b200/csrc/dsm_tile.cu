@@ -81,6 +81,7 @@ __device__ __forceinline__ void relax_frame(const DsmDev &d, int b, int tid, int
         const size_t fo = (size_t)b * d.px_stride;
         int2 *list = d.list + fo;
         int32_t *labels = d.labels + fo;
+        uint8_t *codes = d.code + fo;
         int32_t *t = d.tstable + (size_t)b * d.S;
         for (;;)
         {
@@ -92,9 +93,11 @@ __device__ __forceinline__ void relax_frame(const DsmDev &d, int b, int tid, int
                 const int owner = __ldcg(&labels[en.x]);
                 if (__ldcg(&t[owner]) < en.x)
                 {
-                    labels[en.x] = en.y;
+                    const int win = en.y & 0x0fffffff; // entry: winner seed | winner's candidate code << 28
+                    labels[en.x] = win;
+                    codes[en.x] = (uint8_t)(en.y >> 28);
                     list[e].x = -1;
-                    if (__ldcg(&t[en.y]) > en.x) atomicMin(&t[en.y], en.x);
+                    if (__ldcg(&t[win]) > en.x) atomicMin(&t[win], en.x);
                     changed = 1;
                 }
             }
@@ -113,6 +116,13 @@ __device__ __forceinline__ float pick4(float a0, float a1, float a2, float a3, i
     return i == 0 ? a0 : (i == 1 ? a1 : (i == 2 ? a2 : a3));
 }
 
+// label code of a pixel: which of its (at most) 2x2 candidate seeds it is labelled with, c = 2*ix + iy over the columns
+// {xa, xa+1} and rows {ya, ya+1} defined below (the candidate set depends on the pixel position only, :413-422), or
+// DSM_CODE_NONE for a pixel the reference would have left without any label (input domain).  The u8 code
+// plane mirrors the int32 labels; the passes that only need "is this pixel a member of seed s" read it instead
+// (1 byte per pixel, and the test is a byte compare with a pattern that depends on the window position only).
+#define DSM_CODE_NONE 4
+
 template <bool FIRST>
 __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmDev d)
 {
@@ -125,8 +135,9 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
 
     const size_t fo = (size_t)b * d.px_stride;
     const size_t so = (size_t)b * d.S;
-    int win[4] = {-1, -1, -1, -1};
-    int L[4] = {0, 0, 0, 0};
+    int wc[4] = {DSM_CODE_NONE, DSM_CODE_NONE, DSM_CODE_NONE, DSM_CODE_NONE}; // winner of every pixel as a candidate code
+    int oc[4] = {0, 0, 0, 0};                                                 // current label as a candidate code
+    int sidx0 = 0;                                                            // seed index of candidate 0; candidate c = sidx0 + (c & 1) * spw + (c >> 1)
     if (active)
     {
         const size_t po = fo + (size_t)y * d.Wp + x4;
@@ -146,8 +157,8 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
         {
             const float4 i4 = *reinterpret_cast<const float4 *>(d.invd + po);
             iv[0] = i4.x, iv[1] = i4.y, iv[2] = i4.z, iv[3] = i4.w;
-            const int4 l4 = *reinterpret_cast<const int4 *>(d.labels + po);
-            L[0] = l4.x, L[1] = l4.y, L[2] = l4.z, L[3] = l4.w;
+            const uchar4 c4 = *reinterpret_cast<const uchar4 *>(d.code + po);
+            oc[0] = c4.x, oc[1] = c4.y, oc[2] = c4.z, oc[3] = c4.w;
         }
         const float gi[4] = {(float)g4.x, (float)g4.y, (float)g4.z, (float)g4.w};
         const int bx = x4 >> 3, by = y >> 3, rx0 = x4 & 7, ry = y & 7;
@@ -155,6 +166,7 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
         const int ya = (ry < 4) ? by - 1 : by, yb = ya + 1;
         const bool vxa = xa >= 0 && xa < d.spw, vxb = xb >= 0 && xb < d.spw;
         const bool vya = ya >= 0 && ya < d.sph, vyb = (ry != 4) && yb >= 0 && yb < d.sph;
+        sidx0 = ya * d.spw + xa;
         // candidate c = 2*ix + iy  -> (xa,ya) (xa,yb) (xb,ya) (xb,yb): dx outer, dy inner (:413-414)
         // fast-path operands, shared by the thread's 4 pixels.  Coordinates are pre-scaled by 1/4 (exact), so that
         // dist/16 (:374) is ax'^2 + ay'^2; an invalid candidate sits 1e18 away: its cost (~1e36, finite) is never the minimum
@@ -162,16 +174,13 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
         // the candidates of column xb get the same treatment for that pixel only (sxq0).
         float sxq[4], sxq0[4], ayy[4], sI[4], shi[4], slo[4];
         bool sv[4];
-        int sidx[4];
         bool allmd = true, allmd0 = true; // every valid candidate seed has mean_depth > 0 (:378), over 4 / over column xa only
         const float fyq = (float)y * 0.25f;
 #pragma unroll
         for (int c = 0; c < 4; c++)
         {
-            const int cx = (c >> 1) ? xb : xa, cy = (c & 1) ? yb : ya;
             sv[c] = ((c >> 1) ? vxb : vxa) && ((c & 1) ? vyb : vya);
-            sidx[c] = cy * d.spw + cx;
-            const int li = sv[c] ? sidx[c] : 0; // invalid candidates read seed 0 and are pushed away below
+            const int li = sv[c] ? sidx0 + (c & 1) * d.spw + (c >> 1) : 0; // invalid candidates read seed 0 and are pushed away below
             const float4 s4 = d.seed[so + li];
             const float2 hl = d.seed_hl[so + li];
             sxq[c] = sv[c] ? s4.x * 0.25f : 1e18f;
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
             const float lo23 = fminf(cost[2], cost[3]), hi23 = fmaxf(cost[2], cost[3]);
             const float m1 = fminf(lo01, lo23);
             const float m2 = fminf(fminf(fmaxf(lo01, lo23), fminf(hi01, hi23)), A_BIG); // second smallest, kept finite
-            win[i] = cost[0] == m1 ? sidx[0] : (cost[1] == m1 ? sidx[1] : (cost[2] == m1 ? sidx[2] : sidx[3]));
+            wc[i] = cost[0] == m1 ? 0 : (cost[1] == m1 ? 1 : (cost[2] == m1 ? 2 : 3));
             const bool certain = (m2 - m1 > A_EPS * (m2 + m1) + A_ALPHA) && (m1 < 9e5f);
             if (!certain) uncertain |= 1u << i;
         }
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
 #pragma unroll
             for (int c = 0; c < 4; c++)
             {
-                const int li = sv[c] ? sidx[c] : 0;
+                const int li = sv[c] ? sidx0 + (c & 1) * d.spw + (c >> 1) : 0;
                 const float4 s4 = d.seed[so + li];
                 sc[c].x = s4.x, sc[c].y = s4.y, sc[c].I = s4.z, sc[c].md = s4.w;
                 sc[c].inv = d.inv_md[so + li]; // 1.0 / (double)mean_depth, only consumed when mean_depth > 0 (:378)
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
                 const float my_inv = pick4(iv[0], iv[1], iv[2], iv[3], i);
                 const double my_inv_d = (double)my_inv;
                 float min_d = 1e6f, min_nd = 1e6f;
-                int idx_d = -1, idx_nd = -1;
+                int idx_d = DSM_CODE_NONE, idx_nd = DSM_CODE_NONE; // the reference's -1 (:409-411)
                 bool all_has_depth = true;
 #pragma unroll
                 for (int c = 0; c < 4; c++)
@@ -246,34 +255,36 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
                     all_has_depth &= has || !valid;
                     const bool bd = cdd < min_d, bn = cnd < min_nd;
                     min_d = bd ? cdd : min_d;
-                    idx_d = bd ? sidx[c] : idx_d;
+                    idx_d = bd ? c : idx_d;
                     min_nd = bn ? cnd : min_nd;
-                    idx_nd = bn ? sidx[c] : idx_nd;
+                    idx_nd = bn ? c : idx_nd;
                 }
                 const int wv = all_has_depth ? idx_d : idx_nd;
-                win[0] = i == 0 ? wv : win[0];
-                win[1] = i == 1 ? wv : win[1];
-                win[2] = i == 2 ? wv : win[2];
-                win[3] = i == 3 ? wv : win[3];
+                wc[0] = i == 0 ? wv : wc[0];
+                wc[1] = i == 1 ? wv : wc[1];
+                wc[2] = i == 2 ? wv : wc[2];
+                wc[3] = i == 3 ? wv : wc[3];
             }
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            if (x4 + i >= d.W) win[i] = -1;
+            if (x4 + i >= d.W) wc[i] = DSM_CODE_NONE;
     }
+    const int spw = d.spw;
+    auto seed_of = [&](int c) { return c == DSM_CODE_NONE ? 0 : sidx0 + (c & 1) * spw + (c >> 1); }; // a pixel without winner is labelled 0
 
     if (FIRST)
     { // every label is 0 and seed 0 is unstable: everything commits (:400)
         if (active)
         {
             const size_t po = fo + (size_t)y * d.Wp + x4;
-            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(win[0] < 0 ? 0 : win[0], win[1] < 0 ? 0 : win[1],
-                                                                 win[2] < 0 ? 0 : win[2], win[3] < 0 ? 0 : win[3]);
+            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(seed_of(wc[0]), seed_of(wc[1]), seed_of(wc[2]), seed_of(wc[3]));
+            *reinterpret_cast<uchar4 *>(d.code + po) = make_uchar4(wc[0], wc[1], wc[2], wc[3]);
         }
         return;
     }
 
-    // ---- iterations 2..: commit / defer (see k_assign).  A deferred pixel whose winner IS its current label is dropped:
+    // ---- iterations 2..: commit / defer.  A deferred pixel whose winner IS its current label is dropped:
     // if the raster scan evaluates it (t[label] < idx) the label does not change and the stamp t[winner] = t[label] is
     // already below idx, so it can change nothing -- the relaxation only ever needs the pixels that would switch seeds.
     int2 ent[4];
@@ -281,30 +292,32 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
     if (active)
     {
         bool changed = false;
+        const int32_t *ts = d.tstable + so;
 #pragma unroll
         for (int i = 0; i < 4; i++)
         {
-            if (x4 + i >= d.W || win[i] < 0) continue;
+            if (x4 + i >= d.W || wc[i] == DSM_CODE_NONE) continue;
             const int pidx = y * d.Wp + x4 + i;
-            const int ts = d.tstable[so + L[i]];
-            if (ts < 0)
+            const int win = seed_of(wc[i]);
+            if (ts[seed_of(oc[i])] < 0)
             { // owner unstable since the start of the pass: the reference evaluates this pixel
-                if (win[i] != L[i])
+                if (wc[i] != oc[i])
                 {
-                    L[i] = win[i];
+                    oc[i] = wc[i];
                     changed = true;
                 }
-                if (d.tstable[so + win[i]] > pidx) atomicMin(&d.tstable[so + win[i]], pidx); // stable = false at time pidx (:445/:450)
+                if (ts[win] > pidx) atomicMin(&d.tstable[so + win], pidx); // stable = false at time pidx (:445/:450)
             }
-            else if (win[i] != L[i])
+            else if (wc[i] != oc[i])
             {
-                ent[nent++] = make_int2(pidx, win[i]);
+                ent[nent++] = make_int2(pidx, win | (wc[i] << 28));
             }
         }
         if (changed)
         {
             const size_t po = fo + (size_t)y * d.Wp + x4;
-            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(L[0], L[1], L[2], L[3]);
+            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(seed_of(oc[0]), seed_of(oc[1]), seed_of(oc[2]), seed_of(oc[3]));
+            *reinterpret_cast<uchar4 *>(d.code + po) = make_uchar4(oc[0], oc[1], oc[2], oc[3]);
         }
     }
     // warp-aggregated append of the deferred pixels (rare: most warps have none)
@@ -357,14 +370,33 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
 // -------------------------------------------------------------------------------------------
 #define DL_STRIDE 232 // floats per seed list: >= 15*15 possible members, multiple of 8 (32-byte sectors)
 #define TILE_PLANE_BYTES 12544 // 76 * 41 * 4 = 12464 rounded up to 128: TMA destinations are 128-byte aligned
-#define GAT_SMEM_LAB 0
-#define GAT_SMEM_DEP TILE_PLANE_BYTES
-#define GAT_SMEM_GRY (2 * TILE_PLANE_BYTES)
-#define GAT_SMEM_LIST (GAT_SMEM_GRY + DSM_TILE_GW * DSM_TILE_H) // float [16][DL_STRIDE]: the 16 seeds of one round
+#define TILE_BYTE_PLANE 4608 // 112 * 41 = 4592 rounded up to 128
+#define GAT_SMEM_DEP 0
+#define GAT_SMEM_COD TILE_PLANE_BYTES
+#define GAT_SMEM_GRY (TILE_PLANE_BYTES + TILE_BYTE_PLANE)
+#define GAT_SMEM_LIST (TILE_PLANE_BYTES + 2 * TILE_BYTE_PLANE) // float [16][DL_STRIDE]: the 16 seeds of one round
 #define GAT_SMEM_ND (GAT_SMEM_LIST + 16 * DL_STRIDE * 4)        // int [16] list lengths of the round
 #define GAT_SMEM_BAR (GAT_SMEM_ND + 16 * 4)
 #define GAT_SMEM_BYTES (GAT_SMEM_BAR + 16)
-#define TILE_TX_BYTES (2u * DSM_TILE_W * DSM_TILE_H * 4u + (unsigned)DSM_TILE_GW * DSM_TILE_H)
+#define TILE_TX_BYTES (DSM_TILE_W * DSM_TILE_H * 4u + 2u * DSM_TILE_GW * DSM_TILE_H)
+
+// 16-bit membership mask of one window row from the label-code tile: bit k set iff the pixel at window column k is labelled
+// with the seed whose window this is.  Inside the 16 x 16 window of seed (sx, sy) the pixel at column k, row r sees that
+// seed as candidate ix = (k < 8), iy = (r < 8) (its candidate columns are {sx-1, sx} for k < 8 and {sx, sx+1} otherwise,
+// :413-422), i.e. the expected code byte is (k < 8 ? 2 : 0) | (r < 8 ? 1 : 0).  Four 32-bit words = 16 code bytes.
+__device__ __forceinline__ unsigned zero_bytes_to_nibble(unsigned x)
+{ // bit j of the result set iff byte j of x is zero (exact: no borrow tricks)
+    unsigned t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    t = ~(t | x | 0x7f7f7f7fu);                // 0x80 in every zero byte
+    return ((t >> 7) * 0x00204081u >> 21) & 0xfu; // bits 0, 8, 16, 24 -> bits 21..24 of the product
+}
+__device__ __forceinline__ unsigned member_mask16(const unsigned *codes, int r)
+{
+    const unsigned lo = (r < 8) ? 0x01010101u : 0u; // iy
+    const unsigned e_left = 0x02020202u | lo, e_right = lo;
+    return zero_bytes_to_nibble(codes[0] ^ e_left) | (zero_bytes_to_nibble(codes[1] ^ e_left) << 4) |
+           (zero_bytes_to_nibble(codes[2] ^ e_right) << 8) | (zero_bytes_to_nibble(codes[3] ^ e_right) << 12);
+}
 
 // sum over the set bits k of a 16-bit mask of k: sum_j 2^j popc(mask & {k : bit j of k set})
 __device__ __forceinline__ int mask_index_sum(unsigned m)
@@ -377,9 +409,8 @@ __device__ __forceinline__ unsigned nibble_to_bytes(unsigned n) { return (((n & 
 __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int32_t *t_lab = reinterpret_cast<const int32_t *>(smem + GAT_SMEM_LAB);
     const float *t_dep = reinterpret_cast<const float *>(smem + GAT_SMEM_DEP);
-    const uint8_t *t_gry = smem + GAT_SMEM_GRY;
+    const uint8_t *t_cod = smem + GAT_SMEM_COD, *t_gry = smem + GAT_SMEM_GRY;
     float *lists = reinterpret_cast<float *>(smem + GAT_SMEM_LIST);
     int *s_nd = reinterpret_cast<int *>(smem + GAT_SMEM_ND);
     const unsigned bar = smem_u32(smem + GAT_SMEM_BAR);
@@ -391,8 +422,8 @@ __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDe
     {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, TILE_TX_BYTES);
-        tma_load_3d(smem_u32(smem + GAT_SMEM_LAB), &mp.lab, X0, Y0, b, bar);
         tma_load_3d(smem_u32(smem + GAT_SMEM_DEP), &mp.dep, X0, Y0, b, bar);
+        tma_load_3d(smem_u32(smem + GAT_SMEM_COD), &mp.cod, X0 - DSM_TILE_GX, Y0, b, bar);
         tma_load_3d(smem_u32(smem + GAT_SMEM_GRY), &mp.gry, X0 - DSM_TILE_GX, Y0, b, bar);
     }
     if (threadIdx.x == 1 && blockIdx.x == 0 && blockIdx.y == 0) d.nhard[b] = 0; // this pass's queue of hard Newton seeds
@@ -430,16 +461,16 @@ __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDe
         const unsigned kmask = rowin ? (((1u << (xe - x0)) - 1u) & ~((1u << (xb - x0)) - 1u)) : 0u;
         const int trow = ty * DSM_SP + r, tcol = tx * DSM_SP;
         float zk[16];
-        unsigned mm = 0, zm = 0; // bit k: label == s / depth > 0.1
+        unsigned mm, zm = 0; // bit k: labelled with this seed / depth > 0.1
         {
-            const int4 *pl = reinterpret_cast<const int4 *>(t_lab + trow * DSM_TILE_W + tcol);
+            const unsigned *pc = reinterpret_cast<const unsigned *>(t_cod + trow * DSM_TILE_GW + DSM_TILE_GX + tcol); // 4-byte aligned
+            const unsigned cw[4] = {pc[0], pc[1], pc[2], pc[3]};
+            mm = member_mask16(cw, r);
             const float4 *pz = reinterpret_cast<const float4 *>(t_dep + trow * DSM_TILE_W + tcol);
 #pragma unroll
             for (int qd = 0; qd < 4; qd++)
             {
-                const int4 a = pl[qd];
                 const float4 z = pz[qd];
-                mm |= (a.x == s ? 1u : 0u) << (4 * qd) | (a.y == s ? 2u : 0u) << (4 * qd) | (a.z == s ? 4u : 0u) << (4 * qd) | (a.w == s ? 8u : 0u) << (4 * qd);
                 zk[4 * qd] = z.x, zk[4 * qd + 1] = z.y, zk[4 * qd + 2] = z.z, zk[4 * qd + 3] = z.w;
             }
 #pragma unroll
@@ -509,11 +540,10 @@ __global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDe
 #define NW_CAP 5632   // floats of list staging per CTA (22 KB): 88 entries per seed on average, 225 possible; 8 CTAs per SM
 __global__ void __launch_bounds__(NW_T, 8) k_newton2(const __grid_constant__ DsmDev d)
 {
-    // The lists of the CTA's NW_T seeds are contiguous runs in global memory; the CTA copies them into shared memory with
-    // coalesced 16-byte asynchronous copies (cp.async; one list after the other, lengths rounded up to 4) and every thread then walks its own
-    // list there up to six times.  Lists that do not fit (rare: NW_CAP covers 88 entries per seed) stay in global memory.
+    // Every thread stages its seed's list (a contiguous run in global memory) into shared memory with 16-byte cp.async and
+    // then walks it there up to six times.  Lists that do not fit (rare: NW_CAP covers 88 entries per seed) stay in global memory.
     __shared__ __align__(16) float buf[NW_CAP];
-    __shared__ int s_off[NW_T], s_len[NW_T], s_wsum[NW_T / 32];
+    __shared__ int s_off[NW_T], s_wsum[NW_T / 32];
     const int b = d.frame0 + blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x * NW_T + tid;
@@ -530,20 +560,18 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton2(const __grid_constant__ Dsm
         for (int w = 0; w < warp; w++) base += s_wsum[w];
         const int off = base + wex;
         s_off[tid] = (off + len4 <= NW_CAP) ? off : -1;
-        s_len[tid] = nd;
     }
-    __syncthreads();
-    for (int q = warp; q < NW_T; q += NW_T / 32)
+    // every thread copies its own list (a contiguous run in global memory) with 16-byte cp.async: all copies of the CTA are in
+    // flight at once, no register staging, and a thread waits for its own copies only (it never reads another list)
+    if (s_off[tid] >= 0)
     {
-        const int off = s_off[q], len = s_len[q];
-        if (off < 0 || len == 0) continue; // warp-uniform
-        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + blockIdx.x * NW_T + q) * DL_STRIDE);
-        float4 *dst = reinterpret_cast<float4 *>(buf + off);
-        for (int j4 = lane; 4 * j4 < len; j4 += 32) __pipeline_memcpy_async(dst + j4, src + j4, 16); // LDGSTS: no register staging, no wait
+        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + s) * DL_STRIDE);
+        float4 *dst = reinterpret_cast<float4 *>(buf + s_off[tid]);
+        for (int j4 = 0; 4 * j4 < nd; j4++) __pipeline_memcpy_async(dst + j4, src + j4, 16);
     }
     __pipeline_commit();
-    __pipeline_wait_prior(0); // every copy of the CTA was in flight at once: one memory round trip for all the lists
-    __syncthreads();
+    __pipeline_wait_prior(0);
+    if (!act) return;
     // Every seed runs its mean pass and its Newton passes as long as every entry is inside the Huber range (a pure
     // dependent chain).  A seed that meets an out-of-range entry is appended to the frame's queue of hard seeds with its
     // state; k_newton_hard continues those, one thread each at full occupancy, so that the entry-by-entry
@@ -643,7 +671,7 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton2(const __grid_constant__ Dsm
 __global__ void __launch_bounds__(NW_T, 8) k_newton_hard(const __grid_constant__ DsmDev d)
 {
     __shared__ __align__(16) float buf[NW_CAP];
-    __shared__ int s_off[NW_T], s_len[NW_T], s_seed[NW_T], s_wsum[NW_T / 32];
+    __shared__ int s_off[NW_T], s_wsum[NW_T / 32];
     const int b = d.frame0 + blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nq = d.nhard[b];
@@ -663,21 +691,15 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton_hard(const __grid_constant__
         for (int w = 0; w < warp; w++) base += s_wsum[w];
         const int off = base + wex;
         s_off[tid] = (off + len4 <= NW_CAP) ? off : -1;
-        s_len[tid] = nd;
-        s_seed[tid] = s;
     }
-    __syncthreads();
-    for (int q2 = warp; q2 < NW_T; q2 += NW_T / 32)
+    if (s_off[tid] >= 0)
     {
-        const int off = s_off[q2], len = s_len[q2];
-        if (off < 0 || len == 0) continue; // warp-uniform
-        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + s_seed[q2]) * DL_STRIDE);
-        float4 *dst = reinterpret_cast<float4 *>(buf + off);
-        for (int j4 = lane; 4 * j4 < len; j4 += 32) __pipeline_memcpy_async(dst + j4, src + j4, 16);
+        const float4 *src = reinterpret_cast<const float4 *>(d.dlist + (so + s) * DL_STRIDE);
+        float4 *dst = reinterpret_cast<float4 *>(buf + s_off[tid]);
+        for (int j4 = 0; 4 * j4 < nd; j4++) __pipeline_memcpy_async(dst + j4, src + j4, 16);
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
-    __syncthreads();
     if (!act) return;
     const float4 st = d.pfsum[(so + s) * 2], mn = d.pfsum[(so + s) * 2 + 1];
     const float *dl = s_off[tid] >= 0 ? buf + s_off[tid] : d.dlist + (so + s) * DL_STRIDE; // generic: shared or global
@@ -757,15 +779,15 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton_hard(const __grid_constant__
 // -------------------------------------------------------------------------------------------
 #define PL_STRIDE 232 // floats per plane of a seed's centred-point list (>= 225, multiple of 8)
 #define HREC 24       // doubles per seed: H (9), ho (10), jo (4), packed (margin, qmax2)
-#define PG_SMEM_LAB 0
-#define PG_SMEM_DEP TILE_PLANE_BYTES
-#define PG_SMEM_POS (2 * TILE_PLANE_BYTES)                       // u16 [32][PG_POS_STRIDE]
+#define PG_SMEM_DEP 0
+#define PG_SMEM_COD TILE_PLANE_BYTES
+#define PG_SMEM_POS (TILE_PLANE_BYTES + TILE_BYTE_PLANE)         // u16 [32][PG_POS_STRIDE]
 #define PG_POS_STRIDE 232
 #define PG_SMEM_KX (PG_SMEM_POS + 32 * PG_POS_STRIDE * 2)        // float [80] kx, float [48] ky
 #define PG_SMEM_REC (PG_SMEM_KX + 128 * 4)                       // float maxd[32], int nvalid[32], int ninl[32]
 #define PG_SMEM_BAR (PG_SMEM_REC + 96 * 4)
 #define PG_SMEM_BYTES (PG_SMEM_BAR + 16)
-#define PG_TX_BYTES (2u * DSM_TILE_W * DSM_TILE_H * 4u)
+#define PG_TX_BYTES (DSM_TILE_W * DSM_TILE_H * 4u + (unsigned)DSM_TILE_GW * DSM_TILE_H)
 
 __device__ __forceinline__ float group8_sum_f(float v)
 {
@@ -783,8 +805,8 @@ __device__ __forceinline__ double group8_sum_d(double v)
 __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int32_t *t_lab = reinterpret_cast<const int32_t *>(smem + PG_SMEM_LAB);
     const float *t_dep = reinterpret_cast<const float *>(smem + PG_SMEM_DEP);
+    const uint8_t *t_cod = smem + PG_SMEM_COD;
     uint16_t *s_pos = reinterpret_cast<uint16_t *>(smem + PG_SMEM_POS);
     float *s_kx = reinterpret_cast<float *>(smem + PG_SMEM_KX), *s_ky = s_kx + 80;
     float *s_maxd = reinterpret_cast<float *>(smem + PG_SMEM_REC);
@@ -798,8 +820,8 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
     {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, PG_TX_BYTES);
-        tma_load_3d(smem_u32(smem + PG_SMEM_LAB), &mp.lab, X0, Y0, b, bar);
         tma_load_3d(smem_u32(smem + PG_SMEM_DEP), &mp.dep, X0, Y0, b, bar);
+        tma_load_3d(smem_u32(smem + PG_SMEM_COD), &mp.cod, X0 - DSM_TILE_GX, Y0, b, bar);
     }
     const int W = d.W, H = d.H;
     const size_t so = (size_t)b * d.S;
@@ -836,7 +858,6 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
         const int tx = sl & 7, ty = sl >> 3;
         const int sp_x = blockIdx.x * DSM_TILE_SX + tx, sp_y = blockIdx.y * DSM_TILE_SY + ty;
         const bool live = sp_x < d.spw && sp_y < d.sph;
-        const int s = sp_y * d.spw + sp_x;
         const float4 sd = sdv[rd];
         const int x0 = sp_x * DSM_SP - DSM_SP / 2, y0 = sp_y * DSM_SP - DSM_SP / 2;
         const int y = y0 + r;
@@ -844,16 +865,16 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
         const int kb = x0 < 0 ? -x0 : 0, ke = (W - x0) < 16 ? (W - x0) : 16;
         const unsigned kmask = rowin ? (((1u << ke) - 1u) & ~((1u << kb) - 1u)) : 0u;
         const int trow = ty * DSM_SP + r, tcol = tx * DSM_SP;
-        unsigned mm = 0, vm = 0, im = 0; // bit k: label == s / depth > 0.05 / |mean_depth - depth| < 0.4
+        unsigned mm, vm = 0, im = 0; // bit k: labelled with this seed / depth > 0.05 / |mean_depth - depth| < HUBER_RANGE
         {
-            const int4 *pl = reinterpret_cast<const int4 *>(t_lab + trow * DSM_TILE_W + tcol);
+            const unsigned *pc = reinterpret_cast<const unsigned *>(t_cod + trow * DSM_TILE_GW + DSM_TILE_GX + tcol); // 4-byte aligned
+            const unsigned cw[4] = {pc[0], pc[1], pc[2], pc[3]};
+            mm = member_mask16(cw, r);
             const float4 *pz = reinterpret_cast<const float4 *>(t_dep + trow * DSM_TILE_W + tcol);
 #pragma unroll
             for (int qd = 0; qd < 4; qd++)
             {
-                const int4 a = pl[qd];
                 const float4 z = pz[qd];
-                mm |= ((a.x == s ? 1u : 0u) | (a.y == s ? 2u : 0u) | (a.z == s ? 4u : 0u) | (a.w == s ? 8u : 0u)) << (4 * qd);
                 const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
                 for (int j = 0; j < 4; j++)
