@@ -235,11 +235,11 @@ def kernel_alg_bytes(name, P, S, npool, nnew):
     0.8 P = plane-fit inliers (measured shares of the benchmark frames)."""
     return {
         "seed_init": 5 * S + 36 * S,
-        "slic_assign_first": (1 + 4) * P + (4 + 4) * P + 24 * S,   # gray + depth in, inverse depth + labels out, seeds
-        "slic_assign": (1 + 4 + 4) * P + 28 * S,                   # gray + inverse depth + labels in (labels rewritten where they change), seeds + flags
-        "slic_gather": 9 * P + 4 * S + 20 * S + 4 * 0.9 * P,       # labels + depth + gray in, integer sums + ordered depth lists out
+        "slic_assign_first": (1 + 4) * P + (4 + 4 + 1) * P + 24 * S,  # gray + depth in, inverse depth + labels + label codes out, seeds
+        "slic_assign": (1 + 4 + 1) * P + 28 * S,                   # gray + inverse depth + label codes in (labels / codes rewritten where they change), seeds + flags
+        "slic_gather": 6 * P + 4 * S + 20 * S + 4 * 0.9 * P,       # label codes + depth + gray in, integer sums + ordered depth lists out
         "slic_newton": 4 * 0.9 * P + 24 * S + 52 * S,              # lists + sums in, seed state out
-        "plane_gather": 8 * P + 16 * S + 12 * 0.8 * P + (32 + 192) * S,  # labels + depth in, centred points + per-seed sums out
+        "plane_gather": 5 * P + 16 * S + 12 * 0.8 * P + (32 + 192) * S,  # label codes + depth in, centred points + per-seed sums out
         "plane_solve": (32 + 192 + 16) * S + 48 * S,
         "surfel_fuse": 88 * npool + 48 * S,
         "surfel_init": 52 * S + 44 * nnew,

@@ -548,8 +548,14 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton2(const __grid_constant__ Dsm
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x * NW_T + tid;
     const size_t so = (size_t)b * d.S;
-    const bool act = s < d.S && d.tstable[so + s] != DSM_STABLE; // stable seeds are untouched by update_seeds (:478-479)
-    const int nd = act ? d.und[so + s] : 0;
+    // the four per-seed loads are independent and issued together (one memory round trip), before the list staging
+    const bool inr = s < d.S;
+    const int tflag = inr ? d.tstable[so + s] : DSM_STABLE;
+    const int nd_raw = inr ? d.und[so + s] : 0;
+    const int4 su = inr ? d.usum[so + s] : make_int4(0, 0, 0, 0);
+    const float4 pre = inr ? d.seed[so + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool act = tflag != DSM_STABLE; // stable seeds are untouched by update_seeds (:478-479)
+    const int nd = act ? nd_raw : 0;
     {
         const int len4 = (nd + 3) & ~3;
         int wtot;
@@ -578,7 +584,6 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton2(const __grid_constant__ Dsm
     // classification loop is never executed by a warp in which one lane needs it and 31 wait.
     if (act)
     {
-        const int4 su = d.usum[so + s];
         const int n = su.x;
         if (n == 0)
         { // unreachable for supported shapes (every seed keeps its centre pixel); recorded, never silently ignored
@@ -591,7 +596,6 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton2(const __grid_constant__ Dsm
             const float mi = (float)su.w / fn;
             const float mx = (float)su.y / fn;
             const float my = (float)su.z / fn;
-            const float4 pre = d.seed[so + s];
             // ::fabs(double): float differences, summed in double, rounded once (:527)
             const float diff = (float)(fabs((double)(pre.z - mi)) + fabs((double)(pre.x - mx)) + fabs((double)(pre.y - my)));
             const bool newstable = diff < F_0p2_HI; // (double)diff < 0.2 (:528)
@@ -699,9 +703,9 @@ __global__ void __launch_bounds__(NW_T, 8) k_newton_hard(const __grid_constant__
         for (int j4 = 0; 4 * j4 < nd; j4++) __pipeline_memcpy_async(dst + j4, src + j4, 16);
     }
     __pipeline_commit();
+    const float4 st = d.pfsum[(so + s) * 2], mn = d.pfsum[(so + s) * 2 + 1]; // in flight together with the list copies
     __pipeline_wait_prior(0);
     if (!act) return;
-    const float4 st = d.pfsum[(so + s) * 2], mn = d.pfsum[(so + s) * 2 + 1];
     const float *dl = s_off[tid] >= 0 ? buf + s_off[tid] : d.dlist + (so + s) * DL_STRIDE; // generic: shared or global
     const float4 *dl4 = reinterpret_cast<const float4 *>(dl);
     float md = st.x;
