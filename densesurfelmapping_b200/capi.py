@@ -30,7 +30,7 @@ EXPORTS = [
     "dsm_inactive_reserve", "dsm_inactive_retire", "dsm_inactive_reactivate", "dsm_inactive_transform", "dsm_inactive_export_cloud",
     "dsm_inactive_download", "dsm_inactive_size",
     "dsm_comm_unique_id", "dsm_comm_init", "dsm_comm_destroy", "dsm_gather_deltas", "dsm_gather_wait", "dsm_gathered_device",
-    "dsm_gathered_rank_bytes", "dsm_gathered_download", "dsm_set_constants",
+    "dsm_gathered_rank_bytes", "dsm_gathered_download", "dsm_set_constants", "dsm_set_concurrency",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library():
     L.dsm_write_ply_mesh.argtypes = [ctypes.c_char_p, vp, cs]
     L.dsm_mesh_vertices.argtypes = [vp, cs, vp]
     L.dsm_set_constants.argtypes = [vp, ctypes.POINTER(DsmConstants)]
+    L.dsm_set_concurrency.argtypes = [vp, ctypes.c_int]
     L.dsm_comm_unique_id.argtypes = [vp]
     L.dsm_comm_init.argtypes = [vp, vp, ci, ci]
     L.dsm_comm_destroy.argtypes = [vp]
@@ -243,6 +244,10 @@ class Context:
         """(huber_range, baseline, disparity_error, min_tolerate_diff): CONSTANTS_DRIVE (default) or CONSTANTS_RGBD."""
         k = DsmConstants(*constants)
         self._ck(self.lib.dsm_set_constants(self.h, ctypes.byref(k)))
+
+    def set_concurrency(self, sub_batches: int):
+        """Concurrent sub-batches of batch_run (1..4, default 2); 1 for clean per-kernel profile durations."""
+        self._ck(self.lib.dsm_set_concurrency(self.h, int(sub_batches)))
 
     # ---- multi-GPU gather of the surfel deltas (csrc/dsm_comm.cu) ----
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):

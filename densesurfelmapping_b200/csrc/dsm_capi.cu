@@ -55,6 +55,7 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
     for (int i = 0; i < 4; i++)
         if (ctx->s_comp[i]) cudaStreamSynchronize(ctx->s_comp[i]);
+    if (ctx->s_hi) cudaStreamSynchronize(ctx->s_hi);
     if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &r : ctx->prof_pending)
@@ -112,12 +113,17 @@ extern "C" void dsm_destroy(dsm_ctx *ctx)
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     for (int i = 0; i < 4; i++)
         if (ctx->s_comp[i]) cudaStreamDestroy(ctx->s_comp[i]);
+    if (ctx->s_hi) cudaStreamDestroy(ctx->s_hi);
+    if (ctx->ev_p2) cudaEventDestroy(ctx->ev_p2);
     for (int i = 0; i < 8; i++)
     {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     cudaFreeHost(ctx->h_pose);
     cudaFreeHost(ctx->h_ofs);
     cudaFreeHost(ctx->h_ref);
@@ -222,6 +228,12 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
     ctx->s_h2d = ctx->s_d2h = nullptr;
     for (int i = 0; i < 4; i++) ctx->s_comp[i] = nullptr;
     ctx->ev_start = nullptr;
+    ctx->ev_fork = nullptr;
+    ctx->s_hi = nullptr;
+    ctx->ev_p2 = nullptr;
+    for (int i = 0; i < 4; i++) ctx->ev_join[i] = nullptr;
+    ctx->run_split = 2;
+    ctx->single_pending = false;
     for (int i = 0; i < 8; i++) ctx->ev_h2d[i] = ctx->ev_done[i] = nullptr;
     ctx->gray_packed = nullptr;
     ctx->res_upper = 0;
@@ -314,6 +326,15 @@ extern "C" int dsm_create(const dsm_params *params, int device, void *cuda_strea
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_p2, cudaEventDisableTiming);
+    if (e == cudaSuccess)
+    {
+        int least = 0, greatest = 0;
+        e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->s_hi, cudaStreamNonBlocking, greatest);
+    }
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess)
     { // back-projection factor tables: the same float ops as back_project (fusion_functions.cpp:94-95)
         std::vector<float> hx((size_t)Wp + 16), hy((size_t)H + 16);
@@ -597,7 +618,7 @@ static int enqueue_schedule(dsm_ctx *ctx, int f0, int nf, int maxper, cudaStream
         {
             DsmDev d = ctx->d;
             d.frame0 = f0;
-            dsm_launch_pool_compact(d, f0, maxper, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, st);
+            dsm_launch_pool_compact(d, f0, maxper, ctx->blkcnt, ctx->blkofs, ctx->newofs, ctx->pool_snap, ctx->res_ofs, st);
         }
         return DSM_OK;
     };
@@ -648,12 +669,39 @@ extern "C" int dsm_batch_run(dsm_ctx *ctx)
     if (!ctx) return DSM_E_INVALID;
     if (!ctx->uploaded) return DSM_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    // (Running the batch in L2-sized sub-batches was measured and is slower: 8 / 16 frames per pass through the schedule
-    // take 1.70 / 1.29 ms per 32 frames against 1.08 ms for the whole batch -- the kernels are issue- or latency-bound,
-    // not DRAM-bound, and smaller launches fill the GPU worse.  profiles/README.md, history.)
-    int rc = enqueue_schedule(ctx, 0, ctx->nb, ctx->d.max_pool_per_frame, ctx->stream);
-    if (rc != DSM_OK) return rc;
+    // The frames of a batch are independent, and most kernels of the schedule are issue- or latency-bound rather than
+    // DRAM-bound: two sub-batches run CONCURRENTLY on two streams fill each other's tails and stalls (measured: 32 frames
+    // as 2 x 16 concurrent take less time than 1 x 32).  Running sub-batches one after the other to stay inside L2 was
+    // also measured and is slower (8 / 16 frames per pass: 1.70 / 1.29 ms per 32 frames against 1.08 ms); profiles/README.md.
+    const int parts = (ctx->stop_after > 0 || ctx->nb < 8) ? 1 : (ctx->run_split < ctx->nb ? ctx->run_split : ctx->nb);
+    if (parts <= 1)
+    {
+        int rc = enqueue_schedule(ctx, 0, ctx->nb, ctx->d.max_pool_per_frame, ctx->stream);
+        if (rc != DSM_OK) return rc;
+    }
+    else
+    {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        int f0 = 0;
+        for (int i = 0; i < parts; i++)
+        {
+            const int nf = (ctx->nb - f0 + (parts - i) - 1) / (parts - i);
+            CK(cudaStreamWaitEvent(ctx->s_comp[i], ctx->ev_fork, 0));
+            int rc = enqueue_schedule(ctx, f0, nf, ctx->d.max_pool_per_frame, ctx->s_comp[i]);
+            if (rc != DSM_OK) return rc;
+            CK(cudaEventRecord(ctx->ev_join[i], ctx->s_comp[i]));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+            f0 += nf;
+        }
+    }
     ctx->ran = true;
+    return DSM_OK;
+}
+
+extern "C" int dsm_set_concurrency(dsm_ctx *ctx, int sub_batches)
+{
+    if (!ctx || sub_batches < 1 || sub_batches > 4) return DSM_E_INVALID;
+    ctx->run_split = sub_batches;
     return DSM_OK;
 }
 
@@ -1074,8 +1122,8 @@ extern "C" int dsm_fuse_frame_resident(dsm_ctx *ctx, int ref_idx, const uint8_t 
         if (rc != DSM_OK) return rc;
     }
     ctx->ran = true;
-    CK(cudaMemcpyAsync(ctx->res_ofs + 1, ctx->newofs + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream)); // (the compaction's last kernel stored the new pool size in res_ofs[1])
+    ctx->single_pending = true;
     {
         dsm_surfel_t *t = ctx->d.pool;
         ctx->d.pool = ctx->pool_snap;
@@ -1300,9 +1348,16 @@ extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_
     const int e = 6 + par; // events 6/7: this half's staging buffers and pinned tables are free again
     CK(cudaEventSynchronize(ctx->ev_done[e]));
     if (!dbl) CK(cudaEventSynchronize(ctx->ev_done[6 + (1 - par)]));
-    // single-frame calls (dsm_fuse_frame_resident) may still be running out of the same staging buffers
-    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[0], 0));
-    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[1], 0));
+    // single-frame calls (dsm_fuse_frame_resident) may still be running out of the same staging buffers and frame slots
+    // 0 / 1 (only then: the events are also recorded at the end of every run of this function, and waiting for the
+    // previous run here would serialise this run's copies behind it)
+    const bool after_single = ctx->single_pending;
+    ctx->single_pending = false;
+    if (after_single)
+    {
+        CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[0], 0));
+        CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[1], 0));
+    }
     const size_t so = (size_t)par * (size_t)(ctx->p.max_batch / 2); // fixed halves: runs of different length never overlap
     // pinned tables of this mode live in the second half of h_pose / h_ref (the first half belongs to the single-frame
     // and batch calls, which only wait for their own copies before rewriting it); this half's previous table copy ran
@@ -1320,35 +1375,49 @@ extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_
     CK(cudaMemcpyAsync(dp, depth, (size_t)n * fpx * sizeof(float), cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaEventRecord(ctx->ev_h2d[e], ctx->s_h2d));
     cudaStream_t st = ctx->stream;
-    // the small tables go on the compute stream: the previous run's kernels read the same device tables
-    CK(cudaMemcpy2DAsync(ctx->pose, 16 * sizeof(float), ctx->h_pose + ho * 32, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpy2DAsync(ctx->ipose, 16 * sizeof(float), ctx->h_pose + ho * 32 + 16, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->refidx, ctx->h_ref + ho, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamWaitEvent(st, ctx->ev_h2d[e], 0));
+    // Phase 1 (superpixels, normals, plane fits of all n frames; never touches the pool) runs on a side stream and in this
+    // half's own frame slots [so, so + n): it overlaps the frame-by-frame phase 2 of the PREVIOUS run, which owns the
+    // other half's slots and the main stream.  (With a single half, so == 0 and everything is ordered on the main stream.)
+    // Phase 2 is a chain of small launches per frame: next to phase 1's full-width grids its CTAs would queue behind a
+    // wave of theirs at every launch, so it runs on the context's highest-priority stream (forked from / joined into the
+    // main stream, which keeps the order with every other call on the context).
+    cudaStream_t s1 = dbl ? ctx->s_comp[par] : st;
+    cudaStream_t s2 = dbl ? ctx->s_hi : st;
+    const int slot0 = (int)so;
+    if (dbl)
+    { // this half's slots and device tables were last read by the phase 2 of the run before the previous one
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+        CK(cudaStreamWaitEvent(s1, ctx->ev_done[e], 0));
+    }
+    CK(cudaMemcpy2DAsync(ctx->pose + (size_t)slot0 * 16, 16 * sizeof(float), ctx->h_pose + ho * 32, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, s1));
+    CK(cudaMemcpy2DAsync(ctx->ipose + (size_t)slot0 * 16, 16 * sizeof(float), ctx->h_pose + ho * 32 + 16, 32 * sizeof(float), 16 * sizeof(float), n, cudaMemcpyHostToDevice, s1));
+    CK(cudaMemcpyAsync(ctx->refidx + slot0, ctx->h_ref + ho, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s1));
+    CK(cudaStreamWaitEvent(s1, ctx->ev_h2d[e], 0));
     {
         DsmDev d = ctx->d;
-        d.frame0 = 0;
-        ProfScope p(ctx, DSM_K_REPACK);
-        dsm_launch_repack(d, n, gp, dp, st);
+        d.frame0 = slot0;
+        ProfScope p(ctx, DSM_K_REPACK, s1);
+        dsm_launch_repack(d, n, gp, dp, s1);
     }
-    ctx->nb = n;
+    ctx->nb = slot0 + n;
     ctx->uploaded = true;
     const int32_t *saved = ctx->d.poolofs;
-    // phase 1: all n frames at once (never touches the pool)
-    int rc = enqueue_schedule(ctx, 0, n, 0, st, false, 1);
+    // phase 1: all n frames at once
+    int rc = enqueue_schedule(ctx, slot0, n, 0, s1, false, 1);
+    if (dbl && rc == DSM_OK)
+    {
+        CK(cudaEventRecord(ctx->ev_join[par], s1));
+        CK(cudaStreamWaitEvent(s2, ctx->ev_join[par], 0));
+    }
     // phase 2: frame by frame on the resident pool, compaction into the alternate buffer, swap
     for (int t = 0; t < n && rc == DSM_OK; t++)
     {
-        ctx->d.poolofs = ctx->res_ofs - t; // kernels read poolofs[b], poolofs[b+1] with b == t
+        ctx->d.poolofs = ctx->res_ofs - (slot0 + t); // kernels read poolofs[b], poolofs[b+1] with b == slot0 + t
         int upq = (ctx->res_upper + 65535) / 65536 * 65536;
         if (upq > ctx->p.max_local_surfels) upq = ctx->p.max_local_surfels;
-        rc = enqueue_schedule(ctx, t, 1, upq, st, true, 2);
+        rc = enqueue_schedule(ctx, slot0 + t, 1, upq, s2, true, 2);
         if (rc != DSM_OK) break;
-        if (cudaMemcpyAsync(ctx->res_ofs + 1, ctx->newofs + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        {
-            rc = DSM_E_CUDA;
-            break;
-        }
         dsm_surfel_t *tmp = ctx->d.pool;
         ctx->d.pool = ctx->pool_snap;
         ctx->pool_snap = tmp;
@@ -1357,6 +1426,11 @@ extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_
     ctx->d.poolofs = saved;
     if (rc != DSM_OK) return rc;
     ctx->ran = true;
+    if (dbl)
+    {
+        CK(cudaEventRecord(ctx->ev_p2, s2));
+        CK(cudaStreamWaitEvent(st, ctx->ev_p2, 0));
+    }
     CK(cudaEventRecord(ctx->ev_done[e], st));
     CK(cudaEventRecord(ctx->ev_done[0], st)); // dsm_fuse_frame_resident waits on these before reusing slot 0 / 1
     CK(cudaEventRecord(ctx->ev_done[1], st));
@@ -1365,7 +1439,7 @@ extern "C" int dsm_fuse_stream_resident(dsm_ctx *ctx, int n, const int32_t *ref_
     CK(cudaEventSynchronize(ctx->ev_h2d[e]));
     if (n_new)
     {
-        CK(cudaMemcpyAsync(n_new, ctx->d.nnew, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(n_new, ctx->d.nnew + slot0, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
     return DSM_OK;

@@ -52,6 +52,8 @@ struct dsm_ctx
     uint8_t *gray_packed; // [B][H][W]
     float *depth_packed;  // [B][H][W]
     cudaStream_t s_h2d, s_d2h, s_comp[4];
+    cudaStream_t s_hi;   // highest priority: the frame-by-frame (latency-bound) phase of dsm_fuse_stream_resident
+    cudaEvent_t ev_p2;   // end of that phase, joined into the main stream
     // resident pool (stream mode)
     int res_upper;      // host-side upper bound of the resident pool size (exact after a sync)
     bool res_active;
@@ -70,6 +72,9 @@ struct dsm_ctx
     };
     std::vector<InactSeg> inact_segs;
     cudaEvent_t ev_h2d[8], ev_done[8], ev_start;
+    cudaEvent_t ev_fork, ev_join[4]; // dsm_batch_run: fork / join of the concurrent sub-batches
+    bool single_pending;             // a dsm_fuse_frame_resident call since the last dsm_fuse_stream_resident (they share frame slots 0 / 1)
+    int run_split;                   // sub-batches per dsm_batch_run (dsm_set_concurrency)
     // pinned host staging for the small per-batch tables
     float *h_pose; // [B][32]: pose then inverse
     int32_t *h_ofs;

@@ -123,7 +123,7 @@ void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s);
 void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, int raw_md, cudaStream_t s);
-void dsm_launch_pool_compact(const DsmDev &d, int frame, int upper, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, cudaStream_t s);
+void dsm_launch_pool_compact(const DsmDev &d, int frame, int upper, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, int32_t *ofs_out, cudaStream_t s);
 void dsm_launch_pool_transform(const DsmDev &d, int frame, int upper, const float *Wm_dev, cudaStream_t s);
 void dsm_launch_pool_export(const DsmDev &d, int frame, int upper, int mode, int key, bool as_cloud, int *blkcnt, int *blkofs, int *newofs, void *dst, cudaStream_t s);
 void dsm_launch_set2(int32_t *p, int a, int b, cudaStream_t s);

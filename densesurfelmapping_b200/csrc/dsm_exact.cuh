@@ -14,6 +14,40 @@
 
 #define FULL 0xffffffffu
 
+// ---- programmatic dependent launch (PDL) ----
+// The per-frame schedule is a chain of kernels on one stream, each consuming its predecessor's output.  Every kernel
+// of the chain starts with pdl_enter(): griddepcontrol.wait returns once the preceding grid has completed and its
+// writes are visible (a no-op for a launch without the attribute); griddepcontrol.launch_dependents then lets the NEXT
+// grid of the chain be set up -- its CTAs become resident as SM resources free up in this grid's last wave and wait at
+// their own griddepcontrol.wait -- so the launch latency and the CTA ramp of the next kernel overlap this kernel's tail.
+// Safe by construction: no kernel touches global memory before the wait, and a kernel is only launched with the
+// attribute (pdl_launch) if it begins with pdl_enter().
+#ifndef DSM_PDL
+#define DSM_PDL 1
+#endif
+__device__ __forceinline__ void pdl_enter()
+{
+#if DSM_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+static inline void pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+#if DSM_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+#else
+    kern<<<grid, block, smem, s>>>(args...);
+#endif
+}
+
 // Comparisons of a float against a double literal (the reference promotes the float): for a
 // literal c that is not a float, with c_lo/c_hi the neighbouring floats,
 //   (double)x <  c  <=>  x <  c_hi        (double)x >  c  <=>  x >  c_lo

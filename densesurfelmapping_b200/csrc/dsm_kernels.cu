@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) k_repack(const __grid_constant__ DsmDev d
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_seed_init(const __grid_constant__ DsmDev d)
 {
+    pdl_enter();
     const int b = d.frame0 + blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -187,6 +188,7 @@ __device__ __forceinline__ float get_weight(float depth)
 #define FUSE_BLOCK 256
 __global__ void __launch_bounds__(FUSE_BLOCK) k_fuse(const __grid_constant__ DsmDev d)
 {
+    pdl_enter();
     __shared__ alignas(128) float sm[FUSE_BLOCK * 11];
     __shared__ float s_pose[32];
 #pragma nv_diag_suppress static_var_with_dynamic_init
@@ -295,6 +297,7 @@ __device__ __forceinline__ bool init_emits(const DsmDev &d, size_t so, int s)
 }
 __global__ void __launch_bounds__(1024) k_init_surfels(const __grid_constant__ DsmDev d)
 {
+    pdl_enter();
     __shared__ int s_warp[32];
     __shared__ int s_before[32];
     __shared__ float s_pose[16];
@@ -369,6 +372,7 @@ __device__ __forceinline__ bool pool_pred(const dsm_surfel_t &e, int mode, int k
 
 __global__ void __launch_bounds__(256) k_pool_count(const __grid_constant__ DsmDev d, int b, int *blkcnt, int mode, int key)
 {
+    pdl_enter();
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
     const int i = begin + blockIdx.x * 256 + threadIdx.x;
     const bool live = i < end && pool_pred(d.pool[i], mode, key);
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(256) k_pool_count(const __grid_constant__ DsmD
 
 __global__ void __launch_bounds__(1024) k_pool_scan(const __grid_constant__ DsmDev d, int b, const int *blkcnt, int *blkofs, int *newofs)
 {
+    pdl_enter();
     __shared__ int s_warp[32];
     __shared__ int s_run;
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
@@ -415,6 +420,7 @@ __global__ void __launch_bounds__(1024) k_pool_scan(const __grid_constant__ DsmD
 
 __global__ void __launch_bounds__(256) k_pool_scatter(const __grid_constant__ DsmDev d, int b, const int *blkofs, dsm_surfel_t *dst, int mode, int key)
 {
+    pdl_enter();
     __shared__ int s_warp[8];
     const int begin = d.poolofs[b], end = d.poolofs[b + 1];
     const int i = begin + blockIdx.x * 256 + threadIdx.x;
@@ -463,11 +469,13 @@ __global__ void __launch_bounds__(256) k_pool_scatter_cloud(const __grid_constan
     if (live) dst[blkofs[blockIdx.x] + wofs + __popc(bal & ((1u << lane) - 1))] = pt;
 }
 
-__global__ void __launch_bounds__(256) k_pool_append(const __grid_constant__ DsmDev d, int b, const int *newofs, dsm_surfel_t *dst)
+__global__ void __launch_bounds__(256) k_pool_append(const __grid_constant__ DsmDev d, int b, const int *newofs, dsm_surfel_t *dst, int32_t *ofs_out)
 {
+    pdl_enter();
     const int n = d.nnew[b];
     const int j = blockIdx.x * 256 + threadIdx.x;
     if (j < n) dst[newofs[0] + j] = d.newsurf[(size_t)b * d.S + j];
+    if (j == 0 && ofs_out) ofs_out[1] = newofs[1]; // nothing in this grid reads the pool's offset table
 }
 
 #define XF_BLOCK 256
@@ -544,31 +552,32 @@ void dsm_launch_repack(const DsmDev &d, int nb, const uint8_t *gray_packed, cons
 void dsm_launch_seed_init(const DsmDev &d, int nb, cudaStream_t s)
 {
     dim3 grid((d.S + 255) / 256, nb);
-    k_seed_init<<<grid, 256, 0, s>>>(d);
+    pdl_launch(k_seed_init, grid, dim3(256), 0, s, d);
 }
 void dsm_launch_fuse(const DsmDev &d, int nb, cudaStream_t s)
 {
     if (d.max_pool_per_frame <= 0) return;
     dim3 grid((d.max_pool_per_frame + FUSE_BLOCK - 1) / FUSE_BLOCK, nb);
-    k_fuse<<<grid, FUSE_BLOCK, 0, s>>>(d);
+    pdl_launch(k_fuse, grid, dim3(FUSE_BLOCK), 0, s, d);
 }
 void dsm_launch_init_surfels(const DsmDev &d, int nb, cudaStream_t s)
 {
     dim3 grid((d.S + 1023) / 1024, nb);
-    k_init_surfels<<<grid, 1024, 0, s>>>(d);
+    pdl_launch(k_init_surfels, grid, dim3(1024), 0, s, d);
 }
 void dsm_launch_seeds_export(const DsmDev &d, int frame, dsm_seed_t *out_dev, int raw_md, cudaStream_t s)
 {
     k_seeds_export<<<(d.S + 255) / 256, 256, 0, s>>>(d, frame, out_dev, raw_md);
 }
 
-void dsm_launch_pool_compact(const DsmDev &d, int frame, int upper, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, cudaStream_t s)
+// ofs_out (may be null): the resident pool's offset table {0, n}; the last kernel of the chain stores the new size there
+void dsm_launch_pool_compact(const DsmDev &d, int frame, int upper, int *blkcnt, int *blkofs, int *newofs, dsm_surfel_t *dst, int32_t *ofs_out, cudaStream_t s)
 {
     const int nblk = (upper + 255) / 256;
-    if (nblk > 0) k_pool_count<<<nblk, 256, 0, s>>>(d, frame, blkcnt, 0, 0);
-    k_pool_scan<<<1, 1024, 0, s>>>(d, frame, blkcnt, blkofs, newofs);
-    if (nblk > 0) k_pool_scatter<<<nblk, 256, 0, s>>>(d, frame, blkofs, dst, 0, 0);
-    k_pool_append<<<(d.S + 255) / 256, 256, 0, s>>>(d, frame, newofs, dst);
+    if (nblk > 0) pdl_launch(k_pool_count, dim3(nblk), dim3(256), 0, s, d, frame, blkcnt, 0, 0);
+    pdl_launch(k_pool_scan, dim3(1), dim3(1024), 0, s, d, frame, (const int *)blkcnt, blkofs, newofs);
+    if (nblk > 0) pdl_launch(k_pool_scatter, dim3(nblk), dim3(256), 0, s, d, frame, (const int *)blkofs, dst, 0, 0);
+    pdl_launch(k_pool_append, dim3((d.S + 255) / 256), dim3(256), 0, s, d, frame, (const int *)newofs, dst, ofs_out);
 }
 // move_add_surfels, removal half (surfel_map.cpp:1479-1497): the live surfels whose last_update == key are
 // copied in pool order to dst (count in newofs[0]) and flagged dead in the pool

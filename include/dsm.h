@@ -124,6 +124,12 @@ typedef struct dsm_constants
 #define DSM_CONSTANTS_RGBD {0.05, 0.08, 1.0, 0.05} /* fusion_functions.h:18-21, the commented RGB-D / VINS set */
 int dsm_set_constants(dsm_ctx *ctx, const dsm_constants *constants);
 
+/* dsm_batch_run executes a resident batch as `sub_batches` (1..4) groups of frames on concurrent CUDA streams; results do
+ * not depend on it (frames are independent).  Default 2: most kernels of the schedule are issue- or latency-bound, two
+ * concurrent half-batches fill each other's tails.  1 = the whole batch as one launch sequence (what per-kernel timing
+ * with dsm_profile_* should use: concurrent kernels share the SMs and stretch each other's event-pair durations). */
+int dsm_set_concurrency(dsm_ctx *ctx, int sub_batches);
+
 /* ---- reference-identical single-frame call ----
  * Replaces FusionFunctions::fuse_initialize_map (fusion_functions.cpp:30-83) with the same
  * semantics: `gray` is CV_8UC1 (row pitch gray_pitch bytes), `depth` CV_32FC1 metres (row

@@ -44,9 +44,8 @@ def test_single_rank_gather_equals_batch_download():
 
 
 def _worker(rank, world, uid_q, res_q):
-    import torch
+    # no torch in these processes: the library then loads the system NCCL, as in a plain C++ host process
     from densesurfelmapping_b200 import capi
-    torch.cuda.set_device(rank)
     if rank == 0:
         uid = capi.comm_unique_id()
         for _ in range(world - 1):
@@ -63,11 +62,20 @@ def _worker(rank, world, uid_q, res_q):
     ctx.close()
 
 
+def _gpu_count():
+    import subprocess
+    try:
+        return len([l for l in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout.splitlines() if l.startswith("GPU ")])
+    except Exception:
+        return 0
+
+
 def test_two_rank_gather_over_nccl():
-    import torch
-    if torch.cuda.device_count() < 2:
+    # (torch is deliberately not imported here: this process may already hold the system NCCL from the single-rank test,
+    # and a PyTorch that loads after it would bind to that one instead of its own -- INTEGRATION.md, "NCCL in a PyTorch process")
+    if _gpu_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
-    import torch.multiprocessing as mp
+    import multiprocessing as mp
     mpc = mp.get_context("spawn")
     uid_q, res_q = mpc.Queue(), mpc.Queue()
     procs = [mpc.Process(target=_worker, args=(r, 2, uid_q, res_q)) for r in range(2)]

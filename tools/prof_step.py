@@ -1,4 +1,5 @@
-"""Minimal driver for ncu: uploads one batch of KITTI-shaped frames and runs N resident steps."""
+"""Minimal driver for ncu: uploads one batch of KITTI-shaped frames and runs N resident steps (one launch sequence per
+step; the production default runs two half-batches concurrently, which a profiler serialises anyway)."""
 import sys, os
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,6 +14,7 @@ cam = synth.KITTI
 S = (cam.width // 8) * (cam.height // 8)
 prev, cur = bench.make_batch(cam, B, 0)
 ctx = capi.Context(cam, max_batch=B, max_local_surfels=B * S + 64)
+ctx.set_concurrency(1)  # the whole batch as one launch sequence: 17 full-width launches per step, as in bench.py's per-kernel table
 _, pools = ctx.fuse_batch([0] * B, np.stack([f[0] for f in prev]), np.stack([f[1] for f in prev]), np.stack([f[2] for f in prev]),
                           np.zeros(0, SURFEL_DTYPE), np.zeros(B + 1, np.int32))
 ofs = np.concatenate([[0], np.cumsum([len(p) for p in pools])]).astype(np.int32)
