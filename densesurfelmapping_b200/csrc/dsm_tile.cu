@@ -123,54 +123,6 @@ __device__ __forceinline__ float pick4(float a0, float a1, float a2, float a3, i
 // (1 byte per pixel, and the test is a byte compare with a pattern that depends on the window position only).
 #define DSM_CODE_NONE 4
 
-// The reference's cost expression, candidate order and strict '<' (first wins) for the pixels of one thread that the
-// fp32 filter could not decide (bit i of `uncertain`); returns the four winner codes packed into bytes.  Each lane walks
-// its OWN flagged pixels, so a warp pays max-per-lane (usually one) exact evaluations, not one per pixel slot.
-__device__ __noinline__ unsigned assign_exact(const DsmDev &d, size_t so, int sidx0, unsigned exm, bool rk, int rx0, int x4, int y,
-                                              unsigned uncertain, float4 g, float4 v, unsigned wcp)
-{
-    SeedC sc[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-    {
-        const int li = ((exm >> c) & 1u) ? sidx0 + (c & 1) * d.spw + (c >> 1) : 0;
-        const float4 s4 = d.seed[so + li];
-        sc[c].x = s4.x, sc[c].y = s4.y, sc[c].I = s4.z, sc[c].md = s4.w;
-        sc[c].inv = d.inv_md[so + li]; // 1.0 / (double)mean_depth, only consumed when mean_depth > 0 (:378)
-    }
-    const float fy = (float)y;
-    while (uncertain)
-    {
-        const int i = __ffs(uncertain) - 1;
-        uncertain &= uncertain - 1;
-        const float fx = (float)(x4 + i);
-        const float my_i = pick4(g.x, g.y, g.z, g.w, i);
-        const float my_inv = pick4(v.x, v.y, v.z, v.w, i);
-        const double my_inv_d = (double)my_inv;
-        float min_d = 1e6f, min_nd = 1e6f;
-        int idx_d = DSM_CODE_NONE, idx_nd = DSM_CODE_NONE; // the reference's -1 (:409-411)
-        bool all_has_depth = true;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-        {
-            const bool valid = ((exm >> c) & 1u) && !((c & 1) && rk) && !((c >> 1) && rx0 == 4 && i == 0);
-            float cnd, cdd;
-            const bool has = calc_cost(sc[c], my_i, my_inv, my_inv_d, fx, fy, cnd, cdd);
-            cdd = valid ? cdd : __int_as_float(0x7f800000);
-            cnd = valid ? cnd : __int_as_float(0x7f800000);
-            all_has_depth &= has || !valid;
-            const bool bd = cdd < min_d, bn = cnd < min_nd;
-            min_d = bd ? cdd : min_d;
-            idx_d = bd ? c : idx_d;
-            min_nd = bn ? cnd : min_nd;
-            idx_nd = bn ? c : idx_nd;
-        }
-        const unsigned wv = (unsigned)(all_has_depth ? idx_d : idx_nd);
-        wcp = (wcp & ~(255u << (8 * i))) | (wv << (8 * i));
-    }
-    return wcp;
-}
-
 template <bool FIRST>
 __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmDev d)
 {
@@ -178,184 +130,209 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
     __shared__ int s_last;
     const int b = d.frame0 + blockIdx.z;
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
-    const int y0 = (blockIdx.y * 4 + threadIdx.y) * 2; // a thread owns 4 x 2 pixels: rows y0, y0 + 1 lie in the same half of an 8-row cell
+    const int y = blockIdx.y * 4 + threadIdx.y;
     const int lane = threadIdx.x & 31;
-    const bool active = (x4 < d.W) && (y0 < d.H);
+    const bool active = (x4 < d.W) && (y < d.H);
 
     const size_t fo = (size_t)b * d.px_stride;
     const size_t so = (size_t)b * d.S;
-    const int spw = d.spw;
-    int sidx0 = 0; // seed index of candidate 0; candidate c = sidx0 + (c & 1) * spw + (c >> 1)
-    // Candidate operands, shared by the thread's 8 pixels.  A pixel with x%8 = r passes the |8c+4-x| < 8 test (:418-420)
-    // only for seed columns {b-1,b} (r<4), {b} (r=4), {b,b+1} (r>4), likewise for rows: at most 2 x 2 of the reference's
-    // 3 x 3 candidates exist, candidate c = 2*ix + iy -> (xa,ya) (xa,yb) (xb,ya) (xb,yb): dx outer, dy inner (:413-414).
-    // Coordinates are pre-scaled by 1/4 (exact), so that dist/16 (:374) is ax'^2 + ay'^2; a candidate that does not
-    // exist sits 1e18 away: its cost (~1e36, finite) is never the minimum and the filter arithmetic stays NaN-free.
-    // The pixel at x%8 == 4 sees only its own seed column and the row y%8 == 4 only its own seed row: the other
-    // column / row is pushed away for that pixel / row only.
-    float sxq[4], syq[4], sI[4], shi[4], slo[4];
-    bool ex[4] = {false, false, false, false}; // candidate exists (inside the seed grid)
-    bool mdp[4] = {true, true, true, true};    // mean_depth > 0 (:378), or the candidate does not exist
-    const int rx0 = x4 & 7;
+    int wc[4] = {DSM_CODE_NONE, DSM_CODE_NONE, DSM_CODE_NONE, DSM_CODE_NONE}; // winner of every pixel as a candidate code
+    int oc[4] = {0, 0, 0, 0};                                                 // current label as a candidate code
+    int sidx0 = 0;                                                            // seed index of candidate 0; candidate c = sidx0 + (c & 1) * spw + (c >> 1)
     if (active)
     {
-        const int bx = x4 >> 3, by = y0 >> 3, ry0 = y0 & 7;
+        const size_t po = fo + (size_t)y * d.Wp + x4;
+        const uchar4 g4 = *reinterpret_cast<const uchar4 *>(d.gray + po);
+        float iv[4];
+        if (FIRST)
+        { // (:404-405) my_inv = (float)(1.0 / (double)depth) for depth > 0.01: 53 >= 2*24+2 bits, so the double rounding is
+          // innocuous and the correctly rounded float reciprocal is the same value (-ftz=false: subnormals included)
+            const float4 z4 = *reinterpret_cast<const float4 *>(d.depth + po);
+            iv[0] = (z4.x > F_0p01_LO) ? __frcp_rn(z4.x) : 0.0f;
+            iv[1] = (z4.y > F_0p01_LO) ? __frcp_rn(z4.y) : 0.0f;
+            iv[2] = (z4.z > F_0p01_LO) ? __frcp_rn(z4.z) : 0.0f;
+            iv[3] = (z4.w > F_0p01_LO) ? __frcp_rn(z4.w) : 0.0f;
+            *reinterpret_cast<float4 *>(d.invd + po) = make_float4(iv[0], iv[1], iv[2], iv[3]);
+        }
+        else
+        {
+            const float4 i4 = *reinterpret_cast<const float4 *>(d.invd + po);
+            iv[0] = i4.x, iv[1] = i4.y, iv[2] = i4.z, iv[3] = i4.w;
+            const uchar4 c4 = *reinterpret_cast<const uchar4 *>(d.code + po);
+            oc[0] = c4.x, oc[1] = c4.y, oc[2] = c4.z, oc[3] = c4.w;
+        }
+        const float gi[4] = {(float)g4.x, (float)g4.y, (float)g4.z, (float)g4.w};
+        const int bx = x4 >> 3, by = y >> 3, rx0 = x4 & 7, ry = y & 7;
         const int xa = (rx0 == 0) ? bx - 1 : bx, xb = xa + 1;
-        const int ya = (ry0 < 4) ? by - 1 : by, yb = ya + 1;
-        const bool vxa = xa >= 0 && xa < spw, vxb = xb >= 0 && xb < spw;
-        const bool vya = ya >= 0 && ya < d.sph, vyb = yb >= 0 && yb < d.sph;
-        sidx0 = ya * spw + xa;
+        const int ya = (ry < 4) ? by - 1 : by, yb = ya + 1;
+        const bool vxa = xa >= 0 && xa < d.spw, vxb = xb >= 0 && xb < d.spw;
+        const bool vya = ya >= 0 && ya < d.sph, vyb = (ry != 4) && yb >= 0 && yb < d.sph;
+        sidx0 = ya * d.spw + xa;
+        // candidate c = 2*ix + iy  -> (xa,ya) (xa,yb) (xb,ya) (xb,yb): dx outer, dy inner (:413-414)
+        // fast-path operands, shared by the thread's 4 pixels.  Coordinates are pre-scaled by 1/4 (exact), so that
+        // dist/16 (:374) is ax'^2 + ay'^2; an invalid candidate sits 1e18 away: its cost (~1e36, finite) is never the minimum
+        // and the filter arithmetic stays NaN-free.  When the pixel at x%8 == 4 sees only its own seed column (:418-420)
+        // the candidates of column xb get the same treatment for that pixel only (sxq0).
+        float sxq[4], sxq0[4], ayy[4], sI[4], shi[4], slo[4];
+        bool sv[4];
+        bool allmd = true, allmd0 = true; // every valid candidate seed has mean_depth > 0 (:378), over 4 / over column xa only
+        const float fyq = (float)y * 0.25f;
 #pragma unroll
         for (int c = 0; c < 4; c++)
         {
-            ex[c] = ((c >> 1) ? vxb : vxa) && ((c & 1) ? vyb : vya);
-            const int li = ex[c] ? sidx0 + (c & 1) * spw + (c >> 1) : 0; // missing candidates read seed 0 and are pushed away
+            sv[c] = ((c >> 1) ? vxb : vxa) && ((c & 1) ? vyb : vya);
+            const int li = sv[c] ? sidx0 + (c & 1) * d.spw + (c >> 1) : 0; // invalid candidates read seed 0 and are pushed away below
             const float4 s4 = d.seed[so + li];
             const float2 hl = d.seed_hl[so + li];
-            sxq[c] = ex[c] ? s4.x * 0.25f : 1e18f;
-            syq[c] = s4.y * 0.25f;
+            sxq[c] = sv[c] ? s4.x * 0.25f : 1e18f;
+            sxq0[c] = ((c >> 1) && rx0 == 4) ? 1e18f : sxq[c];
+            const float ay = s4.y * 0.25f - fyq;
+            ayy[c] = ay * ay;
             sI[c] = s4.z, shi[c] = hl.x, slo[c] = hl.y;
-            mdp[c] = s4.w > 0.f || !ex[c];
+            const bool mdpos = s4.w > 0.f || !sv[c];
+            allmd &= mdpos;
+            if (!(c >> 1)) allmd0 &= mdpos;
         }
-    }
-    auto seed_of = [&](int c) { return c == DSM_CODE_NONE ? 0 : sidx0 + (c & 1) * spw + (c >> 1); }; // a pixel without winner is labelled 0
-
-#pragma unroll 1
-    for (int r = 0; r < 2; r++)
-    {
-        const int y = y0 + r;
-        const bool act = active && y < d.H;
-        int2 ent[4];
-        int nent = 0;
-        if (act)
+        if (rx0 != 4) allmd0 = allmd;
+        unsigned uncertain = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
         {
-            const bool rk = (y & 7) == 4; // this row sees only its own seed row: candidates of row yb are out
-            const size_t po = fo + (size_t)y * d.Wp + x4;
-            int wc[4];                // winner of every pixel as a candidate code
-            int oc[4] = {0, 0, 0, 0}; // current label as a candidate code
-            const uchar4 g4 = *reinterpret_cast<const uchar4 *>(d.gray + po);
-            float iv[4];
-            if (FIRST)
-            { // (:404-405) my_inv = (float)(1.0 / (double)depth) for depth > 0.01: 53 >= 2*24+2 bits, so the double rounding is
-              // innocuous and the correctly rounded float reciprocal is the same value (-ftz=false: subnormals included)
-                const float4 z4 = *reinterpret_cast<const float4 *>(d.depth + po);
-                iv[0] = (z4.x > F_0p01_LO) ? __frcp_rn(z4.x) : 0.0f;
-                iv[1] = (z4.y > F_0p01_LO) ? __frcp_rn(z4.y) : 0.0f;
-                iv[2] = (z4.z > F_0p01_LO) ? __frcp_rn(z4.z) : 0.0f;
-                iv[3] = (z4.w > F_0p01_LO) ? __frcp_rn(z4.w) : 0.0f;
-                *reinterpret_cast<float4 *>(d.invd + po) = make_float4(iv[0], iv[1], iv[2], iv[3]);
-            }
-            else
-            {
-                const float4 i4 = *reinterpret_cast<const float4 *>(d.invd + po);
-                iv[0] = i4.x, iv[1] = i4.y, iv[2] = i4.z, iv[3] = i4.w;
-                const uchar4 c4 = *reinterpret_cast<const uchar4 *>(d.code + po);
-                oc[0] = c4.x, oc[1] = c4.y, oc[2] = c4.z, oc[3] = c4.w;
-            }
-            const float gi[4] = {(float)g4.x, (float)g4.y, (float)g4.z, (float)g4.w};
-            float ayy[4];
-            bool allmd = true, allmd0 = true; // every candidate this row / this row's x%8==4 pixel sees has mean_depth > 0 (:378)
-            const float fyq = (float)y * 0.25f;
+            const float fxq = (float)(x4 + i) * 0.25f;
+            const float pi = gi[i], pv = iv[i];
+            // all_has_depth (:443): every valid candidate has a depth and so has the pixel -> costs with the depth term, else without
+            const float w = (pv > 0.f && (i == 0 ? allmd0 : allmd)) ? 400.f : 0.f;
+            float cost[4];
 #pragma unroll
             for (int c = 0; c < 4; c++)
             {
-                const bool out = (c & 1) && rk;
-                const float ay = syq[c] - fyq;
-                ayy[c] = out ? 1e36f : ay * ay;
-                allmd &= mdp[c] || out;
-                allmd0 &= mdp[c] || out || ((c >> 1) && rx0 == 4);
+                const float ax = (i == 0 ? sxq0[c] : sxq[c]) - fxq;
+                const float n = fmaf(ax, ax, ayy[c]);
+                const float idf = sI[c] - pi;
+                const float cn = fmaf(idf * idf, 0.01f, n);
+                const float t = (shi[c] - pv) + slo[c];
+                cost[c] = fmaf(t * t, w, cn);
             }
-            unsigned uncertain = 0;
+            const float lo01 = fminf(cost[0], cost[1]), hi01 = fmaxf(cost[0], cost[1]);
+            const float lo23 = fminf(cost[2], cost[3]), hi23 = fmaxf(cost[2], cost[3]);
+            const float m1 = fminf(lo01, lo23);
+            const float m2 = fminf(fminf(fmaxf(lo01, lo23), fminf(hi01, hi23)), A_BIG); // second smallest, kept finite
+            wc[i] = cost[0] == m1 ? 0 : (cost[1] == m1 ? 1 : (cost[2] == m1 ? 2 : 3));
+            const bool certain = (m2 - m1 > A_EPS * (m2 + m1) + A_ALPHA) && (m1 < 9e5f);
+            if (!certain) uncertain |= 1u << i;
+        }
+        if (uncertain)
+        { // exact path: the reference's expression, candidate order and strict '<' (first wins).  Each lane walks its OWN
+          // flagged pixels, so a warp pays max-per-lane (usually one) exact evaluations, not one per pixel slot.
+            SeedC sc[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int c = 0; c < 4; c++)
             {
-                const float fxq = (float)(x4 + i) * 0.25f;
-                const float pi = gi[i], pv = iv[i];
-                // all_has_depth (:443): every visible candidate has a depth and so has the pixel -> costs with the depth term, else without
-                const float w = (pv > 0.f && (i == 0 ? allmd0 : allmd)) ? 400.f : 0.f;
-                float cost[4];
+                const int li = sv[c] ? sidx0 + (c & 1) * d.spw + (c >> 1) : 0;
+                const float4 s4 = d.seed[so + li];
+                sc[c].x = s4.x, sc[c].y = s4.y, sc[c].I = s4.z, sc[c].md = s4.w;
+                sc[c].inv = d.inv_md[so + li]; // 1.0 / (double)mean_depth, only consumed when mean_depth > 0 (:378)
+            }
+            const float fy = (float)y;
+            while (uncertain)
+            {
+                const int i = __ffs(uncertain) - 1;
+                uncertain &= uncertain - 1;
+                const float fx = (float)(x4 + i);
+                const float my_i = pick4(gi[0], gi[1], gi[2], gi[3], i);
+                const float my_inv = pick4(iv[0], iv[1], iv[2], iv[3], i);
+                const double my_inv_d = (double)my_inv;
+                float min_d = 1e6f, min_nd = 1e6f;
+                int idx_d = DSM_CODE_NONE, idx_nd = DSM_CODE_NONE; // the reference's -1 (:409-411)
+                bool all_has_depth = true;
 #pragma unroll
                 for (int c = 0; c < 4; c++)
                 {
-                    const float sx = (i == 0 && (c >> 1) && rx0 == 4) ? 1e18f : sxq[c];
-                    const float ax = sx - fxq;
-                    const float n = fmaf(ax, ax, ayy[c]);
-                    const float idf = sI[c] - pi;
-                    const float cn = fmaf(idf * idf, 0.01f, n);
-                    const float t = (shi[c] - pv) + slo[c];
-                    cost[c] = fmaf(t * t, w, cn);
+                    const bool valid = sv[c] && ((c >> 1) ? !(rx0 == 4 && i == 0) : true);
+                    float cnd, cdd;
+                    const bool has = calc_cost(sc[c], my_i, my_inv, my_inv_d, fx, fy, cnd, cdd);
+                    cdd = valid ? cdd : __int_as_float(0x7f800000);
+                    cnd = valid ? cnd : __int_as_float(0x7f800000);
+                    all_has_depth &= has || !valid;
+                    const bool bd = cdd < min_d, bn = cnd < min_nd;
+                    min_d = bd ? cdd : min_d;
+                    idx_d = bd ? c : idx_d;
+                    min_nd = bn ? cnd : min_nd;
+                    idx_nd = bn ? c : idx_nd;
                 }
-                const float lo01 = fminf(cost[0], cost[1]), hi01 = fmaxf(cost[0], cost[1]);
-                const float lo23 = fminf(cost[2], cost[3]), hi23 = fmaxf(cost[2], cost[3]);
-                const float m1 = fminf(lo01, lo23);
-                const float m2 = fminf(fminf(fmaxf(lo01, lo23), fminf(hi01, hi23)), A_BIG); // second smallest, kept finite
-                wc[i] = cost[0] == m1 ? 0 : (cost[1] == m1 ? 1 : (cost[2] == m1 ? 2 : 3));
-                const bool certain = (m2 - m1 > A_EPS * (m2 + m1) + A_ALPHA) && (m1 < 9e5f);
-                if (!certain) uncertain |= 1u << i;
+                const int wv = all_has_depth ? idx_d : idx_nd;
+                wc[0] = i == 0 ? wv : wc[0];
+                wc[1] = i == 1 ? wv : wc[1];
+                wc[2] = i == 2 ? wv : wc[2];
+                wc[3] = i == 3 ? wv : wc[3];
             }
-            if (uncertain)
-            { // exact path (rare, out of line so that its fp64 temporaries do not count against the fast path's registers)
-                const unsigned exm = (ex[0] ? 1u : 0u) | (ex[1] ? 2u : 0u) | (ex[2] ? 4u : 0u) | (ex[3] ? 8u : 0u);
-                const unsigned w = assign_exact(d, so, sidx0, exm, rk, rx0, x4, y, uncertain, make_float4(gi[0], gi[1], gi[2], gi[3]),
-                                                make_float4(iv[0], iv[1], iv[2], iv[3]), wc[0] | (wc[1] << 8) | (wc[2] << 16) | (wc[3] << 24));
-                wc[0] = w & 255, wc[1] = (w >> 8) & 255, wc[2] = (w >> 16) & 255, wc[3] = w >> 24;
-            }
+        }
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (x4 + i >= d.W) wc[i] = DSM_CODE_NONE;
+        for (int i = 0; i < 4; i++)
+            if (x4 + i >= d.W) wc[i] = DSM_CODE_NONE;
+    }
+    const int spw = d.spw;
+    auto seed_of = [&](int c) { return c == DSM_CODE_NONE ? 0 : sidx0 + (c & 1) * spw + (c >> 1); }; // a pixel without winner is labelled 0
 
-            if (FIRST)
-            { // every label is 0 and seed 0 is unstable: everything commits (:400)
-                *reinterpret_cast<int4 *>(d.labels + po) = make_int4(seed_of(wc[0]), seed_of(wc[1]), seed_of(wc[2]), seed_of(wc[3]));
-                *reinterpret_cast<uchar4 *>(d.code + po) = make_uchar4(wc[0], wc[1], wc[2], wc[3]);
+    if (FIRST)
+    { // every label is 0 and seed 0 is unstable: everything commits (:400)
+        if (active)
+        {
+            const size_t po = fo + (size_t)y * d.Wp + x4;
+            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(seed_of(wc[0]), seed_of(wc[1]), seed_of(wc[2]), seed_of(wc[3]));
+            *reinterpret_cast<uchar4 *>(d.code + po) = make_uchar4(wc[0], wc[1], wc[2], wc[3]);
+        }
+        return;
+    }
+
+    // ---- iterations 2..: commit / defer.  A deferred pixel whose winner IS its current label is dropped:
+    // if the raster scan evaluates it (t[label] < idx) the label does not change and the stamp t[winner] = t[label] is
+    // already below idx, so it can change nothing -- the relaxation only ever needs the pixels that would switch seeds.
+    int2 ent[4];
+    int nent = 0;
+    if (active)
+    {
+        bool changed = false;
+        const int32_t *ts = d.tstable + so;
+        // Only a pixel whose winner differs from its label has anything to do: with winner == label an evaluated pixel
+        // keeps its label and its stamp update min(t[label], idx) is a no-op (the owner is unstable, t[label] < 0 <= idx),
+        // and a pixel of a stable owner would be deferred only to be dropped again (see above).  So the stamps are read
+        // for the few switching pixels only.
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            if (x4 + i >= d.W || wc[i] == DSM_CODE_NONE || wc[i] == oc[i]) continue;
+            const int pidx = y * d.Wp + x4 + i;
+            const int win = seed_of(wc[i]);
+            if (ts[seed_of(oc[i])] < 0)
+            { // owner unstable since the start of the pass: the reference evaluates this pixel
+                oc[i] = wc[i];
+                changed = true;
+                if (ts[win] > pidx) atomicMin(&d.tstable[so + win], pidx); // stable = false at time pidx (:445/:450)
             }
             else
             {
-                // ---- iterations 2..: commit / defer.  Only a pixel whose winner differs from its label has
-                // anything to do: with winner == label an evaluated pixel keeps its label and its stamp update
-                // min(t[label], idx) is a no-op (the owner is unstable, t[label] < 0 <= idx), and a pixel of a stable owner
-                // would only matter to the relaxation if it switched seeds.  So the stamps are read for the few switching
-                // pixels only.
-                bool changed = false;
-                const int32_t *ts = d.tstable + so;
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                {
-                    if (x4 + i >= d.W || wc[i] == DSM_CODE_NONE || wc[i] == oc[i]) continue;
-                    const int pidx = y * d.Wp + x4 + i;
-                    const int win = seed_of(wc[i]);
-                    if (ts[seed_of(oc[i])] < 0)
-                    { // owner unstable since the start of the pass: the reference evaluates this pixel
-                        oc[i] = wc[i];
-                        changed = true;
-                        if (ts[win] > pidx) atomicMin(&d.tstable[so + win], pidx); // stable = false at time pidx (:445/:450)
-                    }
-                    else
-                    {
-                        ent[nent++] = make_int2(pidx, win | (wc[i] << 28));
-                    }
-                }
-                if (changed)
-                {
-                    *reinterpret_cast<int4 *>(d.labels + po) = make_int4(seed_of(oc[0]), seed_of(oc[1]), seed_of(oc[2]), seed_of(oc[3]));
-                    *reinterpret_cast<uchar4 *>(d.code + po) = make_uchar4(oc[0], oc[1], oc[2], oc[3]);
-                }
+                ent[nent++] = make_int2(pidx, win | (wc[i] << 28));
             }
         }
-        // warp-aggregated append of the deferred pixels (rare: most warps have none)
-        if (!FIRST && __any_sync(FULL, nent > 0))
+        if (changed)
         {
-            int total;
-            const int excl = warp_excl_scan(nent, lane, total);
-            int base = 0;
-            if (lane == 31) base = atomicAdd(&d.nlist[b], total);
-            base = __shfl_sync(FULL, base, 31);
-            int2 *list = d.list + fo;
-            for (int j = 0; j < nent; j++) list[base + excl + j] = ent[j];
+            const size_t po = fo + (size_t)y * d.Wp + x4;
+            *reinterpret_cast<int4 *>(d.labels + po) = make_int4(seed_of(oc[0]), seed_of(oc[1]), seed_of(oc[2]), seed_of(oc[3]));
+            *reinterpret_cast<uchar4 *>(d.code + po) = make_uchar4(oc[0], oc[1], oc[2], oc[3]);
         }
     }
-    if (FIRST) return;
-
+    // warp-aggregated append of the deferred pixels (rare: most warps have none)
+    if (__any_sync(FULL, nent > 0))
+    {
+        int total;
+        const int excl = warp_excl_scan(nent, lane, total);
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&d.nlist[b], total);
+        base = __shfl_sync(FULL, base, 31);
+        int2 *list = d.list + fo;
+        for (int j = 0; j < nent; j++) list[base + excl + j] = ent[j];
+    }
     // frame-completion ticket: the CTA that takes the last ticket of frame b sees every other CTA's labels, list
     // entries and time stamps (release: fence before the ticket; acquire: fence after it) and resolves the frame
     const int tid = threadIdx.y * 64 + threadIdx.x;
@@ -1370,7 +1347,7 @@ int dsm_tile_setup()
 void dsm_launch_assign2(const DsmDev &d, int nb, bool first, cudaStream_t s)
 {
     dim3 block(64, 4);
-    dim3 grid((d.W + 255) / 256, (d.H + 7) / 8, nb); // 4 x 2 pixels per thread
+    dim3 grid((d.W + 255) / 256, (d.H + 3) / 4, nb);
     if (first)
         pdl_launch(k_assign2<true>, grid, block, 0, s, d);
     else
