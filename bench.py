@@ -495,6 +495,27 @@ def run_cfg5(local_rank, stream):
     return res
 
 
+def gpu_numa_cpus(local_rank):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when the box does not say.  Used only while the pinned
+    host buffers of the e2e leg are allocated: pinned pages land on the allocating thread's node, and at N=8 eight
+    55 GB/s copy streams should not all read from one socket's DRAM."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else (None, None)
+    except Exception:
+        return None, None
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -525,7 +546,12 @@ def run_gpu_arm(args, rank, world, local_rank):
                               np.stack([f[2] for f in prev]), empty, zofs)
     offsets = np.concatenate([[0], np.cumsum([len(p) for p in pools])]).astype(np.int32)
     npool = int(offsets[-1])
-    # pinned host buffers for the e2e path
+    # pinned host buffers for the e2e path, allocated on the GPU's NUMA node
+    numa_node, numa_cpus = gpu_numa_cpus(local_rank)
+    aff0 = os.sched_getaffinity(0)
+    if numa_cpus:
+        os.sched_setaffinity(0, numa_cpus)
+
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
@@ -539,6 +565,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     ring = [pinned(pool_np.view(np.uint8) if npool else np.zeros(44, np.uint8)) for _ in range(min(args.steps + 2, 48))]
     out_bufs = [(pinned(np.zeros(B * S * 44, np.uint8))[1], pinned(np.zeros(B, np.int32))[1]) for _ in range(2)]
     h_new, h_cnt = out_bufs[0]
+    if numa_cpus:
+        os.sched_setaffinity(0, aff0)  # only the allocations above were bound (the CPU baseline leg uses every core)
     refs = np.zeros(B, np.int32)
     L = ctx.lib
 
@@ -571,17 +599,23 @@ def run_gpu_arm(args, rank, world, local_rank):
     ctx.batch_upload(refs, h_gray, h_depth, h_pose, pool_np, offsets)
     ctx2.batch_upload(refs, h_gray, h_depth, h_pose, pool_np, offsets)
     res_ctx = [ctx, ctx2] if (world > 1 or args.contexts == 2) else [ctx]
+    ctx3 = None
     if world > 1:
         # Multi-GPU step = this rank's kernels + ONE gather of its surfel deltas onto rank 0 through the C ABI
         # (dsm_gather_deltas: device-side packing of the valid records, ncclAllGather of the byte counts, grouped
-        # ncclSend/ncclRecv).  The gather needs the batch's new-surfel counts on the host, i.e. it waits for the batch's
-        # kernels; the other context keeps the GPU busy meanwhile: step k's kernels are enqueued first, then the
-        # gather of step k-1 is issued.  Each context has its own communicator (ids broadcast over torch.distributed).
-        ids = [capi.comm_unique_id(), capi.comm_unique_id()] if rank == 0 else [None, None]
+        # ncclSend/ncclRecv).  The gather needs the batch's new-surfel counts on the host, i.e. it waits for that batch's
+        # kernels.  With a third context in the rotation the gather issued at step k is the one of step k-2, whose kernels
+        # have finished while steps k-1 and k overlap on the GPU exactly as they do at N=1: the host never waits for running
+        # kernels.  Each context has its own communicator (ids broadcast over torch.distributed).
+        ctx3 = capi.Context(cam, max_batch=B, max_local_surfels=B * S + 64, device=local_rank)
+        ctx3.batch_upload(refs, h_gray, h_depth, h_pose, pool_np, offsets)
+        res_ctx = [ctx, ctx2, ctx3]
+        ids = [capi.comm_unique_id() for _ in res_ctx] if rank == 0 else [None for _ in res_ctx]
         dist.broadcast_object_list(ids, src=0)
         for c, uid in zip(res_ctx, ids):
             c.comm_init(uid, rank, world)
     step_no = [0]
+    GATHER_LAG = 2
 
     def step():
         k = step_no[0]
@@ -589,13 +623,13 @@ def run_gpu_arm(args, rank, world, local_rank):
         c = res_ctx[k % len(res_ctx)]
         c.batch_restore_pool()
         c.batch_run()
-        if world > 1 and k > 0:
-            res_ctx[(k - 1) % len(res_ctx)].gather_deltas(0)
+        if world > 1 and k >= GATHER_LAG:
+            res_ctx[(k - GATHER_LAG) % len(res_ctx)].gather_deltas(0)
 
     def drain():
         if world > 1:
-            if step_no[0] > 0:
-                res_ctx[(step_no[0] - 1) % len(res_ctx)].gather_deltas(0)
+            for k in range(max(step_no[0] - GATHER_LAG, 0), step_no[0]):  # the steps whose gather has not been issued yet
+                res_ctx[k % len(res_ctx)].gather_deltas(0)
             for c in res_ctx:
                 c.gather_wait()
             step_no[0] = 0
@@ -726,8 +760,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "parallelism": f"frames sharded {B}/GPU, no data-path collective; one gather of the valid surfel deltas per step through the C ABI (dsm_gather_deltas: ncclAllGather of counts + grouped ncclSend/ncclRecv)" if world > 1 else "single GPU"},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps, "api": "dsm_fuse_batch_async + dsm_batch_wait on two alternating contexts (C ABI, pinned host buffers)",
-                    "pinned_h2d_gbs": h2d_gbs},
-            "gpu_launches": launches_per_step * args.steps,
+                    "pinned_h2d_gbs": h2d_gbs, "pinned_numa_node": numa_node},
+            "gpu_launches": launches_per_step * args.sub_batches * args.steps,  # every sub-batch runs the whole launch sequence on its frames
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "kernels": {k: dom_launches_per_step[k] for k in dom_members},
                          "achieved": alg / (fam_ms[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (fam_ms[dom] * 1e-3) / 1e9 / peak,
@@ -760,6 +794,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                                     "instances_tried_frames_per_s": arm["calibration_frames_per_s"]}
         print(json.dumps(line), flush=True)
     ctx2.close()
+    if ctx3 is not None:
+        ctx3.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -134,7 +134,10 @@ __device__ __forceinline__ bool stage_in(float *sm, const float *g, int cnt, dsm
             cuda::device::memcpy_async_tx(sm, g, cuda::aligned_size_t<16>(bytes), *bar);
             (void)cuda::device::barrier_arrive_tx(*bar, 1, bytes);
         }
-        while (!cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(*bar), 0)) {}
+        // bounded wait: a bulk copy that never completes (a bad pointer would fault first) traps instead of hanging the GPU
+        unsigned spin = 0;
+        while (!cuda::ptx::mbarrier_try_wait_parity(cuda::device::barrier_native_handle(*bar), 0))
+            if (++spin > (1u << 22)) __trap();
     }
     else
     {

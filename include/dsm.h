@@ -208,8 +208,9 @@ int dsm_fuse_frame_resident(dsm_ctx *ctx, int reference_frame_index,
  * those of n calls of dsm_fuse_frame_resident (same kernels, same order on the pool), but the pose- and pool-independent stages (superpixels, normals, plane fit) of all n frames run as one
  * batch; only fuse / initialise / compaction run frame by frame.  Trades
  * n-1 frames of latency for throughput (offline sequences, or a node that lags behind its camera).  n <= max_batch;
- * with 2n <= max_batch the copy of one run overlaps the kernels of the previous one.  n_new (optional, [n]) = new
- * surfels per frame; passing it synchronises. */
+ * with 2n <= max_batch consecutive runs use alternate halves of the frame slots: the copy and the batched stages of one
+ * run overlap the frame-by-frame stages of the previous one.  n_new (optional, [n]) = new surfels per frame; passing it
+ * synchronises. */
 int dsm_fuse_stream_resident(dsm_ctx *ctx, int n_frames, const int32_t *reference_frame_index,
                              const uint8_t *gray, const float *depth, const float *poses_colmajor, int32_t *n_new);
 int dsm_pool_transform(dsm_ctx *ctx, const float W_colmajor[16]);

@@ -143,6 +143,37 @@ def test_batch_matches_per_frame(capi):
     ctx.close()
 
 
+def test_concurrent_sub_batches_do_not_change_results(capi):
+    """dsm_set_concurrency: a resident batch as 1, 2, 3 or 4 groups of frames on concurrent streams gives byte-identical
+    outputs (frames are independent); two frames of the batch are also checked against the reference."""
+    cam = synth.Camera(132, 100, 60.0, 60.0, 65.5, 49.5, 0.5, 30.0)
+    B = 9
+    frames = [synth.make_frame(cam, 300 + i, synth.pose_stream(i)) for i in range(B)]
+    g, d = np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
+    p = np.stack([synth.pose_stream(i) for i in range(B)])
+    ctx = capi.Context(cam, max_batch=B, max_local_surfels=8192)
+    _, pools = ctx.fuse_batch([0] * B, g, d, p, np.zeros(0, SURFEL_DTYPE), np.zeros(B + 1, np.int32))
+    ofs = np.concatenate([[0], np.cumsum([len(x) for x in pools])]).astype(np.int32)
+    p2 = np.stack([synth.pose_stream(i + 1) for i in range(B)])
+    outs = []
+    for parts in (1, 2, 3, 4, 2):
+        ctx.set_concurrency(parts)
+        ctx.batch_upload([1] * B, g, d, p2, np.concatenate(pools), ofs)
+        ctx.batch_run()
+        local, news = ctx.batch_download()
+        outs.append((local.tobytes(), [n.tobytes() for n in news], [ctx.labels(b).tobytes() for b in (0, B - 1)]))
+    assert all(o == outs[0] for o in outs[1:])
+    with pytest.raises(Exception):
+        ctx.set_concurrency(5)
+    orc = oracle_for(cam)
+    for b in (0, B - 1):
+        lo, no = orc.fuse(1, g[b], d[b], p2[b], pools[b])
+        assert (orc.labels() == ctx.labels(b)).all()
+        check_surfels(local[ofs[b]:ofs[b + 1]], lo, f"frame {b} local")
+        check_surfels(news[b], no, f"frame {b} new")
+    ctx.close()
+
+
 def test_pitched_input_and_errors(capi):
     cam = synth.VGA
     gray, depth = synth.make_frame(cam, 7)

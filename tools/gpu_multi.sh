@@ -14,6 +14,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --m
     bench.py --gpus "$n" --steps 20 --warmup 5 > "$out/bench_n$n.json" 2> "$out/bench_n$n.err"
 tail -c 1800 "$out/bench_n$n.json" | tee -a "$out/summary.txt"
 tail -5 "$out/bench_n$n.err"
+[ "${REFARM:-0}" = 1 ] || exit 0
 echo "== reference arm under torchrun (rank 0 alone works)" | tee -a "$out/summary.txt"
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29518 \
     bench.py --impl reference --gpus "$n" --steps 2 --warmup 1 > "$out/ref_n$n.json" 2> "$out/ref_n$n.err"
