@@ -280,11 +280,16 @@ int dsm_inactive_size(dsm_ctx *ctx, int *n_surfels, int *n_segments);
  *   dsm_gather_deltas    collective, after dsm_batch_run: packs ONLY the valid records of this rank's batch
  *                          int32 'DSMD', n_frames, n_new_total, n_pool_total, n_new[n_frames], pool_ofs[n_frames+1], pad to 16 B,
  *                          dsm_surfel_t new[n_new_total] (frame by frame, seed-index order), dsm_surfel_t pool[n_pool_total]
- *                        and moves it to `root` (ncclAllGather of the byte counts + one grouped ncclSend/ncclRecv) on a side
- *                        stream.  Waits for the batch's kernels (the counts must reach the host), returns before the
- *                        transfer has finished; the next dsm_batch_run may be enqueued at once.
- *   dsm_gather_wait      waits for the transfer
- *   dsm_gathered_*       root only: the payload of every rank, on the device (zero copy) or copied to host memory */
+ *                        and moves it to `root` on a side stream.  Ranks of one node write their payload straight into
+ *                        their slot of the root's receive buffer over NVLink peer memory (CUDA IPC mapping made at the first
+ *                        gather; counts stay on the device, nothing waits on the host, exactly the valid bytes travel);
+ *                        without a peer mapping (or with DSM_GATHER_NCCL=1) the counts go to the host and the payloads move
+ *                        with ncclAllGather (sizes) + one grouped ncclSend/ncclRecv.  Collective: every rank of the
+ *                        communicator calls it with the same root, in the same order.  Returns before the transfer has
+ *                        finished; the next dsm_batch_run may be enqueued at once.  A new gather overwrites the previous one.
+ *   dsm_gather_wait      root: waits until every rank's payload has arrived; other ranks: until their own has left
+ *   dsm_gathered_*       root only: the payload of every rank, on the device (zero copy; payload r occupies
+ *                        [rank_offsets[r], rank_offsets[r] + dsm_gathered_rank_bytes(r))) or copied to host memory */
 #define DSM_COMM_ID_BYTES 128
 int dsm_comm_unique_id(void *id_out128);
 int dsm_comm_init(dsm_ctx *ctx, const void *id128, int rank, int nranks);

@@ -43,8 +43,10 @@ def test_single_rank_gather_equals_batch_download():
     ctx.close()
 
 
-def _worker(rank, world, uid_q, res_q):
+def _worker(rank, world, uid_q, res_q, transport="peer"):
     # no torch in these processes: the library then loads the system NCCL, as in a plain C++ host process
+    if transport == "nccl":
+        os.environ["DSM_GATHER_NCCL"] = "1"
     from densesurfelmapping_b200 import capi
     if rank == 0:
         uid = capi.comm_unique_id()
@@ -54,7 +56,8 @@ def _worker(rank, world, uid_q, res_q):
         uid = uid_q.get(timeout=60)
     ctx, want = _run_batch(capi, rank, rank)
     ctx.comm_init(uid, rank, world)
-    ctx.gather_deltas(0)
+    for _ in range(3):  # three gathers in a row: the slots / staging buffers are reused, the credits advance
+        ctx.gather_deltas(0)
     ctx.gather_wait()
     if rank == 0:
         res_q.put(("root", [ctx.gathered_payload(r).tobytes() for r in range(world)]))
@@ -70,7 +73,9 @@ def _gpu_count():
         return 0
 
 
-def test_two_rank_gather_over_nccl():
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_two_rank_gather(transport):
+    """peer: one-sided writes into the root's CUDA-IPC-mapped slots over NVLink; nccl: counts + grouped send/recv."""
     # (torch is deliberately not imported here: this process may already hold the system NCCL from the single-rank test,
     # and a PyTorch that loads after it would bind to that one instead of its own -- INTEGRATION.md, "NCCL in a PyTorch process")
     if _gpu_count() < 2:
@@ -78,7 +83,7 @@ def test_two_rank_gather_over_nccl():
     import multiprocessing as mp
     mpc = mp.get_context("spawn")
     uid_q, res_q = mpc.Queue(), mpc.Queue()
-    procs = [mpc.Process(target=_worker, args=(r, 2, uid_q, res_q)) for r in range(2)]
+    procs = [mpc.Process(target=_worker, args=(r, 2, uid_q, res_q, transport)) for r in range(2)]
     [p.start() for p in procs]
     got = dict(res_q.get(timeout=180) for _ in range(3))
     [p.join(60) for p in procs]
