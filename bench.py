@@ -517,6 +517,10 @@ def gpu_numa_cpus(local_rank):
 
 
 def run_gpu_arm(args, rank, world, local_rank):
+    if args.contexts is None:
+        args.contexts = 3 if world > 1 else 2  # N>1: one more batch in flight covers the gather's pack kernels (measured at N=2: 0.901 vs 0.920 ms)
+    if world > 1 and args.contexts < 2:
+        args.contexts = 2
     import torch
     import torch.distributed as dist
     from densesurfelmapping_b200 import capi, synth
@@ -598,24 +602,25 @@ def run_gpu_arm(args, rank, world, local_rank):
     # runs them (the e2e leg below does the same through the host-buffer call).  `value` is the steady-state throughput.
     ctx.batch_upload(refs, h_gray, h_depth, h_pose, pool_np, offsets)
     ctx2.batch_upload(refs, h_gray, h_depth, h_pose, pool_np, offsets)
-    res_ctx = [ctx, ctx2] if (world > 1 or args.contexts == 2) else [ctx]
+    res_ctx = [ctx, ctx2] if args.contexts >= 2 else [ctx]
     ctx3 = None
-    if world > 1:
-        # Multi-GPU step = this rank's kernels + ONE gather of its surfel deltas onto rank 0 through the C ABI
-        # (dsm_gather_deltas: device-side packing of the valid records, ncclAllGather of the byte counts, grouped
-        # ncclSend/ncclRecv).  The gather needs the batch's new-surfel counts on the host, i.e. it waits for that batch's
-        # kernels.  With a third context in the rotation the gather issued at step k is the one of step k-2, whose kernels
-        # have finished while steps k-1 and k overlap on the GPU exactly as they do at N=1: the host never waits for running
-        # kernels.  Each context has its own communicator (ids broadcast over torch.distributed).
+    if args.contexts == 3:
         ctx3 = capi.Context(cam, max_batch=B, max_local_surfels=B * S + 64, device=local_rank)
         ctx3.batch_upload(refs, h_gray, h_depth, h_pose, pool_np, offsets)
         res_ctx = [ctx, ctx2, ctx3]
+    if world > 1:
+        # Multi-GPU step = this rank's kernels + ONE gather of its surfel deltas onto rank 0 through the C ABI
+        # (dsm_gather_deltas: a pack kernel that writes the valid records straight into the rank's slot of the root's
+        # receive buffer over NVLink peer memory; nothing waits on the host).  The gather of step k-1 is issued right after
+        # step k's kernels have been enqueued: it waits for its batch by event on a side stream while the other context's
+        # batch keeps the GPU busy, exactly as the two contexts overlap at N=1.  Each context has its own communicator
+        # (ids broadcast over torch.distributed).
         ids = [capi.comm_unique_id() for _ in res_ctx] if rank == 0 else [None for _ in res_ctx]
         dist.broadcast_object_list(ids, src=0)
         for c, uid in zip(res_ctx, ids):
             c.comm_init(uid, rank, world)
     step_no = [0]
-    GATHER_LAG = 2
+    GATHER_LAG = max(len(res_ctx) - 1, 1)
 
     def step():
         k = step_no[0]
@@ -757,7 +762,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                                    f"~{npool // B}-surfel local pool each (BASELINE configs[2]/[3]); superpixel+normal+plane-fit+fuse+initialise per frame",
                        "frames_per_gpu_per_step": B, "sub_batches": args.sub_batches, "resident_contexts": len(res_ctx), "pool_surfels_per_frame": npool // B, "new_surfels_per_frame": nnew_avg,
                        "l2": f"per-step working set {(B * (13.6 * P + 200 * S) + 88 * npool) / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                       "parallelism": f"frames sharded {B}/GPU, no data-path collective; one gather of the valid surfel deltas per step through the C ABI (dsm_gather_deltas: ncclAllGather of counts + grouped ncclSend/ncclRecv)" if world > 1 else "single GPU"},
+                       "parallelism": f"frames sharded {B}/GPU, no data-path collective; one gather of the valid surfel deltas per step through the C ABI (dsm_gather_deltas: pack kernel writing into the root's slots over NVLink peer memory)" if world > 1 else "single GPU"},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps, "api": "dsm_fuse_batch_async + dsm_batch_wait on two alternating contexts (C ABI, pinned host buffers)",
                     "pinned_h2d_gbs": h2d_gbs, "pinned_numa_node": numa_node},
@@ -808,7 +813,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--contexts", type=int, default=2, choices=(1, 2), help="resident contexts used alternately by the timed loop")
+    ap.add_argument("--contexts", type=int, default=None, choices=(1, 2, 3), help="resident contexts used in rotation by the timed loop (default: 2 at N=1, 3 at N>1)")
     ap.add_argument("--sub-batches", type=int, default=2, help="concurrent sub-batches of dsm_batch_run (C ABI default 2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
