@@ -672,7 +672,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     dom_mask = 0
     for k in dom_members:
         dom_mask |= 1 << names.index(k)
-    launches_per_step = int(sum(nl) // warm_on_ctx)
+    launches_per_step = int((sum(nl) + nl[names.index("slic_newton")]) // warm_on_ctx)  # the Newton stage is two launches (k_newton2 + k_newton_hard) under one event pair
     nnew_avg = float(np.mean([len(p) for p in ctx.batch_download()[1]]))
     dom_launches_per_step = {k: int(nl[names.index(k)]) // warm_on_ctx for k in dom_members}
     for c in res_ctx:
