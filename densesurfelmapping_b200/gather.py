@@ -3,8 +3,8 @@
 The path shards trivially: frame b of a batch goes to rank b mod G, every rank runs the whole per-frame pipeline on
 its own frames with NO data-path collective.  The only exchange is ONE gather of the per-rank surfel deltas (valid
 new surfels + updated local pools) onto a root rank at the end of a batch.  On GPUs that gather lives in the C ABI
-(`dsm_comm_init` / `dsm_gather_deltas`, csrc/dsm_comm.cu: device-side packing of the valid records, ncclAllGather of
-the byte counts, one grouped ncclSend/ncclRecv).  This module holds what the host side needs around it:
+(`dsm_comm_init` / `dsm_gather_deltas`, csrc/dsm_comm.cu: a pack kernel that writes the valid records straight into
+the root's memory over NVLink; NCCL send/recv where no peer mapping exists).  This module holds what the host side needs around it:
 
 * `shard_frames`                   the partitioning;
 * `pack_payload` / `unpack_payload` the wire format of one rank's payload, restated in numpy (the GPU tests demand
