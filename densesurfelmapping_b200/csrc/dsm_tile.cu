@@ -408,7 +408,7 @@ __device__ __forceinline__ int mask_index_sum(unsigned m)
 // 4-bit mask -> 0xff per set bit
 __device__ __forceinline__ unsigned nibble_to_bytes(unsigned n) { return (((n & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu; }
 
-__global__ void __launch_bounds__(256, 4) k_gather(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
+__global__ void __launch_bounds__(256, 6) k_gather(const __grid_constant__ DsmDev d, const __grid_constant__ DsmMaps mp)
 {
     pdl_enter();
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1342,6 +1342,10 @@ int dsm_tile_setup()
 {
     cudaError_t e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, GAT_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_plane_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
+    // shared memory is what limits the residency of the two tile kernels (36.6 KB / 33 KB per CTA): ask for the largest carve-out;
+    // k_gather then runs 6 CTAs per SM (measured 60.5 -> 55.5 us per launch; 5 CTAs for k_plane_gather gave nothing)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gather, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_plane_gather, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return e == cudaSuccess ? 0 : -1;
 }
 void dsm_launch_assign2(const DsmDev &d, int nb, bool first, cudaStream_t s)
