@@ -124,13 +124,13 @@ __device__ __forceinline__ float pick4(float a0, float a1, float a2, float a3, i
 #define DSM_CODE_NONE 4
 
 template <bool FIRST>
-__global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmDev d)
+__global__ void __launch_bounds__(128, 8) k_assign2(const __grid_constant__ DsmDev d)
 {
     pdl_enter();
     __shared__ int s_last;
     const int b = d.frame0 + blockIdx.z;
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y; // 128-thread CTAs (64 x 2): finer scheduling granularity than 256 (first pass 100.5 -> 95.2 us)
     const int lane = threadIdx.x & 31;
     const bool active = (x4 < d.W) && (y < d.H);
 
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256, 4) k_assign2(const __grid_constant__ DsmD
     if (s_last)
     {
         __threadfence();
-        relax_frame(d, b, tid, 256);
+        relax_frame(d, b, tid, 128);
     }
 }
 
@@ -1350,8 +1350,8 @@ int dsm_tile_setup()
 }
 void dsm_launch_assign2(const DsmDev &d, int nb, bool first, cudaStream_t s)
 {
-    dim3 block(64, 4);
-    dim3 grid((d.W + 255) / 256, (d.H + 3) / 4, nb);
+    dim3 block(64, 2);
+    dim3 grid((d.W + 255) / 256, (d.H + 1) / 2, nb);
     if (first)
         pdl_launch(k_assign2<true>, grid, block, 0, s, d);
     else
