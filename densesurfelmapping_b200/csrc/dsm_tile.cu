@@ -53,8 +53,12 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
 // -------------------------------------------------------------------------------------------
 // K1  slic_assign (filtered) — update_pixels_kernel (:389-453) + calculate_cost (:364-387)
 //
-// Geometry, candidate order and the raster-order `stable` semantics are those of k_assign (dsm_kernels.cu).
-// What changes is how the winner is found:
+// A thread owns 4 consecutive pixels of one row (CTA = 64 x 2 threads = 256 x 2 pixels); the at most 2 x 2 candidate
+// seeds are shared by the four pixels.  The reference walks the image in raster order and skips a pixel whose current
+// seed is `stable` at that moment (:400); `stable` flips during the walk (:445/:450).  Here every seed carries a time
+// stamp (tstable: -1 = unstable since the start of the pass, DSM_STABLE, or the raster index at which it became
+// unstable); pixels of seeds unstable from the start commit at once, the others are deferred to the frame's relaxation
+// (SURVEY.md H1).  How the winner of a pixel is found:
 //   fast path   costs in fp32 (FMA allowed).  Against the reference's value c = fl24(..fl53(..)) the fp32 value c~
 //               differs by at most 2^-20 (c~ + c) + 1e-12: squared distance and intensity term carry <= 3 roundings of
 //               2^-24 each on either side; the depth term uses 1/mean_depth as hi + lo (error 2^-48 / mean_depth,
@@ -66,7 +70,7 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
 //   exact path  everything else (ties -- common on synthetic constant images --, near ties, all costs >= 9e5):
 //               calc_cost, expression by expression as the reference.
 // The first pass also writes the inverse-depth plane the later passes read instead of the depth image.
-// The last CTA of a frame to finish (ticket counter) runs the raster-order `stable` relaxation of k_relax for
+// The last CTA of a frame to finish (ticket counter) runs the raster-order `stable` relaxation (relax_frame) for
 // that frame, so the pass needs no separate one-CTA-per-frame launch.
 // -------------------------------------------------------------------------------------------
 #define A_EPS 3.814697265625e-06f // 2^-18
@@ -1088,7 +1092,8 @@ __global__ void __launch_bounds__(256, 4) k_plane_gather(const __grid_constant__
 
 // -------------------------------------------------------------------------------------------
 // K4b  plane_solve — get_huber_norm (:104-188) + the projection (:884-912), one thread per seed.
-// Algebra as k_gauss_newton (dsm_kernels.cu): for the points whose residual is inside the Huber range,
+// Algebra: the reference rebuilds H = sum w q~ q~^T and J = sum w r q~ (q~ = (q, 1), theta = (n, b)) from the points in
+// every pass (:131-171).  For the points whose residual is inside the Huber range,
 // sum 2 r q~ = (sum 2 q~ q~^T) theta, so with H over ALL points, H_R = H - ho and J = H_R theta + jo, where ho / jo are
 // the sums over the out-of-range points only.  A pass over the points is needed only to find out which points are
 // out of range.  Let m = min_i | |r_i| - 0.4 | at the last evaluated parameters; a step (dn, db) changes every
